@@ -1,0 +1,108 @@
+"""
+oracle/ref_shim.py -- TEST INFRASTRUCTURE, NOT PRODUCT CODE. Build container only.
+
+Executes the reference's UNMODIFIED hot-path modules straight from
+``/root/reference/src/harmonica`` (read-only; nothing is copied) with the
+restated choclo kernels of ``oracle/choclo_numba.py`` injected as a fake
+``choclo`` package, and with inert stand-ins for the heavyweight imports the
+hot path never touches (verde, xarray, the pyvista helper).
+
+Used to (1) check oracle/choclo_port.c against the reference's own wrappers and
+jitted loops and (2) generate ``tests/golden/*.npz`` (oracle/make_golden.py).
+``/root/reference`` does not exist on the GPU box, so nothing that runs there
+imports this module; ``available()`` says whether it can be used.
+
+Modules loaded (reference file):
+  harmonica._forward.utils            src/harmonica/_forward/utils.py
+  harmonica._forward.prisms.utils     src/harmonica/_forward/prisms/utils.py
+  harmonica._forward.prisms.gravity   src/harmonica/_forward/prisms/gravity.py
+  harmonica._forward.prisms.magnetic  src/harmonica/_forward/prisms/magnetic.py
+  harmonica._forward.prisms.layer     src/harmonica/_forward/prisms/layer.py
+  harmonica._forward.point            src/harmonica/_forward/point.py
+  harmonica._equivalent_sources.utils src/harmonica/_equivalent_sources/utils.py
+"""
+
+import importlib
+import os
+import sys
+import types
+
+REFERENCE_SRC = "/root/reference/src/harmonica"
+
+
+def available():
+    return os.path.isdir(REFERENCE_SRC)
+
+
+def _pkg(name, path):
+    mod = types.ModuleType(name)
+    mod.__path__ = [path]
+    mod.__package__ = name
+    sys.modules[name] = mod
+    return mod
+
+
+_loaded = {}
+
+
+def load():
+    """Return a namespace with the reference's unmodified hot-path modules."""
+    if _loaded:
+        return types.SimpleNamespace(**_loaded)
+    if not available():
+        raise RuntimeError(f"{REFERENCE_SRC} is not mounted (GPU box?)")
+    if "harmonica" in sys.modules and not getattr(sys.modules["harmonica"], "__hb200_shim__", False):
+        raise RuntimeError("a real 'harmonica' is already imported; the shim is not needed")
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import choclo_numba
+
+    choclo_numba.install_fake_choclo()
+
+    hm = _pkg("harmonica", REFERENCE_SRC)
+    hm.__hb200_shim__ = True
+    _pkg("harmonica._forward", os.path.join(REFERENCE_SRC, "_forward"))
+    _pkg("harmonica._forward.prisms", os.path.join(REFERENCE_SRC, "_forward", "prisms"))
+    _pkg("harmonica._equivalent_sources", os.path.join(REFERENCE_SRC, "_equivalent_sources"))
+    # inert stand-ins for imports that layer.py performs at module load
+    # (layer.py:15-18); none of them is reached by _forward_gravity_prism_layer.
+    vis = types.ModuleType("harmonica.visualization")
+    vis.prism_to_pyvista = lambda *a, **k: (_ for _ in ()).throw(NotImplementedError())
+    sys.modules["harmonica.visualization"] = vis
+    if "verde" not in sys.modules:
+        try:
+            importlib.import_module("verde")
+        except ImportError:
+            sys.modules["verde"] = types.ModuleType("verde")
+    if "xarray" not in sys.modules:
+        try:
+            importlib.import_module("xarray")
+        except ImportError:
+            xr = types.ModuleType("xarray")
+            xr.register_dataset_accessor = lambda name: (lambda cls: cls)
+            sys.modules["xarray"] = xr
+
+    _loaded["utils"] = importlib.import_module("harmonica._forward.utils")
+    _loaded["prism_utils"] = importlib.import_module("harmonica._forward.prisms.utils")
+    _loaded["gravity"] = importlib.import_module("harmonica._forward.prisms.gravity")
+    _loaded["magnetic"] = importlib.import_module("harmonica._forward.prisms.magnetic")
+    _loaded["layer"] = importlib.import_module("harmonica._forward.prisms.layer")
+    _loaded["point"] = importlib.import_module("harmonica._forward.point")
+    _loaded["eqs_utils"] = importlib.import_module("harmonica._equivalent_sources.utils")
+    return types.SimpleNamespace(**_loaded)
+
+
+def greens_func_cartesian():
+    """The 3-line Green's function of cartesian.py:634-644, re-typed (that file
+    imports verde/bordado at module load and cannot be executed here); it calls
+    the reference's own ``distance_cartesian``."""
+    from numba import jit
+
+    ref = load()
+    distance_cartesian = ref.utils.distance_cartesian
+
+    @jit(nopython=True)
+    def greens(east, north, upward, point_east, point_north, point_upward):
+        distance = distance_cartesian((east, north, upward), (point_east, point_north, point_upward))
+        return 1 / distance
+
+    return greens
