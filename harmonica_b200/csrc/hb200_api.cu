@@ -1,0 +1,978 @@
+// hb200_api.cu -- C ABI of libharmonica_b200.so (see include/harmonica_b200.h).
+//
+// Host entry points: upload caller-owned numpy buffers, shard the work over the
+// selected B200s (by observers: disjoint output slices, no collective; or by
+// sources: per-device partial fields combined on device 0 by peer copies over
+// NVLink + a fixed-order reduce kernel), launch the kernels of
+// hb200_kernels.cuh, download. Device entry points (*_dev) launch the same
+// kernels on caller-owned device buffers, asynchronously on the caller's stream.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/harmonica_b200.h"
+#include "hb200_kernels.cuh"
+
+using namespace hb;
+
+namespace {
+
+thread_local std::string g_err;
+std::mutex g_mu;
+int g_variant = 1;
+
+int fail(int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(expr)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (expr);                                                          \
+        if (e_ != cudaSuccess)                                                            \
+            return fail(HB200_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                              \
+    } while (0)
+
+size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+struct Dev {
+    int id = -1;
+    int sms = 148;
+    cudaStream_t st = nullptr;
+    char* pool = nullptr;
+    size_t pool_bytes = 0;
+    size_t used = 0;
+    unsigned* d_flags = nullptr;
+
+    int ensure(size_t bytes)
+    {
+        used = 0;
+        if (bytes <= pool_bytes) return HB200_OK;
+        if (pool) cudaFree(pool);
+        pool = nullptr;
+        pool_bytes = 0;
+        size_t want = align_up(bytes + (bytes >> 3), 1 << 20);
+        cudaError_t e = cudaMalloc(&pool, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(HB200_ENOMEM, "cudaMalloc(%zu bytes) on device %d: %s", want, id,
+                        cudaGetErrorString(e));
+        }
+        pool_bytes = want;
+        return HB200_OK;
+    }
+    template <typename T> T* take(size_t count)
+    {
+        T* p = reinterpret_cast<T*>(pool + used);
+        used += align_up(count * sizeof(T));
+        return p;
+    }
+};
+
+std::vector<Dev> g_devs;
+
+int sm_count_current()
+{
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms > 0 ? sms : 148;
+}
+
+// ----------------------------------------------------------- launch helpers
+struct FieldSpec {
+    int fs;      // field set id (hb::F_* / FS_*)
+    int slot;    // first output slot
+    int nout;
+};
+
+double gravity_scale(int field)
+{
+    switch (field) {
+    case F_POT: return 1.0;
+    case F_E: case F_N: return 1e5;            // gravity.py:231-232
+    case F_U: return -1e5;                     // gravity.py:228-229 then :231-232
+    case F_EE: case F_NN: case F_UU: case F_EN: return 1e9;  // :234-235
+    default: return -1e9;                      // g_ez, g_nz: :228-229 then :234-235
+    }
+}
+
+// split a gravity field mask into fused passes
+std::vector<FieldSpec> plan_gravity(uint32_t mask)
+{
+    std::vector<FieldSpec> plan;
+    int slot_of[10], s = 0;
+    for (int f = 0; f < 10; f++) slot_of[f] = (mask >> f & 1u) ? s++ : -1;
+    uint32_t rest = mask;
+    if ((rest & HB200_MASK_TENSOR) == HB200_MASK_TENSOR) {
+        plan.push_back({FS_TENSOR6, slot_of[F_EE], 6});
+        rest &= ~HB200_MASK_TENSOR;
+    }
+    if ((rest & HB200_MASK_ACCEL) == HB200_MASK_ACCEL) {
+        plan.push_back({FS_ACC3, slot_of[F_E], 3});
+        rest &= ~HB200_MASK_ACCEL;
+    }
+    for (int f = 0; f < 10; f++)
+        if (rest >> f & 1u) plan.push_back({f, slot_of[f], 1});
+    return plan;
+}
+
+int popcount(uint32_t m) { return __builtin_popcount(m); }
+
+int choose_chunks(int64_t n_obs, int64_t n_src, int obs_per_block, int sms, int64_t* chunk_len)
+{
+    const int64_t obs_blocks = (n_obs + obs_per_block - 1) / obs_per_block;
+    const int64_t tiles = std::max<int64_t>(1, (n_src + kTile - 1) / kTile);
+    const int64_t target = (int64_t)sms * 8;
+    int64_t chunks = 1;
+    if (obs_blocks < target) chunks = std::min<int64_t>(tiles, (target + obs_blocks - 1) / obs_blocks);
+    chunks = std::min<int64_t>(chunks, 65535);
+    int64_t tiles_per_chunk = (tiles + chunks - 1) / chunks;
+    *chunk_len = tiles_per_chunk * kTile;
+    chunks = (n_src + *chunk_len - 1) / *chunk_len;
+    return (int)std::max<int64_t>(1, chunks);
+}
+
+template <int FS> void launch_prism_fs(const PrismArgs& a, dim3 grid, cudaStream_t st)
+{
+    if (g_variant == 0) prism_kernel<FS, 0><<<grid, kBlock, 0, st>>>(a);
+    else prism_kernel<FS, 1><<<grid, kBlock, 0, st>>>(a);
+}
+
+void launch_prism_any(int fs, const PrismArgs& a, dim3 grid, cudaStream_t st)
+{
+    switch (fs) {
+    case F_POT: launch_prism_fs<F_POT>(a, grid, st); break;
+    case F_E: launch_prism_fs<F_E>(a, grid, st); break;
+    case F_N: launch_prism_fs<F_N>(a, grid, st); break;
+    case F_U: launch_prism_fs<F_U>(a, grid, st); break;
+    case F_EE: launch_prism_fs<F_EE>(a, grid, st); break;
+    case F_NN: launch_prism_fs<F_NN>(a, grid, st); break;
+    case F_UU: launch_prism_fs<F_UU>(a, grid, st); break;
+    case F_EN: launch_prism_fs<F_EN>(a, grid, st); break;
+    case F_EU: launch_prism_fs<F_EU>(a, grid, st); break;
+    case F_NU: launch_prism_fs<F_NU>(a, grid, st); break;
+    case FS_ACC3: launch_prism_fs<FS_ACC3>(a, grid, st); break;
+    case FS_TENSOR6: launch_prism_fs<FS_TENSOR6>(a, grid, st); break;
+    case FS_MAG_B: launch_prism_fs<FS_MAG_B>(a, grid, st); break;
+    case FS_MAG_E: launch_prism_fs<FS_MAG_E>(a, grid, st); break;
+    case FS_MAG_N: launch_prism_fs<FS_MAG_N>(a, grid, st); break;
+    case FS_MAG_U: launch_prism_fs<FS_MAG_U>(a, grid, st); break;
+    }
+}
+
+// One fused pass over packed prism records. `partial` must hold
+// chunks*nout*n_obs doubles when the source list is split.
+int run_prism_pass(int fs, int nout, const double* oe, const double* on, const double* ou,
+                   int64_t n_obs, const double* packed, int64_t n_src, const Scales& sc,
+                   unsigned rules, double* out, double* partial, size_t partial_bytes,
+                   unsigned* d_flags, int sms, cudaStream_t st)
+{
+    if (n_obs == 0) return HB200_OK;
+    if (n_src == 0) {
+        CU(cudaMemsetAsync(out, 0, sizeof(double) * nout * n_obs, st));
+        return HB200_OK;
+    }
+    int64_t chunk_len = 0;
+    int chunks = choose_chunks(n_obs, n_src, kBlock, sms, &chunk_len);
+    if (chunks > 1 && (size_t)chunks * nout * n_obs * sizeof(double) > partial_bytes) {
+        chunks = 1;
+        chunk_len = n_src;
+    }
+    PrismArgs a;
+    a.oe = oe; a.on = on; a.ou = ou; a.n_obs = n_obs;
+    a.packed = packed; a.n_src = n_src; a.chunk_len = chunk_len;
+    a.out = chunks > 1 ? partial : out;
+    a.sc = sc; a.rules = rules; a.flags = d_flags;
+    dim3 grid((unsigned)((n_obs + kBlock - 1) / kBlock), (unsigned)chunks);
+    launch_prism_any(fs, a, grid, st);
+    CU(cudaGetLastError());
+    if (chunks > 1) {
+        const int64_t total = (int64_t)nout * n_obs;
+        reduce_partials_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(partial, chunks, nout,
+                                                                                n_obs, sc, out);
+        CU(cudaGetLastError());
+    }
+    return HB200_OK;
+}
+
+size_t partial_bytes_for(int64_t n_obs, int64_t n_src, int nout, int obs_per_block, int sms)
+{
+    int64_t chunk_len;
+    int chunks = choose_chunks(n_obs, n_src, obs_per_block, sms, &chunk_len);
+    return chunks > 1 ? align_up((size_t)chunks * nout * n_obs * sizeof(double)) : 0;
+}
+
+template <int FIELD> void launch_point_cart(const PointArgs& a, dim3 grid, cudaStream_t st)
+{
+    point_kernel_cart<FIELD><<<grid, kBlock, 0, st>>>(a);
+}
+
+int run_point_pass(int field, int spherical, const double* oe, const double* on, const double* ou,
+                   int64_t n_obs, const double* packed, int64_t n_src, double scale, double* out,
+                   double* partial, size_t partial_bytes, unsigned* d_flags, int sms,
+                   cudaStream_t st)
+{
+    if (n_obs == 0) return HB200_OK;
+    if (n_src == 0) {
+        CU(cudaMemsetAsync(out, 0, sizeof(double) * n_obs, st));
+        return HB200_OK;
+    }
+    const int opb = spherical ? kBlock : kBlock * kPointObs;
+    int64_t chunk_len = 0;
+    int chunks = choose_chunks(n_obs, n_src, opb, sms, &chunk_len);
+    if (chunks > 1 && (size_t)chunks * n_obs * sizeof(double) > partial_bytes) {
+        chunks = 1;
+        chunk_len = n_src;
+    }
+    PointArgs a;
+    a.oe = oe; a.on = on; a.ou = ou; a.n_obs = n_obs;
+    a.packed = packed; a.n_src = n_src; a.chunk_len = chunk_len;
+    a.out = chunks > 1 ? partial : out;
+    a.scale = scale; a.flags = d_flags;
+    dim3 grid((unsigned)((n_obs + opb - 1) / opb), (unsigned)chunks);
+    if (spherical) {
+        if (field == F_POT) point_kernel_sph<F_POT><<<grid, kBlock, 0, st>>>(a);
+        else point_kernel_sph<F_U><<<grid, kBlock, 0, st>>>(a);
+    } else {
+        switch (field) {
+        case F_POT: launch_point_cart<F_POT>(a, grid, st); break;
+        case F_E: launch_point_cart<F_E>(a, grid, st); break;
+        case F_N: launch_point_cart<F_N>(a, grid, st); break;
+        case F_U: launch_point_cart<F_U>(a, grid, st); break;
+        case F_EE: launch_point_cart<F_EE>(a, grid, st); break;
+        case F_NN: launch_point_cart<F_NN>(a, grid, st); break;
+        case F_UU: launch_point_cart<F_UU>(a, grid, st); break;
+        case F_EN: launch_point_cart<F_EN>(a, grid, st); break;
+        case F_EU: launch_point_cart<F_EU>(a, grid, st); break;
+        case F_NU: launch_point_cart<F_NU>(a, grid, st); break;
+        }
+    }
+    CU(cudaGetLastError());
+    if (chunks > 1) {
+        Scales sc;
+        sc.s[0] = scale;
+        reduce_partials_kernel<<<(unsigned)((n_obs + 255) / 256), 256, 0, st>>>(partial, chunks, 1,
+                                                                               n_obs, sc, out);
+        CU(cudaGetLastError());
+    }
+    return HB200_OK;
+}
+
+// ---------------------------------------------------------- device-level ops
+// Workspace layout for the prism ops: [packed records][chunk partials].
+size_t prism_ws_bytes(int64_t n_obs, int64_t n_src, int nf, int sms)
+{
+    return align_up((size_t)n_src * kMagStride * sizeof(double))
+         + partial_bytes_for(n_obs, n_src, std::min(nf, 6), kBlock, sms) + 256;
+}
+
+struct Ws {
+    char* base;
+    size_t bytes, used;
+    Ws(void* p, size_t b) : base((char*)p), bytes(b), used(0) {}
+    double* take(size_t nbytes)
+    {
+        nbytes = align_up(nbytes);
+        if (used + nbytes > bytes) return nullptr;
+        double* p = (double*)(base + used);
+        used += nbytes;
+        return p;
+    }
+    size_t left() const { return bytes - used; }
+};
+
+int gravity_passes(const double* oe, const double* on, const double* ou, int64_t n_obs,
+                   const double* packed, int64_t n_src, uint32_t mask, bool raw, double* out,
+                   unsigned* d_flags, Ws& ws, int sms, cudaStream_t st)
+{
+    double* partial = (double*)(ws.base + ws.used);
+    const size_t partial_bytes = ws.left();
+    for (const FieldSpec& p : plan_gravity(mask)) {
+        Scales sc;
+        for (int c = 0; c < 6; c++) sc.s[c] = 1.0;
+        if (!raw) {
+            if (p.fs == FS_TENSOR6) for (int c = 0; c < 6; c++) sc.s[c] = gravity_scale(F_EE + c);
+            else if (p.fs == FS_ACC3) for (int c = 0; c < 3; c++) sc.s[c] = gravity_scale(F_E + c);
+            else sc.s[0] = gravity_scale(p.fs);
+        }
+        int rc = run_prism_pass(p.fs, p.nout, oe, on, ou, n_obs, packed, n_src, sc, 0u,
+                                out + (int64_t)p.slot * n_obs, partial, partial_bytes, d_flags, sms,
+                                st);
+        if (rc) return rc;
+    }
+    return HB200_OK;
+}
+
+int prism_gravity_dev_impl(const double* oe, const double* on, const double* ou, int64_t n_obs,
+                           const double* prisms, const double* density, int64_t n_prisms,
+                           uint32_t mask, bool raw, double* out, unsigned* d_flags, void* wsp,
+                           size_t ws_bytes, int sms, cudaStream_t st)
+{
+    Ws ws(wsp, ws_bytes);
+    double* packed = ws.take((size_t)std::max<int64_t>(n_prisms, 1) * kPrismStride * sizeof(double));
+    if (!packed) return fail(HB200_EINVAL, "workspace too small");
+    if (n_prisms > 0) {
+        pack_prisms_kernel<<<(unsigned)((n_prisms + 255) / 256), 256, 0, st>>>(prisms, density,
+                                                                              n_prisms, packed);
+        CU(cudaGetLastError());
+    }
+    return gravity_passes(oe, on, ou, n_obs, packed, n_prisms, mask, raw, out, d_flags, ws, sms, st);
+}
+
+int prism_layer_dev_impl(const double* oe, const double* on, const double* ou, int64_t n_obs,
+                         const double* east_c, int64_t n_east, const double* north_c,
+                         int64_t n_north, const double* bottom, const double* top,
+                         const double* density, double thr, uint32_t mask, bool raw, double* out,
+                         unsigned* d_flags, void* wsp, size_t ws_bytes, int sms, cudaStream_t st)
+{
+    const int64_t n_src = n_east * n_north;
+    Ws ws(wsp, ws_bytes);
+    double* packed = ws.take((size_t)std::max<int64_t>(n_src, 1) * kPrismStride * sizeof(double));
+    if (!packed) return fail(HB200_EINVAL, "workspace too small");
+    if (n_src > 0) {
+        pack_layer_kernel<<<(unsigned)((n_src + 255) / 256), 256, 0, st>>>(
+            east_c, north_c, n_east, n_north, bottom, top, density, thr, packed);
+        CU(cudaGetLastError());
+    }
+    return gravity_passes(oe, on, ou, n_obs, packed, n_src, mask, raw, out, d_flags, ws, sms, st);
+}
+
+int prism_magnetic_dev_impl(const double* oe, const double* on, const double* ou, int64_t n_obs,
+                            const double* prisms, const double* me, const double* mn,
+                            const double* mu, int64_t n_prisms, uint32_t cmask, uint32_t rules,
+                            bool raw, double* out, unsigned* d_flags, void* wsp, size_t ws_bytes,
+                            int sms, cudaStream_t st)
+{
+    Ws ws(wsp, ws_bytes);
+    double* packed = ws.take((size_t)std::max<int64_t>(n_prisms, 1) * kMagStride * sizeof(double));
+    if (!packed) return fail(HB200_EINVAL, "workspace too small");
+    if (n_prisms > 0) {
+        pack_mag_kernel<<<(unsigned)((n_prisms + 255) / 256), 256, 0, st>>>(prisms, me, mn, mu,
+                                                                           n_prisms, packed);
+        CU(cudaGetLastError());
+    }
+    double* partial = (double*)(ws.base + ws.used);
+    const size_t partial_bytes = ws.left();
+    // magnetic.py:195-197, :271: T -> nT; mu0/4pi as choclo
+    const double mu0 = 4 * kPi * 1e-7;
+    const double cm = mu0 / 4 / kPi;
+    Scales sc;
+    for (int c = 0; c < 6; c++) sc.s[c] = raw ? 1.0 : cm * 1e9;
+    if (cmask == HB200_B_ALL)
+        return run_prism_pass(FS_MAG_B, 3, oe, on, ou, n_obs, packed, n_prisms, sc, rules, out,
+                              partial, partial_bytes, d_flags, sms, st);
+    int slot = 0;
+    for (int c = 0; c < 3; c++) {
+        if (!(cmask >> c & 1u)) continue;
+        int rc = run_prism_pass(FS_MAG_E + c, 1, oe, on, ou, n_obs, packed, n_prisms, sc, rules,
+                                out + (int64_t)slot * n_obs, partial, partial_bytes, d_flags, sms,
+                                st);
+        if (rc) return rc;
+        slot++;
+    }
+    return HB200_OK;
+}
+
+double point_scale(int field)
+{
+    // point.py:253-260
+    return gravity_scale(field);
+}
+
+size_t point_ws_bytes(int64_t n_obs, int64_t n_src, int sms)
+{
+    return align_up((size_t)n_src * kSphStride * sizeof(double))
+         + partial_bytes_for(n_obs, n_src, 1, kBlock, sms) + 256;
+}
+
+int point_gravity_dev_impl(const double* oe, const double* on, const double* ou, int64_t n_obs,
+                           const double* pe, const double* pn, const double* pu, const double* w,
+                           int64_t n_src, uint32_t mask, int spherical, int scale_by_G, bool raw,
+                           double* out, unsigned* d_flags, void* wsp, size_t ws_bytes, int sms,
+                           cudaStream_t st)
+{
+    Ws ws(wsp, ws_bytes);
+    const int stride = spherical ? kSphStride : kPointStride;
+    double* packed = ws.take((size_t)std::max<int64_t>(n_src, 1) * stride * sizeof(double));
+    if (!packed) return fail(HB200_EINVAL, "workspace too small");
+    if (n_src > 0) {
+        const unsigned nb = (unsigned)((n_src + 255) / 256);
+        if (spherical) pack_points_sph_kernel<<<nb, 256, 0, st>>>(pe, pn, pu, w, n_src, packed);
+        else pack_points_kernel<<<nb, 256, 0, st>>>(pe, pn, pu, w, n_src, scale_by_G, packed);
+        CU(cudaGetLastError());
+    }
+    double* partial = (double*)(ws.base + ws.used);
+    const size_t partial_bytes = ws.left();
+    int slot = 0;
+    for (int f = 0; f < 10; f++) {
+        if (!(mask >> f & 1u)) continue;
+        const double scale = (raw || !scale_by_G) ? 1.0 : point_scale(f);
+        int rc = run_point_pass(f, spherical, oe, on, ou, n_obs, packed, n_src, scale,
+                                out + (int64_t)slot * n_obs, partial, partial_bytes, d_flags, sms,
+                                st);
+        if (rc) return rc;
+        slot++;
+    }
+    return HB200_OK;
+}
+
+// ------------------------------------------------------------- host sharding
+int lazy_init()
+{
+    if (!g_devs.empty()) return HB200_OK;
+    return hb200_init(nullptr, 0);
+}
+
+struct HostArray {
+    const double* host;  // may be null (optional array)
+    int64_t rows;        // rows (sharded along rows when `sharded`)
+    int width;           // doubles per row
+    bool sharded;        // follows the source shard
+};
+
+struct ShardPlan {
+    int ndev;
+    bool by_sources;
+};
+
+ShardPlan plan_shards(int64_t n_obs, int64_t n_src, int shard_mode, bool src_shardable)
+{
+    ShardPlan p;
+    const int avail = (int)g_devs.size();
+    const double pairs = (double)n_obs * (double)n_src;
+    int want = (int)std::min<double>(avail, std::max(1.0, pairs / 2e8));
+    p.by_sources = false;
+    if (shard_mode == HB200_SHARD_SOURCES && src_shardable) p.by_sources = true;
+    else if (shard_mode == HB200_SHARD_AUTO && src_shardable && want > 1
+             && n_obs < (int64_t)4096 * want && n_src >= (int64_t)4096 * want)
+        p.by_sources = true;
+    if (shard_mode != HB200_SHARD_AUTO) want = avail;
+    const int64_t units = p.by_sources ? n_src : n_obs;
+    want = (int)std::max<int64_t>(1, std::min<int64_t>(want, units));
+    p.ndev = want;
+    return p;
+}
+
+// Generic host driver. `launch` runs the op on one device for the observer
+// range and source range that device owns.
+template <typename Launch>
+int run_host_job(const double* oe, const double* on, const double* ou, int64_t n_obs,
+                 std::vector<HostArray> arrays, int64_t n_src, int nf, size_t ws_bytes_per_dev_hint,
+                 int shard_mode, bool src_shardable, const Scales& final_scales, double* out,
+                 uint32_t* flags, Launch launch,
+                 size_t (*ws_fn)(int64_t, int64_t, int, int))
+{
+    (void)ws_bytes_per_dev_hint;
+    std::lock_guard<std::mutex> lock(g_mu);
+    int rc = lazy_init();
+    if (rc) return rc;
+    if (flags) *flags = 0;
+    if (n_obs == 0) return HB200_OK;
+    const ShardPlan plan = plan_shards(n_obs, n_src, shard_mode, src_shardable);
+    const int nd = plan.ndev;
+
+    struct Part {
+        int64_t olo, ohi, slo, shi;
+        double *d_oe, *d_on, *d_ou, *d_out;
+        std::vector<double*> d_arr;
+        void* ws;
+        size_t ws_bytes;
+    };
+    std::vector<Part> parts(nd);
+    for (int d = 0; d < nd; d++) {
+        Part& p = parts[d];
+        if (plan.by_sources) {
+            p.olo = 0; p.ohi = n_obs;
+            p.slo = n_src * d / nd; p.shi = n_src * (d + 1) / nd;
+        } else {
+            p.olo = n_obs * d / nd; p.ohi = n_obs * (d + 1) / nd;
+            p.slo = 0; p.shi = n_src;
+        }
+    }
+    // phase 1: allocate + upload + launch on every device (async per device)
+    for (int d = 0; d < nd; d++) {
+        Dev& dev = g_devs[d];
+        Part& p = parts[d];
+        CU(cudaSetDevice(dev.id));
+        const int64_t no = p.ohi - p.olo, ns = p.shi - p.slo;
+        size_t need = 3 * align_up(no * sizeof(double)) + align_up((size_t)nf * no * sizeof(double));
+        for (const HostArray& a : arrays) {
+            const int64_t rows = a.sharded ? ns : a.rows;
+            need += align_up((size_t)std::max<int64_t>(rows, 1) * a.width * sizeof(double));
+        }
+        p.ws_bytes = ws_fn(no, ns, nf, dev.sms);
+        need += align_up(p.ws_bytes);
+        if (plan.by_sources && d == 0)
+            need += align_up((size_t)nd * nf * n_obs * sizeof(double)) + 256;
+        rc = dev.ensure(need + 4096);
+        if (rc) return rc;
+        p.d_oe = dev.take<double>(no);
+        p.d_on = dev.take<double>(no);
+        p.d_ou = dev.take<double>(no);
+        p.d_out = dev.take<double>((size_t)nf * no);
+        CU(cudaMemcpyAsync(p.d_oe, oe + p.olo, no * sizeof(double), cudaMemcpyHostToDevice, dev.st));
+        CU(cudaMemcpyAsync(p.d_on, on + p.olo, no * sizeof(double), cudaMemcpyHostToDevice, dev.st));
+        CU(cudaMemcpyAsync(p.d_ou, ou + p.olo, no * sizeof(double), cudaMemcpyHostToDevice, dev.st));
+        for (const HostArray& a : arrays) {
+            const int64_t rows = a.sharded ? ns : a.rows;
+            double* dptr = nullptr;
+            if (a.host) {
+                dptr = dev.take<double>((size_t)std::max<int64_t>(rows, 1) * a.width);
+                const double* src = a.host + (a.sharded ? p.slo * a.width : 0);
+                if (rows > 0)
+                    CU(cudaMemcpyAsync(dptr, src, (size_t)rows * a.width * sizeof(double),
+                                       cudaMemcpyHostToDevice, dev.st));
+            }
+            p.d_arr.push_back(dptr);
+        }
+        p.ws = dev.take<char>(p.ws_bytes);
+        CU(cudaMemsetAsync(dev.d_flags, 0, sizeof(unsigned), dev.st));
+        rc = launch(dev, p.d_oe, p.d_on, p.d_ou, no, p.d_arr, ns, /*raw=*/plan.by_sources, p.d_out,
+                    p.ws, p.ws_bytes);
+        if (rc) return rc;
+    }
+    // phase 2: collect
+    unsigned all_flags = 0;
+    if (!plan.by_sources) {
+        for (int d = 0; d < nd; d++) {
+            Dev& dev = g_devs[d];
+            Part& p = parts[d];
+            CU(cudaSetDevice(dev.id));
+            const int64_t no = p.ohi - p.olo;
+            for (int k = 0; k < nf; k++)
+                CU(cudaMemcpyAsync(out + (int64_t)k * n_obs + p.olo, p.d_out + (int64_t)k * no,
+                                   no * sizeof(double), cudaMemcpyDeviceToHost, dev.st));
+        }
+    } else {
+        // reduce-sum of the per-device partial fields on device 0: peer copies
+        // (NVLink when peer access is enabled) + fixed-order reduce kernel.
+        Dev& d0 = g_devs[0];
+        CU(cudaSetDevice(d0.id));
+        double* gathered = d0.take<double>((size_t)nd * nf * n_obs);
+        for (int d = 0; d < nd; d++) {
+            Dev& dev = g_devs[d];
+            CU(cudaSetDevice(dev.id));
+            CU(cudaStreamSynchronize(dev.st));
+        }
+        CU(cudaSetDevice(d0.id));
+        for (int d = 0; d < nd; d++)
+            CU(cudaMemcpyPeerAsync(gathered + (size_t)d * nf * n_obs, d0.id, parts[d].d_out,
+                                   g_devs[d].id, (size_t)nf * n_obs * sizeof(double), d0.st));
+        const int64_t total = (int64_t)nf * n_obs;
+        reduce_partials_kernel<<<(unsigned)((total + 255) / 256), 256, 0, d0.st>>>(
+            gathered, nd, nf, n_obs, final_scales, parts[0].d_out);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(out, parts[0].d_out, total * sizeof(double), cudaMemcpyDeviceToHost,
+                           d0.st));
+    }
+    for (int d = 0; d < nd; d++) {
+        Dev& dev = g_devs[d];
+        CU(cudaSetDevice(dev.id));
+        unsigned f = 0;
+        CU(cudaMemcpyAsync(&f, dev.d_flags, sizeof(unsigned), cudaMemcpyDeviceToHost, dev.st));
+        CU(cudaStreamSynchronize(dev.st));
+        all_flags |= f;
+    }
+    if (flags) *flags = all_flags;
+    return HB200_OK;
+}
+
+size_t ws_prism(int64_t no, int64_t ns, int nf, int sms) { return prism_ws_bytes(no, ns, nf, sms); }
+size_t ws_point(int64_t no, int64_t ns, int nf, int sms)
+{
+    (void)nf;
+    return point_ws_bytes(no, ns, sms);
+}
+
+Scales gravity_scales_for_mask(uint32_t mask)
+{
+    Scales sc;
+    int s = 0;
+    for (int c = 0; c < 6; c++) sc.s[c] = 1.0;
+    for (int f = 0; f < 10 && s < 6; f++)
+        if (mask >> f & 1u) sc.s[s++] = gravity_scale(f);
+    return sc;
+}
+
+}  // namespace
+
+// =============================================================== C ABI
+extern "C" {
+
+int hb200_version(void) { return 100; }
+
+const char* hb200_last_error(void) { return g_err.c_str(); }
+
+int hb200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int ok = 0;
+    for (int d = 0; d < n; d++) {
+        int major = 0;
+        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d);
+        if (major == 10) ok++;
+    }
+    return ok;
+}
+
+int hb200_set_variant(int variant)
+{
+    if (variant != 0 && variant != 1) return fail(HB200_EINVAL, "variant must be 0 or 1");
+    g_variant = variant;
+    return HB200_OK;
+}
+int hb200_get_variant(void) { return g_variant; }
+
+void hb200_shutdown(void)
+{
+    for (Dev& d : g_devs) {
+        cudaSetDevice(d.id);
+        if (d.pool) cudaFree(d.pool);
+        if (d.d_flags) cudaFree(d.d_flags);
+        if (d.st) cudaStreamDestroy(d.st);
+    }
+    g_devs.clear();
+}
+
+int hb200_num_devices(void) { return (int)g_devs.size(); }
+
+int hb200_init(const int* devices, int n_devices)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(HB200_ENODEV, "no CUDA device visible (%s); harmonica_b200 has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    std::vector<int> ids;
+    if (devices && n_devices > 0) ids.assign(devices, devices + n_devices);
+    else for (int d = 0; d < n; d++) ids.push_back(d);
+    hb200_shutdown();
+    for (int id : ids) {
+        if (id < 0 || id >= n) return fail(HB200_EINVAL, "device %d out of range [0, %d)", id, n);
+        int major = 0;
+        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, id);
+        if (major != 10)
+            return fail(HB200_ENODEV, "device %d is sm_%d*, this library is built for sm_100a only",
+                        id, major * 10);
+        Dev d;
+        d.id = id;
+        CU(cudaSetDevice(id));
+        cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, id);
+        CU(cudaStreamCreateWithFlags(&d.st, cudaStreamNonBlocking));
+        CU(cudaMalloc(&d.d_flags, sizeof(unsigned)));
+        g_devs.push_back(d);
+    }
+    // peer access towards device 0 (source-sharded reduce)
+    for (size_t a = 1; a < g_devs.size(); a++) {
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, g_devs[0].id, g_devs[a].id);
+        if (can) {
+            cudaSetDevice(g_devs[0].id);
+            if (cudaDeviceEnablePeerAccess(g_devs[a].id, 0) != cudaSuccess) cudaGetLastError();
+        }
+    }
+    return HB200_OK;
+}
+
+int hb200_prism_gravity(const double* easting, const double* northing, const double* upward,
+                        int64_t n_obs, const double* prisms, const double* density,
+                        int64_t n_prisms, uint32_t field_mask, int shard_mode, double* out,
+                        uint32_t* flags)
+{
+    if (!field_mask || (field_mask >> 10)) return fail(HB200_EINVAL, "bad field_mask 0x%x", field_mask);
+    if (n_obs < 0 || n_prisms < 0) return fail(HB200_EINVAL, "negative size");
+    const int nf = popcount(field_mask);
+    if (nf > 6) return fail(HB200_EINVAL, "at most 6 fields per call");
+    std::vector<HostArray> arrays = {{prisms, n_prisms, 6, true}, {density, n_prisms, 1, true}};
+    auto launch = [=](Dev& dev, const double* oe, const double* on, const double* ou, int64_t no,
+                      std::vector<double*>& arr, int64_t ns, bool raw, double* d_out, void* ws,
+                      size_t wsb) {
+        return prism_gravity_dev_impl(oe, on, ou, no, arr[0], arr[1], ns, field_mask, raw, d_out,
+                                      dev.d_flags, ws, wsb, dev.sms, dev.st);
+    };
+    return run_host_job(easting, northing, upward, n_obs, arrays, n_prisms, nf, 0, shard_mode, true,
+                        gravity_scales_for_mask(field_mask), out, flags, launch, ws_prism);
+}
+
+int hb200_prism_singular_scan(const double* easting, const double* northing,
+                              const double* upward, int64_t n_obs, const double* prisms,
+                              int64_t n_prisms, int field, uint32_t* flags)
+{
+    if (!flags) return fail(HB200_EINVAL, "flags must not be NULL");
+    *flags = 0;
+    if (n_obs <= 0 || n_prisms <= 0) return HB200_OK;
+    std::vector<HostArray> arrays = {{prisms, n_prisms, 6, false}};
+    auto launch = [=](Dev& dev, const double* oe, const double* on, const double* ou, int64_t no,
+                      std::vector<double*>& arr, int64_t ns, bool raw, double* d_out, void* ws,
+                      size_t wsb) {
+        (void)raw; (void)d_out; (void)ns;
+        Ws w(ws, wsb);
+        double* packed = w.take((size_t)n_prisms * kPrismStride * sizeof(double));
+        if (!packed) return fail(HB200_EINVAL, "workspace too small");
+        pack_prisms_kernel<<<(unsigned)((n_prisms + 255) / 256), 256, 0, dev.st>>>(arr[0], nullptr,
+                                                                                  n_prisms, packed);
+        int64_t chunk_len;
+        int chunks = choose_chunks(no, n_prisms, kBlock, dev.sms, &chunk_len);
+        PrismArgs a;
+        a.oe = oe; a.on = on; a.ou = ou; a.n_obs = no; a.packed = packed; a.n_src = n_prisms;
+        a.chunk_len = chunk_len; a.out = nullptr; a.rules = 0; a.flags = dev.d_flags;
+        dim3 grid((unsigned)((no + kBlock - 1) / kBlock), (unsigned)chunks);
+        singular_scan_kernel<<<grid, kBlock, 0, dev.st>>>(a, field);
+        CU(cudaGetLastError());
+        return HB200_OK;
+    };
+    Scales sc;
+    for (int c = 0; c < 6; c++) sc.s[c] = 1.0;
+    std::vector<double> dummy((size_t)n_obs);
+    return run_host_job(easting, northing, upward, n_obs, arrays, n_prisms, 1, 0,
+                        HB200_SHARD_OBSERVERS, false, sc, dummy.data(), flags, launch, ws_prism);
+}
+
+int hb200_prism_magnetic(const double* easting, const double* northing, const double* upward,
+                         int64_t n_obs, const double* prisms, const double* mag_e,
+                         const double* mag_n, const double* mag_u, int64_t n_prisms,
+                         uint32_t component_mask, uint32_t rules, int shard_mode, double* out,
+                         uint32_t* flags)
+{
+    if (!component_mask || (component_mask >> 3))
+        return fail(HB200_EINVAL, "bad component_mask 0x%x", component_mask);
+    const int nf = popcount(component_mask);
+    std::vector<HostArray> arrays = {{prisms, n_prisms, 6, true}, {mag_e, n_prisms, 1, true},
+                                     {mag_n, n_prisms, 1, true}, {mag_u, n_prisms, 1, true}};
+    auto launch = [=](Dev& dev, const double* oe, const double* on, const double* ou, int64_t no,
+                      std::vector<double*>& arr, int64_t ns, bool raw, double* d_out, void* ws,
+                      size_t wsb) {
+        return prism_magnetic_dev_impl(oe, on, ou, no, arr[0], arr[1], arr[2], arr[3], ns,
+                                       component_mask, rules, raw, d_out, dev.d_flags, ws, wsb,
+                                       dev.sms, dev.st);
+    };
+    const double mu0 = 4 * kPi * 1e-7;
+    Scales sc;
+    for (int c = 0; c < 6; c++) sc.s[c] = mu0 / 4 / kPi * 1e9;
+    return run_host_job(easting, northing, upward, n_obs, arrays, n_prisms, nf, 0, shard_mode, true,
+                        sc, out, flags, launch, ws_prism);
+}
+
+int hb200_prism_layer_gravity(const double* easting, const double* northing,
+                              const double* upward, int64_t n_obs, const double* prisms_easting,
+                              int64_t n_east, const double* prisms_northing, int64_t n_north,
+                              const double* bottom, const double* top, const double* density,
+                              double thickness_threshold, uint32_t field_mask, int shard_mode,
+                              double* out, uint32_t* flags)
+{
+    (void)shard_mode;  // the layer is replicated; observers are sharded
+    if (!field_mask || (field_mask >> 10)) return fail(HB200_EINVAL, "bad field_mask 0x%x", field_mask);
+    if (n_east < 2 || n_north < 2)
+        return fail(HB200_EINVAL, "a prism layer needs at least 2 coordinates per axis");
+    const int nf = popcount(field_mask);
+    if (nf > 6) return fail(HB200_EINVAL, "at most 6 fields per call");
+    const int64_t n_src = n_east * n_north;
+    std::vector<HostArray> arrays = {{prisms_easting, n_east, 1, false},
+                                     {prisms_northing, n_north, 1, false},
+                                     {bottom, n_src, 1, false},
+                                     {top, n_src, 1, false},
+                                     {density, n_src, 1, false}};
+    auto launch = [=](Dev& dev, const double* oe, const double* on, const double* ou, int64_t no,
+                      std::vector<double*>& arr, int64_t ns, bool raw, double* d_out, void* ws,
+                      size_t wsb) {
+        (void)ns;
+        return prism_layer_dev_impl(oe, on, ou, no, arr[0], n_east, arr[1], n_north, arr[2], arr[3],
+                                    arr[4], thickness_threshold, field_mask, raw, d_out, dev.d_flags,
+                                    ws, wsb, dev.sms, dev.st);
+    };
+    return run_host_job(easting, northing, upward, n_obs, arrays, n_src, nf, 0,
+                        HB200_SHARD_OBSERVERS, false, gravity_scales_for_mask(field_mask), out,
+                        flags, launch, ws_prism);
+}
+
+int hb200_point_gravity(const double* easting, const double* northing, const double* upward,
+                        int64_t n_obs, const double* src_easting, const double* src_northing,
+                        const double* src_upward, const double* masses, int64_t n_src,
+                        uint32_t field_mask, int spherical, int shard_mode, double* out,
+                        uint32_t* flags)
+{
+    if (!field_mask || (field_mask >> 10)) return fail(HB200_EINVAL, "bad field_mask 0x%x", field_mask);
+    if (spherical && (field_mask & ~((1u << F_POT) | (1u << F_U))))
+        return fail(HB200_EINVAL, "spherical point masses: only potential and g_z exist");
+    const int nf = popcount(field_mask);
+    if (nf > 6) return fail(HB200_EINVAL, "at most 6 fields per call");
+    std::vector<HostArray> arrays = {{src_easting, n_src, 1, true}, {src_northing, n_src, 1, true},
+                                     {src_upward, n_src, 1, true}, {masses, n_src, 1, true}};
+    auto launch = [=](Dev& dev, const double* oe, const double* on, const double* ou, int64_t no,
+                      std::vector<double*>& arr, int64_t ns, bool raw, double* d_out, void* ws,
+                      size_t wsb) {
+        return point_gravity_dev_impl(oe, on, ou, no, arr[0], arr[1], arr[2], arr[3], ns, field_mask,
+                                      spherical, 1, raw, d_out, dev.d_flags, ws, wsb, dev.sms,
+                                      dev.st);
+    };
+    return run_host_job(easting, northing, upward, n_obs, arrays, n_src, nf, 0, shard_mode, true,
+                        gravity_scales_for_mask(field_mask), out, flags, launch, ws_point);
+}
+
+int hb200_eqs_predict(const double* easting, const double* northing, const double* upward,
+                      int64_t n_obs, const double* src_easting, const double* src_northing,
+                      const double* src_upward, const double* coefs, int64_t n_src,
+                      int shard_mode, double* out, uint32_t* flags)
+{
+    std::vector<HostArray> arrays = {{src_easting, n_src, 1, true}, {src_northing, n_src, 1, true},
+                                     {src_upward, n_src, 1, true}, {coefs, n_src, 1, true}};
+    auto launch = [=](Dev& dev, const double* oe, const double* on, const double* ou, int64_t no,
+                      std::vector<double*>& arr, int64_t ns, bool raw, double* d_out, void* ws,
+                      size_t wsb) {
+        return point_gravity_dev_impl(oe, on, ou, no, arr[0], arr[1], arr[2], arr[3], ns,
+                                      1u << F_POT, 0, 0, raw, d_out, dev.d_flags, ws, wsb, dev.sms,
+                                      dev.st);
+    };
+    Scales sc;
+    for (int c = 0; c < 6; c++) sc.s[c] = 1.0;
+    return run_host_job(easting, northing, upward, n_obs, arrays, n_src, 1, 0, shard_mode, true, sc,
+                        out, flags, launch, ws_point);
+}
+
+int hb200_eqs_jacobian(const double* easting, const double* northing, const double* upward,
+                       int64_t n_obs, const double* src_easting, const double* src_northing,
+                       const double* src_upward, int64_t n_src, double* jac)
+{
+    std::lock_guard<std::mutex> lock(g_mu);
+    int rc = lazy_init();
+    if (rc) return rc;
+    if (n_obs <= 0 || n_src <= 0) return HB200_OK;
+    Dev& dev = g_devs[0];
+    CU(cudaSetDevice(dev.id));
+    // rows are produced in slabs so that the device buffer stays bounded
+    const int64_t slab = std::max<int64_t>(16, std::min<int64_t>(n_obs, (int64_t)(1 << 28) / n_src));
+    size_t need = 3 * align_up(n_obs * 8) + 3 * align_up(n_src * 8) + align_up((size_t)slab * n_src * 8);
+    rc = dev.ensure(need + 4096);
+    if (rc) return rc;
+    double* d_o[3];
+    double* d_p[3];
+    const double* ho[3] = {easting, northing, upward};
+    const double* hp[3] = {src_easting, src_northing, src_upward};
+    for (int c = 0; c < 3; c++) {
+        d_o[c] = dev.take<double>(n_obs);
+        d_p[c] = dev.take<double>(n_src);
+        CU(cudaMemcpyAsync(d_o[c], ho[c], n_obs * 8, cudaMemcpyHostToDevice, dev.st));
+        CU(cudaMemcpyAsync(d_p[c], hp[c], n_src * 8, cudaMemcpyHostToDevice, dev.st));
+    }
+    double* d_jac = dev.take<double>((size_t)slab * n_src);
+    for (int64_t i0 = 0; i0 < n_obs; i0 += slab) {
+        const int64_t rows = std::min(slab, n_obs - i0);
+        dim3 grid((unsigned)((n_src + 255) / 256), (unsigned)((rows + 15) / 16));
+        eqs_jacobian_kernel<<<grid, 256, 0, dev.st>>>(d_o[0] + i0, d_o[1] + i0, d_o[2] + i0, rows,
+                                                     d_p[0], d_p[1], d_p[2], n_src, d_jac);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(jac + i0 * n_src, d_jac, (size_t)rows * n_src * 8, cudaMemcpyDeviceToHost,
+                           dev.st));
+        CU(cudaStreamSynchronize(dev.st));
+    }
+    return HB200_OK;
+}
+
+// ---- device-buffer entry points
+size_t hb200_prism_ws_bytes(int64_t n_obs, int64_t n_sources, int n_fields)
+{
+    return prism_ws_bytes(n_obs, n_sources, n_fields, 148);
+}
+
+int hb200_prism_gravity_dev(const double* easting, const double* northing, const double* upward,
+                            int64_t n_obs, const double* prisms, const double* density,
+                            int64_t n_prisms, uint32_t field_mask, double* out,
+                            uint32_t* flags_dev, void* ws, size_t ws_bytes, void* stream)
+{
+    if (!field_mask || (field_mask >> 10)) return fail(HB200_EINVAL, "bad field_mask 0x%x", field_mask);
+    return prism_gravity_dev_impl(easting, northing, upward, n_obs, prisms, density, n_prisms,
+                                  field_mask, false, out, flags_dev, ws, ws_bytes,
+                                  sm_count_current(), (cudaStream_t)stream);
+}
+
+int hb200_prism_magnetic_dev(const double* easting, const double* northing,
+                             const double* upward, int64_t n_obs, const double* prisms,
+                             const double* mag_e, const double* mag_n, const double* mag_u,
+                             int64_t n_prisms, uint32_t component_mask, uint32_t rules,
+                             double* out, uint32_t* flags_dev, void* ws, size_t ws_bytes,
+                             void* stream)
+{
+    if (!component_mask || (component_mask >> 3))
+        return fail(HB200_EINVAL, "bad component_mask 0x%x", component_mask);
+    return prism_magnetic_dev_impl(easting, northing, upward, n_obs, prisms, mag_e, mag_n, mag_u,
+                                   n_prisms, component_mask, rules, false, out, flags_dev, ws,
+                                   ws_bytes, sm_count_current(), (cudaStream_t)stream);
+}
+
+int hb200_prism_layer_gravity_dev(const double* easting, const double* northing,
+                                  const double* upward, int64_t n_obs,
+                                  const double* prisms_easting, int64_t n_east,
+                                  const double* prisms_northing, int64_t n_north,
+                                  const double* bottom, const double* top, const double* density,
+                                  double thickness_threshold, uint32_t field_mask, double* out,
+                                  uint32_t* flags_dev, void* ws, size_t ws_bytes, void* stream)
+{
+    if (!field_mask || (field_mask >> 10)) return fail(HB200_EINVAL, "bad field_mask 0x%x", field_mask);
+    return prism_layer_dev_impl(easting, northing, upward, n_obs, prisms_easting, n_east,
+                                prisms_northing, n_north, bottom, top, density, thickness_threshold,
+                                field_mask, false, out, flags_dev, ws, ws_bytes, sm_count_current(),
+                                (cudaStream_t)stream);
+}
+
+int hb200_point_gravity_dev(const double* easting, const double* northing, const double* upward,
+                            int64_t n_obs, const double* src_easting, const double* src_northing,
+                            const double* src_upward, const double* weights, int64_t n_src,
+                            uint32_t field_mask, int spherical, int scale_by_G, double* out,
+                            uint32_t* flags_dev, void* ws, size_t ws_bytes, void* stream)
+{
+    if (!field_mask || (field_mask >> 10)) return fail(HB200_EINVAL, "bad field_mask 0x%x", field_mask);
+    return point_gravity_dev_impl(easting, northing, upward, n_obs, src_easting, src_northing,
+                                  src_upward, weights, n_src, field_mask, spherical, scale_by_G,
+                                  false, out, flags_dev, ws, ws_bytes, sm_count_current(),
+                                  (cudaStream_t)stream);
+}
+
+int hb200_fp64_peak(int iters, double* flops, double* seconds)
+{
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    const int sms = sm_count_current();
+    const int blocks = sms * 8, threads = 256;
+    double* d_out = nullptr;
+    CU(cudaMalloc(&d_out, sizeof(double) * blocks * threads));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    fp64_peak_kernel<<<blocks, threads>>>(d_out, 16, 0.999999, 1e-9);  // warm-up
+    CU(cudaEventRecord(e0));
+    fp64_peak_kernel<<<blocks, threads>>>(d_out, iters, 0.999999, 1e-9);
+    CU(cudaEventRecord(e1));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    CU(cudaGetLastError());
+    const double n_fma = (double)blocks * threads * 8.0 * 16.0 * iters;
+    if (seconds) *seconds = ms * 1e-3;
+    if (flops) *flops = 2.0 * n_fma / (ms * 1e-3);
+    cudaFree(d_out);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return HB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,272 @@
+// hb200_fast.cuh -- merged-transcendental evaluation of the 8-vertex prism sum.
+//
+// Valid for pairs whose six shifted coordinates are all non-zero (observer not
+// in the plane of any prism face); every other pair takes prism_pair_direct,
+// which carries the reference's singular-point rules verbatim.
+//
+// The reference (choclo kernels behind gravity.py:526-537 / magnetic.py:319)
+// evaluates per vertex 1-3 safe_log and 1-3 safe_atan2 and forms an
+// alternating sum. Here vertex terms that share their prefactor are merged
+// BEFORE the transcendental:
+//   * logs:  sum_v s_v log(num_v/den_v) = log(prod num^s / prod den^s)
+//            with (num, den) chosen per vertex by the safe_log rule
+//              x >= 0:            (x + r, 1)
+//              x <  0:            (y^2 + z^2, r - x)
+//              x <  0, r == -x:   (1, -2x)
+//   * atans: atan(y0/x0) - atan(y1/x1) = atan2(y0 x1 - x0 y1, x0 x1 + y0 y1)
+//            for the two vertices that differ in one factor of y; x0 and x1
+//            then have the same sign, so the identity is exact, and it
+//            simplifies to  atan2(c a (b0 r1 - b1 r0), a^2 r0 r1 + b0 b1 c^2).
+// Merged forms are algebraically identical to the vertex sum and round better
+// (the far-field cancellation happens inside the ratio, not between logs).
+// g_z: 16 log + 8 atan + 24 div per pair  ->  4 log + 4 atan2 + 4 div.
+#pragma once
+#include "hb200_math.cuh"
+
+namespace hb {
+
+HB_HD bool is_neg(double x)
+{
+#if defined(__CUDA_ARCH__)
+    return __double2hiint(x) < 0;
+#else
+    return signbit(x);
+#endif
+}
+
+// r == |x| for r >= 0, on the integer pipe
+HB_HD bool eq_abs(double r, double x)
+{
+#if defined(__CUDA_ARCH__)
+    return ((((unsigned)__double2hiint(r) ^ (unsigned)__double2hiint(x)) & 0x7fffffffu)
+            | ((unsigned)__double2loint(r) ^ (unsigned)__double2loint(x))) == 0u;
+#else
+    return r == fabs(x);
+#endif
+}
+
+struct FastCtx {
+    double se[2], sn[2], su[2];
+    double se2[2], sn2[2], su2[2];
+    double en2[2][2], eu2[2][2], nu2[2][2];
+    double r[2][2][2];
+};
+
+template <int FS> HB_HD void make_fast_ctx(FastCtx& c, const PairGeom& g)
+{
+    typedef Traits<FS> T;
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        c.se[i] = g.se[i]; c.sn[i] = g.sn[i]; c.su[i] = g.su[i];
+        c.se2[i] = g.se2[i]; c.sn2[i] = g.sn2[i]; c.su2[i] = g.su2[i];
+    }
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+            c.en2[a][b] = add_rn(g.se2[a], g.sn2[b]);
+            if (T::ln) c.eu2[a][b] = add_rn(g.se2[a], g.su2[b]);
+            if (T::le) c.nu2[a][b] = add_rn(g.sn2[a], g.su2[b]);
+        }
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+#pragma unroll
+            for (int k = 0; k < 2; k++) c.r[i][j][k] = sqrt(add_rn(c.en2[i][j], g.su2[k]));
+}
+
+// (num, den) of safe_log type X (0: x = e, 1: x = n, 2: x = u) at vertex ijk
+template <int X>
+HB_HD void log_nd(const FastCtx& c, int i, int j, int k, double& num, double& den)
+{
+    const double x = (X == 0) ? c.se[i] : (X == 1) ? c.sn[j] : c.su[k];
+    const double Y = (X == 0) ? c.nu2[j][k] : (X == 1) ? c.eu2[i][k] : c.en2[i][j];
+    const double rr = c.r[i][j][k];
+    const double T = rr + fabs(x);
+    const bool neg = is_neg(x);
+    const bool axis = eq_abs(rr, x);
+    num = neg ? (axis ? 1.0 : Y) : T;
+    den = neg ? T : 1.0;
+}
+
+// map (fixed axis F with index f, the other two indices a, b in axis order) -> ijk
+template <int F> HB_HD void ijk_of(int f, int a, int b, int& i, int& j, int& k)
+{
+    if (F == 0) { i = f; j = a; k = b; }
+    else if (F == 1) { i = a; j = f; k = b; }
+    else { i = a; j = b; k = f; }
+}
+
+// top/bot products of the 4 vertices with index f fixed on axis F, signs (-1)^(a+b)
+template <int X, int F>
+HB_HD void log_group4_tb(const FastCtx& c, int f, double& top, double& bot)
+{
+    double n[2][2], d[2][2];
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+            int i, j, k;
+            ijk_of<F>(f, a, b, i, j, k);
+            log_nd<X>(c, i, j, k, n[a][b], d[a][b]);
+        }
+    top = (n[0][0] * n[1][1]) * (d[0][1] * d[1][0]);
+    bot = (n[0][1] * n[1][0]) * (d[0][0] * d[1][1]);
+}
+
+// sum_{a,b} (-1)^(a+b) L^X over the 4 vertices with index f on axis F
+template <int X, int F> HB_HD double log_group4(const FastCtx& c, int f)
+{
+    double top, bot;
+    log_group4_tb<X, F>(c, f, top, bot);
+    return log(top / bot);
+}
+
+// sum over all 8 vertices of s_ijk L^X
+template <int X> HB_HD double log_sum8(const FastCtx& c)
+{
+    double t0, b0, t1, b1;
+    log_group4_tb<X, 0>(c, 0, t0, b0);
+    log_group4_tb<X, 0>(c, 1, t1, b1);
+    return log((t0 * b1) / (b0 * t1));
+}
+
+// L^X(x_0) - L^X(x_1) along X's own axis; (a, b) = the other two indices in axis order
+template <int X> HB_HD double log_pair(const FastCtx& c, int a, int b)
+{
+    int i, j, k;
+    double n0, d0, n1, d1;
+    ijk_of<X>(0, a, b, i, j, k);
+    log_nd<X>(c, i, j, k, n0, d0);
+    ijk_of<X>(1, a, b, i, j, k);
+    log_nd<X>(c, i, j, k, n1, d1);
+    return log((n0 * d1) / (n1 * d0));
+}
+
+// S[f] = sum over the 4 vertices with index f on axis X of (-1)^(b+c) A^X, where
+// A^X = atan(b c / (a r)), a = shift on axis X. Two atan2 per call.
+template <int X> HB_HD double atan_sum4(const FastCtx& c, int f)
+{
+    const double a = (X == 0) ? c.se[f] : (X == 1) ? c.sn[f] : c.su[f];
+    const double a2 = (X == 0) ? c.se2[f] : (X == 1) ? c.sn2[f] : c.su2[f];
+    // paired variable b (first remaining axis), remaining variable cc (second remaining axis)
+    const double b0 = (X == 0) ? c.sn[0] : c.se[0];
+    const double b1 = (X == 0) ? c.sn[1] : c.se[1];
+    const double b0b1 = b0 * b1;
+    double D[2];
+#pragma unroll
+    for (int m = 0; m < 2; m++) {
+        const double cc = (X == 2) ? c.sn[m] : c.su[m];
+        const double cc2 = (X == 2) ? c.sn2[m] : c.su2[m];
+        int i, j, k;
+        ijk_of<X>(f, 0, m, i, j, k);
+        const double r0 = c.r[i][j][k];
+        ijk_of<X>(f, 1, m, i, j, k);
+        const double r1 = c.r[i][j][k];
+        const double im = (cc * a) * (b0 * r1 - b1 * r0);
+        const double re = a2 * (r0 * r1) + b0b1 * cc2;
+        D[m] = atan2(im, re);
+    }
+    return D[0] - D[1];
+}
+
+template <int FS> HB_HD void prism_pair_fast(const PairGeom& g, const double* prm, double* acc)
+{
+    typedef Traits<FS> T;
+    FastCtx c;
+    make_fast_ctx<FS>(c, g);
+    const double* e = c.se;
+    const double* n = c.sn;
+    const double* u = c.su;
+    if (FS == F_U) {
+        const double v = e[0] * log_group4<1, 0>(c, 0) - e[1] * log_group4<1, 0>(c, 1)
+                       + n[0] * log_group4<0, 1>(c, 0) - n[1] * log_group4<0, 1>(c, 1)
+                       - (u[0] * atan_sum4<2>(c, 0) - u[1] * atan_sum4<2>(c, 1));
+        acc[0] += prm[0] * -v;
+    } else if (FS == F_E) {
+        const double v = n[0] * log_group4<2, 1>(c, 0) - n[1] * log_group4<2, 1>(c, 1)
+                       + u[0] * log_group4<1, 2>(c, 0) - u[1] * log_group4<1, 2>(c, 1)
+                       - (e[0] * atan_sum4<0>(c, 0) - e[1] * atan_sum4<0>(c, 1));
+        acc[0] += prm[0] * -v;
+    } else if (FS == F_N) {
+        const double v = u[0] * log_group4<0, 2>(c, 0) - u[1] * log_group4<0, 2>(c, 1)
+                       + e[0] * log_group4<2, 0>(c, 0) - e[1] * log_group4<2, 0>(c, 1)
+                       - (n[0] * atan_sum4<1>(c, 0) - n[1] * atan_sum4<1>(c, 1));
+        acc[0] += prm[0] * -v;
+    } else if (FS == F_POT || FS == FS_ACC3) {
+        double Pu[2][2], Pe[2][2], Pn[2][2], SA[3][2];
+#pragma unroll
+        for (int a = 0; a < 2; a++)
+#pragma unroll
+            for (int b = 0; b < 2; b++) {
+                Pu[a][b] = log_pair<2>(c, a, b);  // [i][j]
+                Pe[a][b] = log_pair<0>(c, a, b);  // [j][k]
+                Pn[a][b] = log_pair<1>(c, a, b);  // [i][k]
+            }
+#pragma unroll
+        for (int f = 0; f < 2; f++) {
+            SA[0][f] = atan_sum4<0>(c, f);
+            SA[1][f] = atan_sum4<1>(c, f);
+            SA[2][f] = atan_sum4<2>(c, f);
+        }
+        if (FS == F_POT) {
+            double v = 0.0;
+#pragma unroll
+            for (int a = 0; a < 2; a++)
+#pragma unroll
+                for (int b = 0; b < 2; b++) {
+                    const double sg = ((a + b) & 1) ? -1.0 : 1.0;
+                    v += sg * (e[a] * n[b] * Pu[a][b] + n[a] * u[b] * Pe[a][b]
+                               + e[a] * u[b] * Pn[a][b]);
+                }
+            v -= 0.5 * (c.se2[0] * SA[0][0] - c.se2[1] * SA[0][1]);
+            v -= 0.5 * (c.sn2[0] * SA[1][0] - c.sn2[1] * SA[1][1]);
+            v -= 0.5 * (c.su2[0] * SA[2][0] - c.su2[1] * SA[2][1]);
+            acc[0] += prm[0] * v;
+        } else {
+            // E: sum_j (-1)^j n_j Gu(j) + sum_k (-1)^k u_k Gn(k) - sum_i (-1)^i e_i SAe[i]
+            const double ve = n[0] * (Pu[0][0] - Pu[1][0]) - n[1] * (Pu[0][1] - Pu[1][1])
+                            + u[0] * (Pn[0][0] - Pn[1][0]) - u[1] * (Pn[0][1] - Pn[1][1])
+                            - (e[0] * SA[0][0] - e[1] * SA[0][1]);
+            // N: sum_k (-1)^k u_k Ge(k) + sum_i (-1)^i e_i Gu(i) - sum_j (-1)^j n_j SAn[j]
+            const double vn = u[0] * (Pe[0][0] - Pe[1][0]) - u[1] * (Pe[0][1] - Pe[1][1])
+                            + e[0] * (Pu[0][0] - Pu[0][1]) - e[1] * (Pu[1][0] - Pu[1][1])
+                            - (n[0] * SA[1][0] - n[1] * SA[1][1]);
+            // U: sum_i (-1)^i e_i Gn(i) + sum_j (-1)^j n_j Ge(j) - sum_k (-1)^k u_k SAu[k]
+            const double vu = e[0] * (Pn[0][0] - Pn[0][1]) - e[1] * (Pn[1][0] - Pn[1][1])
+                            + n[0] * (Pe[0][0] - Pe[0][1]) - n[1] * (Pe[1][0] - Pe[1][1])
+                            - (u[0] * SA[2][0] - u[1] * SA[2][1]);
+            acc[0] += prm[0] * -ve;
+            acc[1] += prm[0] * -vn;
+            acc[2] += prm[0] * -vu;
+        }
+    } else {
+        // second-derivative kernels: tensor components and magnetics
+        double kee = 0, knn = 0, kuu = 0, ken = 0, keu = 0, knu = 0;
+        if (T::ae) kee = -(atan_sum4<0>(c, 0) - atan_sum4<0>(c, 1));
+        if (T::an) knn = -(atan_sum4<1>(c, 0) - atan_sum4<1>(c, 1));
+        if (T::au) kuu = -(atan_sum4<2>(c, 0) - atan_sum4<2>(c, 1));
+        if (T::lu) ken = log_sum8<2>(c);
+        if (T::ln) keu = log_sum8<1>(c);
+        if (T::le) knu = log_sum8<0>(c);
+        if (FS == F_EE) acc[0] += prm[0] * kee;
+        else if (FS == F_NN) acc[0] += prm[0] * knn;
+        else if (FS == F_UU) acc[0] += prm[0] * kuu;
+        else if (FS == F_EN) acc[0] += prm[0] * ken;
+        else if (FS == F_EU) acc[0] += prm[0] * keu;
+        else if (FS == F_NU) acc[0] += prm[0] * knu;
+        else if (FS == FS_TENSOR6) {
+            acc[0] += prm[0] * kee; acc[1] += prm[0] * knn; acc[2] += prm[0] * kuu;
+            acc[3] += prm[0] * ken; acc[4] += prm[0] * keu; acc[5] += prm[0] * knu;
+        } else if (FS == FS_MAG_B) {
+            acc[0] += prm[0] * kee + prm[1] * ken + prm[2] * keu;
+            acc[1] += prm[0] * ken + prm[1] * knn + prm[2] * knu;
+            acc[2] += prm[0] * keu + prm[1] * knu + prm[2] * kuu;
+        } else if (FS == FS_MAG_E) acc[0] += prm[0] * kee + prm[1] * ken + prm[2] * keu;
+        else if (FS == FS_MAG_N) acc[0] += prm[0] * ken + prm[1] * knn + prm[2] * knu;
+        else if (FS == FS_MAG_U) acc[0] += prm[0] * keu + prm[1] * knu + prm[2] * kuu;
+    }
+}
+
+}  // namespace hb

@@ -1,0 +1,402 @@
+// hb200_kernels.cuh -- CUDA kernels (sm_100a) of the pairwise forward models.
+//
+// Work decomposition (all kernels): one thread owns one observation point and
+// keeps its float64 accumulators in registers; a CTA of BLOCK observers walks
+// the source list in tiles staged in shared memory as packed records; every
+// lane of a warp reads the SAME record (one broadcast LDS.128 per double2), so
+// the only per-pair memory traffic is shared-memory broadcast. grid.y splits
+// the source list into chunks when there are too few observer CTAs to fill
+// the 148 SMs; chunk partials are combined in a fixed order (deterministic).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "hb200_math.cuh"
+#include "hb200_fast.cuh"
+
+namespace hb {
+
+constexpr int kBlock = 128;  // observers per CTA
+constexpr int kTile = 128;   // sources per shared-memory tile
+
+constexpr int kPrismStride = 8;   // w e s n b t G*rho skip
+constexpr int kMagStride = 10;    // w e s n b t me mn mu skip
+constexpr int kPointStride = 4;   // e n u weight
+constexpr int kSphStride = 6;     // lon(rad) cos(lat) sin(lat) radius weight pad
+
+struct Scales {
+    double s[6];
+};
+
+// ------------------------------------------------------------ pack kernels
+// prisms (P,6) AoS + density -> packed records. gravity.py:526-537 reads the
+// same six columns per pair; here they are read once.
+__global__ void pack_prisms_kernel(const double* __restrict__ prisms,
+                                   const double* __restrict__ density, int64_t n,
+                                   double* __restrict__ packed)
+{
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    double* q = packed + j * kPrismStride;
+#pragma unroll
+    for (int c = 0; c < 6; c++) q[c] = prisms[j * 6 + c];
+    q[6] = density ? kG * density[j] : 0.0;
+    q[7] = 0.0;
+}
+
+__global__ void pack_mag_kernel(const double* __restrict__ prisms, const double* __restrict__ me,
+                                const double* __restrict__ mn, const double* __restrict__ mu,
+                                int64_t n, double* __restrict__ packed)
+{
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    double* q = packed + j * kMagStride;
+#pragma unroll
+    for (int c = 0; c < 6; c++) q[c] = prisms[j * 6 + c];
+    q[6] = me[j];
+    q[7] = mn[j];
+    q[8] = mu[j];
+    q[9] = 0.0;
+}
+
+// layer.py:584-610: bounds from 1-D centres, skip rules in the reference's
+// order, records emitted easting-outer / northing-inner (record index
+// = j * n_north + k for easting index j, northing index k).
+__global__ void pack_layer_kernel(const double* __restrict__ east_c,
+                                  const double* __restrict__ north_c, int64_t n_east,
+                                  int64_t n_north, const double* __restrict__ bottom,
+                                  const double* __restrict__ top,
+                                  const double* __restrict__ density, double thickness_threshold,
+                                  double* __restrict__ packed)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_east * n_north) return;
+    const int64_t j = idx / n_north, k = idx % n_north;
+    const double half_e = (east_c[1] - east_c[0]) / 2;
+    const double half_n = (north_c[1] - north_c[0]) / 2;
+    const double rho = density[k * n_east + j];
+    const double b = bottom[k * n_east + j], t = top[k * n_east + j];
+    bool skip = (rho == 0.0) || isnan(rho);
+    skip = skip || (t - b < thickness_threshold);
+    skip = skip || isnan(t) || isnan(b);
+    double* q = packed + idx * kPrismStride;
+    q[0] = east_c[j] - half_e;
+    q[1] = east_c[j] + half_e;
+    q[2] = north_c[k] - half_n;
+    q[3] = north_c[k] + half_n;
+    q[4] = b;
+    q[5] = t;
+    q[6] = kG * rho;
+    q[7] = skip ? 1.0 : 0.0;
+}
+
+// point sources: weight = G*mass (choclo.point: G * mass * kernel) or the EQS
+// coefficient as is (utils.py:90: coeffs[j] * greens_function).
+__global__ void pack_points_kernel(const double* __restrict__ pe, const double* __restrict__ pn,
+                                   const double* __restrict__ pu, const double* __restrict__ w,
+                                   int64_t n, int scale_by_G, double* __restrict__ packed)
+{
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    double* q = packed + j * kPointStride;
+    q[0] = pe[j];
+    q[1] = pn[j];
+    q[2] = pu[j];
+    q[3] = scale_by_G ? kG * w[j] : w[j];
+}
+
+// point.py:426-435: radians / cos / sin of the sources computed once.
+__global__ void pack_points_sph_kernel(const double* __restrict__ lon,
+                                       const double* __restrict__ lat,
+                                       const double* __restrict__ rad,
+                                       const double* __restrict__ mass, int64_t n,
+                                       double* __restrict__ packed)
+{
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const double d2r = kPi / 180.0;
+    const double phi = lat[j] * d2r;
+    double* q = packed + j * kSphStride;
+    q[0] = lon[j] * d2r;
+    q[1] = cos(phi);
+    q[2] = sin(phi);
+    q[3] = rad[j];
+    q[4] = mass[j];
+    q[5] = 0.0;
+}
+
+// ------------------------------------------------------------ prism kernel
+struct PrismArgs {
+    const double* oe;
+    const double* on;
+    const double* ou;
+    int64_t n_obs;
+    const double* packed;
+    int64_t n_src;
+    int64_t chunk_len;  // sources per blockIdx.y
+    double* out;        // gridDim.y == 1: final [nout][n_obs]; else partial [y][nout][n_obs]
+    Scales sc;
+    unsigned rules;
+    unsigned* flags;
+};
+
+template <int FS, int VARIANT>
+__global__ void __launch_bounds__(kBlock) prism_kernel(const PrismArgs a)
+{
+    typedef Traits<FS> T;
+    constexpr int STRIDE = T::mag ? kMagStride : kPrismStride;
+    __shared__ double2 tile[kTile * STRIDE / 2];
+
+    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    const int64_t ic = i < a.n_obs ? i : a.n_obs - 1;
+    const double E = a.oe[ic], N = a.on[ic], U = a.ou[ic];
+
+    double acc[T::nout];
+#pragma unroll
+    for (int c = 0; c < T::nout; c++) acc[c] = 0.0;
+    unsigned flags = 0;
+
+    const int64_t begin = (int64_t)blockIdx.y * a.chunk_len;
+    const int64_t end = begin + a.chunk_len < a.n_src ? begin + a.chunk_len : a.n_src;
+    const double2* src = reinterpret_cast<const double2*>(a.packed);
+
+    for (int64_t t0 = begin; t0 < end; t0 += kTile) {
+        const int cnt = (int)((end - t0) < kTile ? (end - t0) : kTile);
+        __syncthreads();
+        for (int x = threadIdx.x; x < cnt * (STRIDE / 2); x += kBlock)
+            tile[x] = src[t0 * (STRIDE / 2) + x];
+        __syncthreads();
+#pragma unroll 1
+        for (int s = 0; s < cnt; s++) {
+            const double2* p = tile + s * (STRIDE / 2);
+            const double2 we = p[0], sn = p[1], bt = p[2], q3 = p[3];
+            double prm[3];
+            if (T::mag) {
+                const double2 q4 = p[4];
+                if (q4.y != 0.0) continue;  // warp-uniform
+                prm[0] = q3.x; prm[1] = q3.y; prm[2] = q4.x;
+            } else {
+                if (q3.y != 0.0) continue;  // warp-uniform
+                prm[0] = q3.x; prm[1] = 0.0; prm[2] = 0.0;
+            }
+            PairGeom g;
+            make_geom(g, E, N, U, we.x, we.y, sn.x, sn.y, bt.x, bt.y);
+            if (VARIANT == 0) {
+                prism_pair_direct<FS>(g, prm, a.rules, acc, flags);
+            } else {
+                if (any_zero_shift(g)) prism_pair_direct<FS>(g, prm, a.rules, acc, flags);
+                else prism_pair_fast<FS>(g, prm, acc);
+            }
+        }
+    }
+    if (i < a.n_obs) {
+        if (gridDim.y == 1) {
+#pragma unroll
+            for (int c = 0; c < T::nout; c++) a.out[c * a.n_obs + i] = acc[c] * a.sc.s[c];
+        } else {
+#pragma unroll
+            for (int c = 0; c < T::nout; c++)
+                a.out[((int64_t)blockIdx.y * T::nout + c) * a.n_obs + i] = acc[c];
+        }
+        if (flags && a.flags) atomicOr(a.flags, flags);
+    }
+}
+
+// out[c][i] = scale[c] * sum_y partial[y][c][i]   (fixed order: deterministic)
+__global__ void reduce_partials_kernel(const double* __restrict__ partial, int n_parts, int nout,
+                                       int64_t n_obs, Scales sc, double* __restrict__ out)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nout * n_obs) return;
+    const int c = (int)(idx / n_obs);
+    double s = 0.0;
+    for (int y = 0; y < n_parts; y++) s += partial[(int64_t)y * nout * n_obs + idx];
+    out[idx] = s * sc.s[c];
+}
+
+// ----------------------------------------------------- singular-point scan
+// gravity.py:272-449 as one pass; field selects the predicate set.
+__global__ void __launch_bounds__(kBlock) singular_scan_kernel(const PrismArgs a, int field)
+{
+    __shared__ double2 tile[kTile * kPrismStride / 2];
+    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    const int64_t ic = i < a.n_obs ? i : a.n_obs - 1;
+    const double E = a.oe[ic], N = a.on[ic], U = a.ou[ic];
+    bool hit = false;
+    const int64_t begin = (int64_t)blockIdx.y * a.chunk_len;
+    const int64_t end = begin + a.chunk_len < a.n_src ? begin + a.chunk_len : a.n_src;
+    const double2* src = reinterpret_cast<const double2*>(a.packed);
+    for (int64_t t0 = begin; t0 < end; t0 += kTile) {
+        const int cnt = (int)((end - t0) < kTile ? (end - t0) : kTile);
+        __syncthreads();
+        for (int x = threadIdx.x; x < cnt * (kPrismStride / 2); x += kBlock)
+            tile[x] = src[t0 * (kPrismStride / 2) + x];
+        __syncthreads();
+        for (int s = 0; s < cnt; s++) {
+            const double2* p = tile + s * (kPrismStride / 2);
+            const double2 we = p[0], sn = p[1], bt = p[2];
+            PairGeom g;
+            g.se[0] = we.y - E; g.se[1] = we.x - E;
+            g.sn[0] = sn.y - N; g.sn[1] = sn.x - N;
+            g.su[0] = bt.y - U; g.su[1] = bt.x - U;
+            const PairPreds pr = make_preds(g);
+            bool sing;
+            switch (field) {
+            case F_EE: sing = pr.n_edge | pr.u_edge; break;
+            case F_NN: sing = pr.e_edge | pr.u_edge; break;
+            case F_UU: sing = pr.e_edge | pr.n_edge; break;
+            case F_EN: sing = pr.u_edge; break;
+            case F_EU: sing = pr.n_edge; break;
+            case F_NU: sing = pr.e_edge; break;
+            default: sing = pr.e_edge | pr.n_edge | pr.u_edge; break;
+            }
+            hit |= sing;
+        }
+    }
+    if (hit && i < a.n_obs) atomicOr(a.flags, FLAG_SINGULAR);
+}
+
+// ------------------------------------------------------------ point kernel
+struct PointArgs {
+    const double* oe;
+    const double* on;
+    const double* ou;
+    int64_t n_obs;
+    const double* packed;
+    int64_t n_src;
+    int64_t chunk_len;
+    double* out;
+    double scale;
+    unsigned* flags;
+};
+
+constexpr int kPointObs = 2;  // observers per thread (amortises the record loads)
+
+template <int FIELD>
+__global__ void __launch_bounds__(kBlock) point_kernel_cart(const PointArgs a)
+{
+    __shared__ double2 tile[kTile * kPointStride / 2];
+    double E[kPointObs], N[kPointObs], U[kPointObs], acc[kPointObs];
+    int64_t idx[kPointObs];
+#pragma unroll
+    for (int o = 0; o < kPointObs; o++) {
+        idx[o] = ((int64_t)blockIdx.x * kPointObs + o) * kBlock + threadIdx.x;
+        const int64_t ic = idx[o] < a.n_obs ? idx[o] : a.n_obs - 1;
+        E[o] = a.oe[ic]; N[o] = a.on[ic]; U[o] = a.ou[ic];
+        acc[o] = 0.0;
+    }
+    unsigned flags = 0;
+    const int64_t begin = (int64_t)blockIdx.y * a.chunk_len;
+    const int64_t end = begin + a.chunk_len < a.n_src ? begin + a.chunk_len : a.n_src;
+    const double2* src = reinterpret_cast<const double2*>(a.packed);
+    for (int64_t t0 = begin; t0 < end; t0 += kTile) {
+        const int cnt = (int)((end - t0) < kTile ? (end - t0) : kTile);
+        __syncthreads();
+        for (int x = threadIdx.x; x < cnt * (kPointStride / 2); x += kBlock)
+            tile[x] = src[t0 * (kPointStride / 2) + x];
+        __syncthreads();
+#pragma unroll 4
+        for (int s = 0; s < cnt; s++) {
+            const double2 en = tile[2 * s], uw = tile[2 * s + 1];
+#pragma unroll
+            for (int o = 0; o < kPointObs; o++) {
+                const double k = point_kernel<FIELD>(E[o] - en.x, N[o] - en.y, U[o] - uw.x, flags);
+                acc[o] = fma(uw.y, k, acc[o]);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < kPointObs; o++) {
+        if (idx[o] < a.n_obs) {
+            if (gridDim.y == 1) a.out[idx[o]] = acc[o] * a.scale;
+            else a.out[(int64_t)blockIdx.y * a.n_obs + idx[o]] = acc[o];
+        }
+    }
+    if (flags && a.flags) atomicOr(a.flags, flags);
+}
+
+// point.py:324-354, 436-447 with _forward/utils.py:198-201.
+template <int FIELD>
+__global__ void __launch_bounds__(kBlock) point_kernel_sph(const PointArgs a)
+{
+    __shared__ double2 tile[kTile * kSphStride / 2];
+    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    const int64_t ic = i < a.n_obs ? i : a.n_obs - 1;
+    const double d2r = kPi / 180.0;
+    const double lam = a.oe[ic] * d2r;
+    const double phi = a.on[ic] * d2r;
+    const double cphi = cos(phi), sphi = sin(phi), rad = a.ou[ic];
+    double acc = 0.0;
+    unsigned flags = 0;
+    const int64_t begin = (int64_t)blockIdx.y * a.chunk_len;
+    const int64_t end = begin + a.chunk_len < a.n_src ? begin + a.chunk_len : a.n_src;
+    const double2* src = reinterpret_cast<const double2*>(a.packed);
+    for (int64_t t0 = begin; t0 < end; t0 += kTile) {
+        const int cnt = (int)((end - t0) < kTile ? (end - t0) : kTile);
+        __syncthreads();
+        for (int x = threadIdx.x; x < cnt * (kSphStride / 2); x += kBlock)
+            tile[x] = src[t0 * (kSphStride / 2) + x];
+        __syncthreads();
+        for (int s = 0; s < cnt; s++) {
+            const double2 q0 = tile[3 * s], q1 = tile[3 * s + 1], q2 = tile[3 * s + 2];
+            const double coslambda = cos(q0.x - lam);
+            const double cospsi = q1.x * sphi + q0.y * cphi * coslambda;
+            const double dr = rad - q1.y;
+            const double d2 = dr * dr + 2 * rad * q1.y * (1 - cospsi);
+            if (d2 == 0.0) flags |= FLAG_ZERO_DIV;
+            const double dist = sqrt(d2);
+            double k;
+            if (FIELD == F_POT) {
+                k = 1 / dist * kG;
+            } else {
+                const double delta_z = rad - q1.y * cospsi;
+                k = -kG * delta_z / (dist * dist * dist);
+            }
+            acc += q2.x * k;
+        }
+    }
+    if (i < a.n_obs) {
+        if (gridDim.y == 1) a.out[i] = acc * a.scale;
+        else a.out[(int64_t)blockIdx.y * a.n_obs + i] = acc;
+    }
+    if (flags && a.flags) atomicOr(a.flags, flags);
+}
+
+// utils.py:54-74: dense Green's-function matrix, row-major (n_obs, n_src).
+// HBM-write bound: 8 bytes per pair; threads run along the source index so
+// stores are coalesced.
+__global__ void eqs_jacobian_kernel(const double* __restrict__ oe, const double* __restrict__ on,
+                                    const double* __restrict__ ou, int64_t n_obs,
+                                    const double* __restrict__ pe, const double* __restrict__ pn,
+                                    const double* __restrict__ pu, int64_t n_src,
+                                    double* __restrict__ jac)
+{
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_src) return;
+    const double se = pe[j], sn = pn[j], su = pu[j];
+    const int64_t i0 = (int64_t)blockIdx.y * 16;
+#pragma unroll 4
+    for (int r = 0; r < 16; r++) {
+        const int64_t i = i0 + r;
+        if (i >= n_obs) break;
+        const double de = oe[i] - se, dn = on[i] - sn, du = ou[i] - su;
+        jac[i * n_src + j] = 1.0 / sqrt(de * de + dn * dn + du * du);
+    }
+}
+
+// ----------------------------------------------------- FP64 issue-rate probe
+__global__ void fp64_peak_kernel(double* out, int iters, double a, double b)
+{
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3;
+    double x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    out[(int64_t)blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+}  // namespace hb

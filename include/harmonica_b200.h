@@ -1,0 +1,174 @@
+/*
+ * harmonica_b200.h -- C ABI of libharmonica_b200.so
+ *
+ * The drop-in boundary for harmonica's pairwise source->observer forward
+ * models. The reference (fatiando/harmonica) has no FFI of its own on this
+ * path: its hot loops are Numba-jitted Python. Each entry point below replaces
+ * one jitted loop (plus the choclo kernel it calls) and is what the
+ * reference's Python wrapper would bind through ctypes (INTEGRATION.md shows
+ * the stub). Citations are file:line under /root/reference/src/harmonica.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all arrays are C-contiguous float64
+ *  - host entry points (no suffix): caller-owned HOST buffers, blocking; the
+ *    library owns device memory, streams and peer access. Work is sharded over
+ *    the devices selected by hb200_init() by observation points (shard_mode 1,
+ *    default) or by sources with a peer reduce-sum (shard_mode 2).
+ *  - *_dev entry points: caller-owned DEVICE buffers on the current device,
+ *    asynchronous on `stream` (a cudaStream_t passed as void*); workspace is
+ *    caller-provided (query with the matching *_ws_bytes).
+ *  - outputs are field-major: out[k * n_obs + i] for the k-th requested field
+ *    in ascending field-id order, ALREADY in harmonica's units and sign
+ *    convention (mGal / Eotvos / nT, z down for g_z, g_ez, g_nz).
+ *  - return value: HB200_OK or a negative HB200_E*; text via hb200_last_error()
+ *  - *flags (may be NULL) receives an OR of HB200_FLAG_*
+ */
+#ifndef HARMONICA_B200_H
+#define HARMONICA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HB200_OK 0
+#define HB200_EINVAL (-1)  /* bad argument */
+#define HB200_ECUDA (-2)   /* CUDA runtime error, see hb200_last_error() */
+#define HB200_ENODEV (-3)  /* no usable sm_100 device */
+#define HB200_ENOMEM (-4)
+
+/* field ids (bit positions of field_mask). Names follow harmonica's FIELDS
+ * dict, _forward/prisms/gravity.py:37-48. */
+enum hb200_field {
+    HB200_POTENTIAL = 0, HB200_G_E = 1, HB200_G_N = 2, HB200_G_Z = 3,
+    HB200_G_EE = 4, HB200_G_NN = 5, HB200_G_ZZ = 6,
+    HB200_G_EN = 7, HB200_G_EZ = 8, HB200_G_NZ = 9
+};
+#define HB200_MASK_ACCEL 0x00Eu  /* g_e | g_n | g_z, one fused pass */
+#define HB200_MASK_TENSOR 0x3F0u /* the six tensor components, one fused pass */
+
+/* magnetic component mask, _forward/prisms/magnetic.py:20-25 */
+#define HB200_B_E 1u
+#define HB200_B_N 2u
+#define HB200_B_U 4u
+#define HB200_B_ALL 7u /* field="b": one fused pass */
+
+/* behaviour switches of the magnetic kernels (choclo version dependent) */
+#define HB200_MAG_NAN_ON_EDGES 1u
+#define HB200_MAG_FACE_OUTSIDE_LIMIT 2u
+#define HB200_MAG_DEFAULT 3u
+
+#define HB200_FLAG_SINGULAR 1u /* an observer sits on a singular point of a prism */
+#define HB200_FLAG_ZERO_DIV 2u /* observer coincides with a point source */
+
+#define HB200_SHARD_AUTO 0
+#define HB200_SHARD_OBSERVERS 1
+#define HB200_SHARD_SOURCES 2
+
+/* ---- library / device management ---------------------------------------- */
+int hb200_version(void);
+/* number of visible CUDA devices with compute capability 10.x */
+int hb200_device_count(void);
+/* select the devices used by the host entry points; devices == NULL selects
+ * all visible ones. Idempotent; called lazily with NULL if never called. */
+int hb200_init(const int* devices, int n_devices);
+int hb200_num_devices(void);
+void hb200_shutdown(void);
+const char* hb200_last_error(void);
+/* variant 0 = rule-exact direct evaluation for every pair; 1 (default) =
+ * merged-transcendental fast path with the direct path on singular pairs */
+int hb200_set_variant(int variant);
+int hb200_get_variant(void);
+
+/* ---- host-buffer entry points ------------------------------------------- */
+/* replaces jit_prism_gravity, _forward/prisms/gravity.py:489-545, with the
+ * sign/unit post-scaling of :227-235 folded into the epilogue. prisms is
+ * (n_prisms, 6) row-major [w, e, s, n, bottom, top]. */
+int hb200_prism_gravity(const double* easting, const double* northing, const double* upward,
+                        int64_t n_obs, const double* prisms, const double* density,
+                        int64_t n_prisms, uint32_t field_mask, int shard_mode, double* out,
+                        uint32_t* flags);
+
+/* replaces _any_singular_point_g_*, _forward/prisms/gravity.py:272-449:
+ * *flags gets HB200_FLAG_SINGULAR if any pair is singular for `field`. */
+int hb200_prism_singular_scan(const double* easting, const double* northing,
+                              const double* upward, int64_t n_obs, const double* prisms,
+                              int64_t n_prisms, int field, uint32_t* flags);
+
+/* replaces _jit_prism_magnetic_field / _jit_prism_magnetic_component,
+ * _forward/prisms/magnetic.py:275-400, output in nT (:195-197, :271). */
+int hb200_prism_magnetic(const double* easting, const double* northing, const double* upward,
+                         int64_t n_obs, const double* prisms, const double* mag_e,
+                         const double* mag_n, const double* mag_u, int64_t n_prisms,
+                         uint32_t component_mask, uint32_t rules, int shard_mode, double* out,
+                         uint32_t* flags);
+
+/* replaces _forward_gravity_prism_layer, _forward/prisms/layer.py:522-633.
+ * bottom/top/density are (n_north, n_east) row-major; prisms are visited
+ * easting-outer / northing-inner like the reference. */
+int hb200_prism_layer_gravity(const double* easting, const double* northing,
+                              const double* upward, int64_t n_obs, const double* prisms_easting,
+                              int64_t n_east, const double* prisms_northing, int64_t n_north,
+                              const double* bottom, const double* top, const double* density,
+                              double thickness_threshold, uint32_t field_mask, int shard_mode,
+                              double* out, uint32_t* flags);
+
+/* replaces point_mass_cartesian / point_mass_spherical,
+ * _forward/point.py:357-454. spherical != 0: coordinates are longitude,
+ * latitude (degrees), radius; only HB200_POTENTIAL and HB200_G_Z exist. */
+int hb200_point_gravity(const double* easting, const double* northing, const double* upward,
+                        int64_t n_obs, const double* src_easting, const double* src_northing,
+                        const double* src_upward, const double* masses, int64_t n_src,
+                        uint32_t field_mask, int spherical, int shard_mode, double* out,
+                        uint32_t* flags);
+
+/* replaces predict, _equivalent_sources/utils.py:77-101 with
+ * greens_func_cartesian (cartesian.py:634-644): out[i] = sum_j coefs[j] / dist */
+int hb200_eqs_predict(const double* easting, const double* northing, const double* upward,
+                      int64_t n_obs, const double* src_easting, const double* src_northing,
+                      const double* src_upward, const double* coefs, int64_t n_src,
+                      int shard_mode, double* out, uint32_t* flags);
+
+/* replaces jacobian, _equivalent_sources/utils.py:54-74: jac[i*n_src+j] = 1/dist */
+int hb200_eqs_jacobian(const double* easting, const double* northing, const double* upward,
+                       int64_t n_obs, const double* src_easting, const double* src_northing,
+                       const double* src_upward, int64_t n_src, double* jac);
+
+/* ---- device-buffer entry points (current device, async on stream) -------- */
+size_t hb200_prism_ws_bytes(int64_t n_obs, int64_t n_sources, int n_fields);
+int hb200_prism_gravity_dev(const double* easting, const double* northing, const double* upward,
+                            int64_t n_obs, const double* prisms, const double* density,
+                            int64_t n_prisms, uint32_t field_mask, double* out,
+                            uint32_t* flags_dev, void* ws, size_t ws_bytes, void* stream);
+int hb200_prism_magnetic_dev(const double* easting, const double* northing,
+                             const double* upward, int64_t n_obs, const double* prisms,
+                             const double* mag_e, const double* mag_n, const double* mag_u,
+                             int64_t n_prisms, uint32_t component_mask, uint32_t rules,
+                             double* out, uint32_t* flags_dev, void* ws, size_t ws_bytes,
+                             void* stream);
+int hb200_prism_layer_gravity_dev(const double* easting, const double* northing,
+                                  const double* upward, int64_t n_obs,
+                                  const double* prisms_easting, int64_t n_east,
+                                  const double* prisms_northing, int64_t n_north,
+                                  const double* bottom, const double* top, const double* density,
+                                  double thickness_threshold, uint32_t field_mask, double* out,
+                                  uint32_t* flags_dev, void* ws, size_t ws_bytes, void* stream);
+/* weights = masses (scale_by_G != 0) or EQS coefficients (scale_by_G == 0,
+ * field_mask must then be the potential bit: 1/dist) */
+int hb200_point_gravity_dev(const double* easting, const double* northing, const double* upward,
+                            int64_t n_obs, const double* src_easting, const double* src_northing,
+                            const double* src_upward, const double* weights, int64_t n_src,
+                            uint32_t field_mask, int spherical, int scale_by_G, double* out,
+                            uint32_t* flags_dev, void* ws, size_t ws_bytes, void* stream);
+
+/* FP64 FMA issue-rate microbenchmark on the current device: runs `iters`
+ * dependent-chain rounds of 8 independent DFMA chains per thread on every SM
+ * and returns the achieved FP64 FLOP/s (2 flop per DFMA) in *flops. */
+int hb200_fp64_peak(int iters, double* flops, double* seconds);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HARMONICA_B200_H */

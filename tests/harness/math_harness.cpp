@@ -1,0 +1,62 @@
+// tests/harness/math_harness.cpp -- TEST INFRASTRUCTURE.
+// Compiles the product's per-pair math (harmonica_b200/csrc/hb200_math.cuh,
+// hb200_fast.cuh) for the HOST so that the CPU test-suite can check the very
+// statements the CUDA kernels execute against the oracle without a GPU.
+// Never loaded by the product package.
+#include <cstdint>
+#include <cstring>
+
+#include "../../harmonica_b200/csrc/hb200_math.cuh"
+#include "../../harmonica_b200/csrc/hb200_fast.cuh"
+
+using namespace hb;
+
+template <int FS>
+static void pair_fs(int variant, const double* o, const double* p, const double* prm, unsigned rules,
+                    double* acc, unsigned* flags)
+{
+    PairGeom g;
+    make_geom(g, o[0], o[1], o[2], p[0], p[1], p[2], p[3], p[4], p[5]);
+    unsigned f = 0;
+    if (variant == 0 || any_zero_shift(g)) prism_pair_direct<FS>(g, prm, rules, acc, f);
+    else prism_pair_fast<FS>(g, prm, acc);
+    *flags |= f;
+}
+
+static void pair_any(int fs, int variant, const double* o, const double* p, const double* prm,
+                     unsigned rules, double* acc, unsigned* flags)
+{
+    switch (fs) {
+#define C(X) case X: pair_fs<X>(variant, o, p, prm, rules, acc, flags); break;
+        C(F_POT) C(F_E) C(F_N) C(F_U) C(F_EE) C(F_NN) C(F_UU) C(F_EN) C(F_EU) C(F_NU)
+        C(FS_ACC3) C(FS_TENSOR6) C(FS_MAG_B) C(FS_MAG_E) C(FS_MAG_N) C(FS_MAG_U)
+#undef C
+    }
+}
+
+extern "C" {
+
+int hbt_nout(int fs)
+{
+    if (fs == FS_ACC3 || fs == FS_MAG_B) return 3;
+    if (fs == FS_TENSOR6) return 6;
+    return 1;
+}
+
+// out[c * n_obs + i] = sum_j pair(i, j)[c]; prm is (n_prisms, 3) row-major
+void hbt_prism_loop(int fs, int variant, int64_t n_obs, const double* oe, const double* on,
+                    const double* ou, int64_t n_prisms, const double* prisms, const double* prm,
+                    unsigned rules, double* out, unsigned* flags)
+{
+    const int nout = hbt_nout(fs);
+    unsigned f = 0;
+    for (int64_t i = 0; i < n_obs; i++) {
+        double acc[6] = {0, 0, 0, 0, 0, 0};
+        const double o[3] = {oe[i], on[i], ou[i]};
+        for (int64_t j = 0; j < n_prisms; j++)
+            pair_any(fs, variant, o, prisms + 6 * j, prm + 3 * j, rules, acc, &f);
+        for (int c = 0; c < nout; c++) out[c * n_obs + i] = acc[c];
+    }
+    if (flags) *flags = f;
+}
+}

@@ -1,0 +1,369 @@
+"""
+GPU parity tests: the CUDA path (through the public API -> ctypes -> C ABI ->
+kernels) against the CPU oracle and the committed golden fixtures.
+
+Tolerance (north_star): max abs error <= 1e-9 * max|field| (TOL), NaN patterns
+identical. Run with `pytest -m gpu` on a B200.
+"""
+
+import ctypes
+import warnings
+
+import numpy as np
+import numpy.testing as npt
+import pytest
+
+import oracle as O
+from _common import (GRAVITY_FIELDS, TENSOR_FIELDS, TOL, config1, golden, layer_config2, max_rel,
+                     random_prisms)
+
+pytestmark = pytest.mark.gpu
+G = 6.6743e-11
+
+
+@pytest.fixture(params=[1, 0], ids=["merged", "direct"])
+def variant(request, hb):
+    lib = hb._lib.load()
+    lib.hb200_set_variant(request.param)
+    yield request.param
+    lib.hb200_set_variant(1)
+
+
+def quiet(fn, *a, **k):
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return fn(*a, **k)
+
+
+# ------------------------------------------------------------ golden fixtures
+@pytest.mark.parametrize("where", ["above", "any"])
+@pytest.mark.parametrize("field", GRAVITY_FIELDS)
+def test_golden_prism_gravity(hb, variant, field, where):
+    g = golden("prism_gravity_random")
+    coords = tuple(g[f"{where}_{c}"] for c in "enu")
+    got = hb.prism_gravity(coords, g["prisms"], g["density"], field)
+    assert max_rel(got, g[f"{where}_{field}"]) <= TOL
+
+
+@pytest.mark.parametrize("field", GRAVITY_FIELDS)
+def test_golden_singular_suite(hb, variant, field):
+    """observers on vertices, edges, faces, edge extensions, inside (reference values)"""
+    g = golden("prism_singular_suite")
+    coords = (g["easting"], g["northing"], g["upward"])
+    if field in TENSOR_FIELDS:
+        with pytest.warns(UserWarning, match="Found observation point on singular point of a prism."):
+            got = hb.prism_gravity(coords, g["prisms"], g["density"], field)
+    else:
+        with warnings.catch_warnings():
+            warnings.simplefilter("error")
+            got = hb.prism_gravity(coords, g["prisms"], g["density"], field)
+    assert max_rel(got, g[f"two_{field}"]) <= TOL
+    got = quiet(hb.prism_gravity, coords, g["prisms"][0], g["density"][0], field)
+    assert max_rel(got, g[f"one_{field}"]) <= TOL
+
+
+@pytest.mark.parametrize("field", ["b", "b_e", "b_n", "b_u"])
+def test_golden_prism_magnetic(hb, variant, field):
+    for name, key in (("prism_magnetic_random", ""), ("prism_singular_suite", "two_")):
+        g = golden(name)
+        coords = (g["easting"], g["northing"], g["upward"])
+        got = hb.prism_magnetic(coords, g["prisms"], tuple(g["mag"]), field)
+        if field == "b":
+            assert isinstance(got, tuple) and len(got) == 3
+        assert max_rel(np.array(got), g[key + field]) <= TOL
+
+
+@pytest.mark.parametrize("field", GRAVITY_FIELDS + ("g_ne", "g_ze", "g_zn"))
+def test_golden_point_gravity(hb, field):
+    g = golden("point_gravity_random")
+    coords = (g["easting"], g["northing"], g["upward"])
+    got = hb.point_gravity(coords, tuple(g["points"]), g["masses"], field)
+    assert max_rel(got, g[field]) <= TOL
+
+
+@pytest.mark.parametrize("field", ["potential", "g_z"])
+def test_golden_point_gravity_spherical(hb, field):
+    g = golden("point_gravity_random")
+    got = hb.point_gravity(tuple(g["sph_obs"]), tuple(g["sph_points"]), g["masses"], field,
+                           coordinate_system="spherical")
+    assert max_rel(got, g[f"sph_{field}"]) <= TOL
+
+
+def test_golden_point_potential_csv(hb):
+    """the reference's own golden vector, test/test_point_gravity.py:144-154"""
+    g = golden("point_potential_csv")
+    got = hb.point_gravity((g["easting"], g["northing"], g["upward"]), g["point"], g["mass"], "potential")
+    npt.assert_allclose(got, g["potential"])
+
+
+@pytest.mark.parametrize("thr", [("thr0", None), ("thr10", 10.0)])
+@pytest.mark.parametrize("field", GRAVITY_FIELDS)
+def test_golden_prism_layer(hb, variant, field, thr):
+    g = golden("prism_layer")
+    coords = (g["easting"], g["northing"], g["upward"])
+    with pytest.warns(UserWarning, match="Found NaN values in 'density'"):
+        got = hb.prism_layer_gravity(coords, g["east_c"], g["north_c"], g["bottom"], g["top"],
+                                     g["density"], field, thr[1])
+    assert max_rel(got, g[f"{thr[0]}_{field}"]) <= TOL
+
+
+def test_golden_eqs(hb):
+    g = golden("eqs_predict")
+    coords = (g["easting"], g["northing"], g["upward"])
+    assert max_rel(hb.eqs_predict(coords, tuple(g["points"]), g["coefs"]), g["predicted"]) <= TOL
+    npt.assert_allclose(hb.eqs_jacobian(coords, tuple(g["points"])), g["jacobian"], rtol=1e-14)
+    res = np.ones(80)
+    hb.predict_numba_parallel(coords, tuple(g["points"]), g["coefs"], res)
+    assert max_rel(res - 1.0, g["predicted"]) <= 10 * TOL
+    eqs = hb.EquivalentSources(points=tuple(g["points"]), coefs=g["coefs"])
+    assert max_rel(eqs.predict(coords), g["predicted"]) <= TOL
+    eqs32 = hb.EquivalentSources(points=tuple(g["points"]), coefs=g["coefs"], dtype="float32")
+    out32 = eqs32.predict(coords)
+    assert out32.dtype == np.float32
+    npt.assert_allclose(out32, g["predicted"], rtol=2e-4)
+
+
+# ------------------------------------------------ reference doctests / known answers
+def test_reference_doctests_and_slab(hb, variant):
+    """gravity.py:170-193 and test/test_prism.py:269-297 through the CUDA path"""
+    coords = ([-40, 0, 40], [0, 0, 0], [30, 30, 30])
+    gz = hb.prism_gravity(coords, [-34, 5, -18, 14, -345, -146], 2670, field="g_z")
+    assert "({:.5f}, {:.5f}, {:.5f})".format(*gz) == "(0.06552, 0.06629, 0.06174)"
+    gz = hb.prism_gravity(coords, [[-134, -5, -45, 45, -200, -50], [5, 134, -45, 45, -180, -30]],
+                          [-300, 300], field="g_z")
+    assert "({:.5f}, {:.5f}, {:.5f})".format(*gz) == "(-0.05380, 0.02908, 0.11237)"
+    height, thickness, density = 1.5, 10.5, 2670
+    sizes = np.logspace(3, 9, 7)
+    res = np.array([
+        hb.prism_gravity((0, 0, height), [-s / 2, s / 2, -s / 2, s / 2, height - thickness, height],
+                         density, field="g_z") for s in sizes]).ravel()  # fmt: skip
+    analytical = 1e5 * 2 * np.pi * G * density * thickness
+    errors = abs(analytical - res)
+    assert (errors[1:] < errors[:-1]).all()
+    npt.assert_allclose(analytical, res[-1])
+
+
+# ------------------------------------------------------------ seeded vs oracle
+@pytest.fixture(scope="module")
+def medium():
+    coords, prisms, density = config1(1500, 2500, seed=21)
+    # a third of the observers anywhere (below / inside the model)
+    rng = np.random.default_rng(22)
+    coords[2][:800] = rng.uniform(-11e3, 0, 800)
+    return coords, prisms, density
+
+
+@pytest.mark.parametrize("field", GRAVITY_FIELDS)
+def test_prism_gravity_vs_oracle(hb, variant, medium, field):
+    coords, prisms, density = medium
+    got = hb.prism_gravity(coords, prisms, density, field)
+    assert max_rel(got, O.prism_gravity(coords, prisms, density, field)) <= TOL
+
+
+def test_fused_multi_field(hb, variant, medium):
+    coords, prisms, density = medium
+    ten = hb.prism_gravity(coords, prisms, density, TENSOR_FIELDS)
+    acc = hb.prism_gravity(coords, prisms, density, ("g_z", "g_e", "g_n"))
+    for f, got in zip(TENSOR_FIELDS, ten):
+        assert max_rel(got, O.prism_gravity(coords, prisms, density, f)) <= TOL
+    for f, got in zip(("g_z", "g_e", "g_n"), acc):
+        assert max_rel(got, O.prism_gravity(coords, prisms, density, f)) <= TOL
+    mixed = hb.prism_gravity(coords, prisms, density, ("potential", "g_zz"))
+    assert max_rel(mixed[1], O.prism_gravity(coords, prisms, density, "g_zz")) <= TOL
+
+
+def test_prism_magnetic_vs_oracle(hb, variant, medium):
+    coords, prisms, _ = medium
+    rng = np.random.default_rng(23)
+    M = tuple(rng.normal(size=prisms.shape[0]) for _ in range(3))
+    want = np.array(O.prism_magnetic(coords, prisms, M, "b"))
+    assert max_rel(np.array(hb.prism_magnetic(coords, prisms, M, "b")), want) <= TOL
+    for k, f in enumerate(("b_e", "b_n", "b_u")):
+        assert max_rel(hb.prism_magnetic(coords, prisms, M, f), want[k]) <= TOL
+
+
+def test_magnetic_rule_switches(hb):
+    g = golden("prism_singular_suite")
+    coords = (g["easting"], g["northing"], g["upward"])
+    for rules in (0, 1, 2, 3):
+        got = np.array(hb.prism_magnetic(coords, g["prisms"], tuple(g["mag"]), "b", rules=rules))
+        want = np.array(O.prism_magnetic(coords, g["prisms"], tuple(g["mag"]), "b", flags=rules))
+        assert max_rel(got, want) <= TOL
+
+
+def test_point_and_eqs_vs_oracle(hb):
+    rng = np.random.default_rng(24)
+    n_src, n_obs = 3000, 5001
+    pts = (rng.uniform(-5e4, 5e4, n_src), rng.uniform(-5e4, 5e4, n_src), rng.uniform(-5e3, -1e3, n_src))
+    m = rng.uniform(1e6, 1e9, n_src)
+    coords = (rng.uniform(-5e4, 5e4, n_obs), rng.uniform(-5e4, 5e4, n_obs), rng.uniform(0, 500, n_obs))
+    for f in GRAVITY_FIELDS:
+        assert max_rel(hb.point_gravity(coords, pts, m, f), O.point_gravity(coords, pts, m, f)) <= TOL, f
+    coefs = rng.normal(size=n_src)
+    assert max_rel(hb.eqs_predict(coords, pts, coefs), O.eqs_predict(coords, pts, coefs)) <= TOL
+    with pytest.raises(ZeroDivisionError):
+        hb.point_gravity(([pts[0][5]], [pts[1][5]], [pts[2][5]]), pts, m, "potential")
+    with pytest.raises(ZeroDivisionError):
+        hb.eqs_predict(([pts[0][5]], [pts[1][5]], [pts[2][5]]), pts, coefs)
+
+
+def test_layer_vs_oracle_and_flat(hb, variant):
+    """layer.py accessor == oracle layer loop; == prism_gravity(_to_prisms()) (test_prism_layer.py:240-261)"""
+    coords, east_c, north_c, bottom, top, density = layer_config2(n=40, seed=5)
+    sub = tuple(c[::7].copy() for c in coords)
+    layer = hb.PrismLayer((east_c, north_c), np.zeros((40, 40)), 0.0, properties={"density": density})
+    layer.top, layer.bottom = top, bottom
+    for f in GRAVITY_FIELDS:
+        got = quiet(layer.prism_layer.gravity, sub, f)
+        want = O.prism_layer_gravity(sub, east_c, north_c, bottom, top, density, f)
+        assert max_rel(got, want) <= TOL, f
+    # flat: prisms with NaN bounds or NaN/zero density removed by hand
+    prisms = layer._to_prisms()
+    rho = density.ravel()
+    keep = ~(np.isnan(prisms).any(axis=1) | np.isnan(rho))
+    flat = hb.prism_gravity(sub, prisms[keep], rho[keep], "g_z")
+    npt.assert_allclose(quiet(layer.gravity, sub, "g_z"), flat, rtol=1e-9)
+    # observers ON the surface: cell centres (top faces) and cell corners (shared vertical edges)
+    e0, n0 = east_c[10], north_c[12]
+    surf = (np.array([e0, e0 + 100.0]), np.array([n0, n0 + 100.0]), np.array([top[12, 10], top[12, 10]]))
+    if np.isfinite(surf[2]).all():
+        for f in ("g_z", "potential", "g_e"):
+            got = quiet(layer.gravity, surf, f)
+            want = O.prism_layer_gravity(surf, east_c, north_c, bottom, top, density, f)
+            assert max_rel(got, want) <= TOL, f
+
+
+# ----------------------------------------------------------------- edge cases
+def test_shapes_dtypes_and_empty_inputs(hb):
+    prism = [-34, 5, -18, 14, -345, -146]
+    out = hb.prism_gravity((0, 0, 1000), prism, 2670, "g_z")
+    assert out.shape == () and out.dtype == np.float64
+    e, n = np.meshgrid(np.linspace(-50, 50, 6), np.linspace(-40, 40, 4))
+    u = np.full_like(e, 30.0)
+    out = hb.prism_gravity((e, n, u), prism, 2670, "g_z", dtype="float32")
+    assert out.shape == (4, 6) and out.dtype == np.float32
+    npt.assert_allclose(out, O.prism_gravity((e, n, u), prism, 2670, "g_z"), rtol=1e-6)
+    # extra coordinate entries are ignored (coordinates[:3])
+    out4 = hb.prism_gravity((e, n, u, np.zeros_like(e)), prism, 2670, "g_z")
+    npt.assert_array_equal(out4, hb.prism_gravity((e, n, u), prism, 2670, "g_z"))
+    # only null prisms -> exact zeros (gravity.py:452-486)
+    z = hb.prism_gravity((e, n, u), [[0, 0, -1, 1, -2, -1], [-1, 1, -1, 1, -2, -1]], [5.0, 0.0], "g_z")
+    assert (z == 0).all()
+    zb = hb.prism_magnetic((e, n, u), [[-1, 1, -1, 1, -2, -1]], ([0.0], [0.0], [0.0]), "b")
+    assert all((c == 0).all() for c in zb)
+    # no observers
+    assert hb.prism_gravity(([], [], []), prism, 2670, "g_z").shape == (0,)
+    # integer inputs
+    npt.assert_allclose(hb.prism_gravity(([0], [0], [30]), prism, 2670, "g_z"),
+                        O.prism_gravity(([0.0], [0.0], [30.0]), prism, 2670, "g_z"), rtol=1e-12)
+    # disable_checks: an inverted prism gives minus the potential (test_prism.py:139-158)
+    a = hb.prism_gravity((e, n, u), [-100, 100, -100, 100, -200, -100], 1000, "potential")
+    b = hb.prism_gravity((e, n, u), [100, -100, -100, 100, -200, -100], 1000, "potential",
+                         disable_checks=True)
+    npt.assert_allclose(b, -a, rtol=1e-9)
+
+
+def test_singular_warning_rules(hb):
+    """test/test_prism.py:380-502: which points warn for which component"""
+    prism = [-30.0, 50.0, -20.0, 40.0, -80.0, -10.0]
+    w, e, s, n, b, t = prism
+    vertices = [(x, y, z) for x in (w, e) for y in (s, n) for z in (b, t)]
+    for f in TENSOR_FIELDS:
+        for v in vertices:
+            with pytest.warns(UserWarning, match="Found observation point"):
+                assert np.isnan(hb.prism_gravity(v, prism, 2670, f))
+    singular_edges = {"g_ee": ("n", "u"), "g_nn": ("e", "u"), "g_zz": ("e", "n"), "g_en": ("u",),
+                      "g_ez": ("n",), "g_nz": ("e",)}
+    mid = {"e": (10.0, n, t), "n": (e, 10.0, b), "u": (w, s, -45.0)}
+    for f, edges in singular_edges.items():
+        for name, point in mid.items():
+            with warnings.catch_warnings(record=True) as rec:
+                warnings.simplefilter("always")
+                val = hb.prism_gravity(point, prism, 2670, f)
+            warned = any("singular point" in str(r.message) for r in rec)
+            assert warned == (name in edges), (f, name)
+            assert bool(np.isnan(val)) == (name in edges), (f, name)
+    # disable_checks silences the warning but keeps the NaN
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        assert np.isnan(hb.prism_gravity(vertices[0], prism, 2670, "g_zz", disable_checks=True))
+    # a NULL prism still triggers the warning (the scan runs before the discard), value stays finite
+    with pytest.warns(UserWarning, match="Found observation point"):
+        val = hb.prism_gravity(vertices[0], [prism, [-100, -90, 0, 10, -5, -1]], [0.0, 100.0], "g_zz")
+    assert np.isfinite(val)
+
+
+def test_progressbar_gives_identical_results(hb, medium):
+    coords, prisms, density = medium
+    a = hb.prism_gravity(coords, prisms[:200], density[:200], "g_z")
+    b = hb.prism_gravity(coords, prisms[:200], density[:200], "g_z", progressbar=True)
+    npt.assert_array_equal(a, b)
+
+
+def test_few_observers_many_sources_uses_source_chunks(hb, variant):
+    """small N: grid.y splits the source list; partials are reduced in a fixed order"""
+    coords, prisms, density = config1(20000, 37, seed=31)
+    for f in ("g_z", "g_en"):
+        got = hb.prism_gravity(coords, prisms, density, f)
+        assert max_rel(got, O.prism_gravity(coords, prisms, density, f)) <= TOL
+        npt.assert_array_equal(got, hb.prism_gravity(coords, prisms, density, f))  # deterministic
+    got = hb.prism_gravity(coords, prisms, density, "g_z", shard="sources")
+    assert max_rel(got, O.prism_gravity(coords, prisms, density, "g_z")) <= TOL
+
+
+# ---------------------------------------------- BASELINE sizes (properties + samples)
+def test_config1_full_size(hb):
+    """BASELINE config 1: 10k prisms x 10k observers, g_z, against the oracle in full"""
+    coords, prisms, density = config1()
+    got = hb.prism_gravity(coords, prisms, density, "g_z")
+    want = O.prism_gravity(coords, prisms, density, "g_z")
+    assert max_rel(got, want) <= TOL
+
+
+def test_config2_layer_full_size_properties(hb):
+    """BASELINE config 2 (500x500 layer, 250k observers): oracle on an observer sample,
+    linearity in density, and Laplace's equation on the full grid"""
+    coords, east_c, north_c, bottom, top, density = layer_config2()
+    got = quiet(hb.prism_layer_gravity, coords, east_c, north_c, bottom, top, density, "g_z")
+    assert got.shape == (250000,) and np.isfinite(got).all()
+    idx = np.random.default_rng(0).choice(250000, 96, replace=False)
+    sub = tuple(c[idx].copy() for c in coords)
+    want = O.prism_layer_gravity(sub, east_c, north_c, bottom, top, density, "g_z")
+    assert np.max(np.abs(got[idx] - want)) <= TOL * np.max(np.abs(got))
+    twice = quiet(hb.prism_layer_gravity, coords, east_c, north_c, bottom, top, 2 * density, "g_z")
+    npt.assert_allclose(twice, 2 * got, rtol=1e-12)
+    small = tuple(c[::50].copy() for c in coords)
+    d = {f: quiet(hb.prism_layer_gravity, small, east_c, north_c, bottom, top, density, f)
+         for f in ("g_ee", "g_nn", "g_zz")}
+    assert np.max(np.abs(d["g_ee"] + d["g_nn"] + d["g_zz"])) <= 1e-9 * np.max(np.abs(d["g_zz"]))
+
+
+# ------------------------------------------------------- device-buffer entry points
+def test_device_entry_points(hb):
+    torch = pytest.importorskip("torch")
+    lib = hb._lib.load()
+    coords, prisms, density = config1(3000, 4096, seed=41)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    oe, on, ou, pr, rho = t(coords[0]), t(coords[1]), t(coords[2]), t(prisms), t(density)
+    out = torch.empty((6, 4096), dtype=torch.float64, device=dev)
+    flags = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws_bytes = lib.hb200_prism_ws_bytes(4096, 3000, 6)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    rc = lib.hb200_prism_gravity_dev(oe.data_ptr(), on.data_ptr(), ou.data_ptr(), 4096, pr.data_ptr(),
+                                     rho.data_ptr(), 3000, 0x3F0, out.data_ptr(), flags.data_ptr(),
+                                     ws.data_ptr(), ws_bytes, ctypes.c_void_p(stream))
+    assert rc == 0, lib.hb200_last_error()
+    torch.cuda.synchronize()
+    res = out.cpu().numpy()
+    for k, f in enumerate(TENSOR_FIELDS):
+        assert max_rel(res[k], O.prism_gravity(coords, prisms, density, f)) <= TOL
+    assert int(flags.item()) == 0
+
+
+def test_fp64_peak_probe(hb):
+    lib = hb._lib.load()
+    flops, secs = ctypes.c_double(0), ctypes.c_double(0)
+    assert lib.hb200_fp64_peak(2000, ctypes.byref(flops), ctypes.byref(secs)) == 0
+    assert 5e12 < flops.value < 1e14

@@ -1,0 +1,140 @@
+"""
+Host logic of the drop-in package without a GPU: signatures, validation order
+and messages (reference file:line in each test), and the C ABI itself: the
+library loads and exports every symbol include/harmonica_b200.h declares.
+"""
+
+import ctypes
+import inspect
+import os
+import re
+
+import numpy as np
+import pytest
+
+import harmonica_b200 as hb
+from harmonica_b200 import _lib
+from _common import ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "harmonica_b200.h")).read()
+    declared = set(re.findall(r"\b(hb200_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.load()  # binds every symbol; raises AttributeError if one is missing
+    assert lib.hb200_version() >= 100
+    assert isinstance(ctypes.cast(lib.hb200_last_error, ctypes.c_void_p).value, int)
+
+
+def test_no_cpu_fallback_without_gpu():
+    """the product path must fail loudly when no sm_100 device is usable"""
+    lib = _lib.load()
+    if lib.hb200_device_count() > 0:
+        pytest.skip("a B200 is visible")
+    with pytest.raises(hb.HarmonicaB200Error, match="no CPU fallback"):
+        hb.prism_gravity(([0.0], [0.0], [10.0]), [-1, 1, -1, 1, -2, -1], 2670, "g_z")
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "harmonica_b200")
+    for name in os.listdir(pkg):
+        if name.endswith(".py"):
+            src = open(os.path.join(pkg, name)).read()
+            assert "oracle" not in src.replace("the oracle", ""), name
+
+
+def test_signatures_match_the_reference():
+    """gravity.py:51-60, magnetic.py:28-37, point.py:30-38, layer.py:314-323"""
+    def names(fn, n):
+        return list(inspect.signature(fn).parameters)[:n]
+
+    assert names(hb.prism_gravity, 8) == ["coordinates", "prisms", "density", "field", "parallel",
+                                          "dtype", "progressbar", "disable_checks"]
+    assert names(hb.prism_magnetic, 8) == ["coordinates", "prisms", "magnetization", "field",
+                                           "parallel", "dtype", "progressbar", "disable_checks"]
+    assert names(hb.point_gravity, 7) == ["coordinates", "points", "masses", "field",
+                                          "coordinate_system", "parallel", "dtype"]
+    assert names(hb.PrismLayer.gravity, 7) == ["self", "coordinates", "field", "density_name",
+                                               "thickness_threshold", "parallel", "progressbar"]
+    sig = inspect.signature(hb.prism_gravity)
+    assert sig.parameters["dtype"].default == "float64" and sig.parameters["parallel"].default is True
+
+
+COORDS = ([0.0, 10.0], [0.0, 5.0], [10.0, 20.0])
+PRISM = [-1, 1, -1, 1, -2, -1]
+
+
+def test_prism_gravity_errors():
+    """gravity.py:196-198, :208-213, prisms/utils.py:24-43"""
+    with pytest.raises(ValueError, match="Gravitational field g_x not recognized"):
+        hb.prism_gravity(COORDS, PRISM, 2670, "g_x")
+    with pytest.raises(ValueError, match=r"Number of elements in density \(2\) mismatch the number of prisms \(1\)"):
+        hb.prism_gravity(COORDS, PRISM, [1, 2], "g_z")
+    with pytest.raises(ValueError, match="The west boundary can't be greater than the east one"):
+        hb.prism_gravity(COORDS, [1, -1, -1, 1, -2, -1], 2670, "g_z")
+    with pytest.raises(ValueError, match="The south boundary can't be greater than the north one"):
+        hb.prism_gravity(COORDS, [-1, 1, 1, -1, -2, -1], 2670, "g_z")
+    with pytest.raises(ValueError, match="The bottom boundary can't be greater than the top one"):
+        hb.prism_gravity(COORDS, [-1, 1, -1, 1, -1, -2], 2670, "g_z")
+
+
+def test_prism_magnetic_errors():
+    """magnetic.py:103-107, :447-457"""
+    M = ([1.0], [0.0], [2.0])
+    with pytest.raises(ValueError, match="Invalid field 'bz'. Please choose one of 'b,b_e,b_n,b_u'."):
+        hb.prism_magnetic(COORDS, PRISM, M, "bz")
+    with pytest.raises(ValueError, match="Invalid magnetization vectors with '2' elements"):
+        hb.prism_magnetic(COORDS, PRISM, ([1.0], [2.0]), "b")
+    with pytest.raises(ValueError, match=r"Number of magnetization vectors \(2\) mismatch the number of prisms \(1\)"):
+        hb.prism_magnetic(COORDS, PRISM, ([1.0, 1.0], [0.0, 1.0], [2.0, 1.0]), "b")
+    with pytest.raises(ValueError, match="west boundary"):
+        hb.prism_magnetic(COORDS, [1, -1, -1, 1, -2, -1], M, "b_u")
+
+
+def test_point_gravity_errors():
+    """_forward/utils.py:85-87, point.py:243-246, :310-315"""
+    pts, m = ([0.0], [0.0], [-10.0]), [1e6]
+    with pytest.raises(ValueError, match="Coordinate system geodetic not recognized."):
+        hb.point_gravity(COORDS, pts, m, "g_z", coordinate_system="geodetic")
+    with pytest.raises(ValueError, match=r"Number of elements in masses \(2\) mismatch the number of points \(1\)"):
+        hb.point_gravity(COORDS, pts, [1, 2], "g_z")
+    with pytest.raises(ValueError, match="Gravitational field 'g_x' not recognized"):
+        hb.point_gravity(COORDS, pts, m, "g_x")
+    with pytest.raises(ValueError, match="Gravitational field 'g_ee' not recognized"):
+        hb.point_gravity(COORDS, pts, m, "g_ee", coordinate_system="spherical")
+    for f in ("g_n", "g_e"):
+        with pytest.raises(NotImplementedError):
+            hb.point_gravity(COORDS, pts, m, f, coordinate_system="spherical")
+
+
+def test_prism_layer_host_logic():
+    """layer.py:141-154, :264-312, :378, :435-483"""
+    east, north = np.linspace(0, 10, 5), np.linspace(2, 8, 4)
+    surface = np.arange(20, dtype=float).reshape(4, 5)
+    layer = hb.PrismLayer((east, north), surface, 0.0, properties={"density": 2670 * np.ones((4, 5))})
+    assert layer.prism_layer is layer and layer.shape == (4, 5) and layer.size == 20
+    assert [float(b) for b in layer.boundaries] == [-1.25, 11.25, 1.0, 9.0]
+    assert [float(b) for b in layer.get_prism((0, 2))] == [3.75, 6.25, 1.0, 3.0, 0.0, 2.0]
+    prisms = layer._to_prisms()
+    assert prisms.shape == (20, 6) and list(prisms[2]) == [3.75, 6.25, 1.0, 3.0, 0.0, 2.0]
+    layer.update_top_bottom(-surface, 0.0)  # surface below the reference swaps top and bottom
+    assert layer.top.max() == 0.0 and layer.bottom.min() == -19.0
+    with pytest.raises(ValueError, match="Gravitational field 'g_x' not recognized."):
+        layer.gravity(COORDS, "g_x")
+    with pytest.raises(ValueError, match="Passed easting coordinates are not evenly spaced."):
+        hb.PrismLayer((np.array([0.0, 1.0, 3.0]), north), np.zeros((4, 3)), 0.0)
+    with pytest.raises(ValueError, match="Invalid surface array with shape"):
+        hb.PrismLayer((east, north), np.zeros((5, 4)), 0.0)
+
+
+def test_eqs_host_logic():
+    with pytest.raises(ValueError, match="Number of coefficients"):
+        hb.eqs_predict(COORDS, ([0.0], [0.0], [-1.0]), [1.0, 2.0])
+    with pytest.raises(RuntimeError, match="not fitted"):
+        hb.EquivalentSources().predict(COORDS)
+
+
+def test_shard_argument():
+    with pytest.raises(ValueError, match="Invalid shard"):
+        _lib.shard_mode("rows")
+    assert _lib.shard_mode("sources") == _lib.SHARD_SOURCES

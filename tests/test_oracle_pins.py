@@ -1,0 +1,195 @@
+"""
+Pins of the CPU oracle (oracle/choclo_port.c) against every known-answer the
+reference's own tests and docs hold for the hot path, plus
+formula-independent checks. CPU only.
+"""
+
+import numpy as np
+import numpy.testing as npt
+import pytest
+
+import oracle as O
+from _common import GRAVITY_FIELDS, golden
+
+G = 6.6743e-11
+
+
+def test_point_potential_golden_csv():
+    """reference test/test_point_gravity.py:144-154 + test/data/sample_point_gravity.csv"""
+    g = golden("point_potential_csv")
+    got = O.point_gravity((g["easting"], g["northing"], g["upward"]), g["point"], g["mass"], "potential")
+    npt.assert_allclose(got, g["potential"])  # default rtol=1e-7, like the reference
+
+
+def test_prism_gz_doctests():
+    """reference src/harmonica/_forward/prisms/gravity.py:170-193 (5 decimals)"""
+    coords = ([-40, 0, 40], [0, 0, 0], [30, 30, 30])
+    gz = O.prism_gravity(coords, [-34, 5, -18, 14, -345, -146], 2670, "g_z")
+    assert "({:.5f}, {:.5f}, {:.5f})".format(*gz) == "(0.06552, 0.06629, 0.06174)"
+    prisms = [[-134, -5, -45, 45, -200, -50], [5, 134, -45, 45, -180, -30]]
+    gz = O.prism_gravity(coords, prisms, [-300, 300], "g_z")
+    assert "({:.5f}, {:.5f}, {:.5f})".format(*gz) == "(-0.05380, 0.02908, 0.11237)"
+
+
+def test_prism_against_infinite_slab():
+    """reference test/test_prism.py:269-297: observer ON the top face, sizes 1e3..1e9 m"""
+    height, thickness, density = 1.5, 10.5, 2670
+    sizes = np.logspace(3, 9, 7)
+    results = np.array([
+        O.prism_gravity((0, 0, height), [-s / 2, s / 2, -s / 2, s / 2, height - thickness, height],
+                        density, "g_z") for s in sizes]).ravel()  # fmt: skip
+    analytical = 1e5 * 2 * np.pi * G * density * thickness  # _gravity_corrections.py:16-78
+    errors = abs(analytical - results)
+    assert (errors[1:] < errors[:-1]).all()
+    npt.assert_allclose(analytical, results[-1])
+
+
+def test_prism_laplace():
+    """reference test/test_prism.py:247-266"""
+    e, n = np.meshgrid(np.linspace(-10e3, 10e3, 10), np.linspace(-10e3, 10e3, 10))
+    coords = (e, n, np.full_like(e, 300.0))
+    prisms = [[1e3, 7e3, -5e3, 2e3, -1e3, -500], [-4e3, 1e3, 4e3, 10e3, -2e3, 200]]
+    rho = [2670.0, 2900.0]
+    d = {f: O.prism_gravity(coords, prisms, rho, f) for f in ("g_ee", "g_nn", "g_zz")}
+    npt.assert_allclose(d["g_ee"] + d["g_nn"], -d["g_zz"])
+
+
+def test_prism_null_and_inverted():
+    """reference test/test_prism.py:115-158: null prisms contribute nothing; an inverted
+    prism (checks disabled) gives minus the potential"""
+    coords = ([0.0, 30.0], [10.0, -20.0], [50.0, 60.0])
+    p = np.array([[-100, 100, -100, 100, -200, -100.0]])
+    base = O.prism_gravity(coords, p, [1000.0], "potential")
+    both = O.prism_gravity(coords, np.vstack([p, [[5, 5, -1, 1, -3, -2.0]], [[0, 9, 0, 9, -9, -8.0]]]),
+                           [1000.0, 2000.0, 0.0], "potential")
+    npt.assert_array_equal(base, both)
+    inv = O.prism_gravity(coords, [[100, -100, -100, 100, -200, -100.0]], [1000.0], "potential")
+    npt.assert_allclose(inv, -base)
+
+
+@pytest.mark.parametrize("field,dfield,axis", [("g_e", "potential", 0), ("g_n", "potential", 1),
+                                                ("g_z", "potential", 2), ("g_ee", "g_e", 0),
+                                                ("g_en", "g_e", 1), ("g_ez", "g_e", 2),
+                                                ("g_nn", "g_n", 1), ("g_nz", "g_n", 2),
+                                                ("g_zz", "g_z", 2)])  # fmt: skip
+def test_prism_finite_differences(field, dfield, axis):
+    """every kernel is the derivative of the one below it (SURVEY 8c mitigation)"""
+    rng = np.random.default_rng(3)
+    prisms = [[-300, 250, -180, 420, -900, -150.0]]
+    rho = [2670.0]
+    c = np.stack([rng.uniform(-2e3, 2e3, 30), rng.uniform(-2e3, 2e3, 30), rng.uniform(50, 800, 30)])
+    h = 0.05
+    cp, cm = c.copy(), c.copy()
+    cp[axis] += h
+    cm[axis] -= h
+    fd = (O.prism_gravity(tuple(cp), prisms, rho, dfield) - O.prism_gravity(tuple(cm), prisms, rho, dfield)) / (2 * h)
+    unit = {"potential": 1.0, "g_e": 1e-5, "g_n": 1e-5, "g_z": 1e-5}[dfield]
+    out_unit = 1e5 if field in ("g_e", "g_n", "g_z") else 1e9
+    fd = fd * unit * out_unit
+    # harmonica's z points down: d/dz_down = -d/du; g_z itself is already "down"
+    if axis == 2:
+        fd = -fd
+    got = O.prism_gravity(tuple(c), prisms, rho, field)
+    npt.assert_allclose(got, fd, rtol=2e-6, atol=1e-9 * np.max(np.abs(got)))
+
+
+def test_prism_potential_against_quadrature():
+    """formula-independent pin: potential == G rho * triple integral of 1/r (mpmath)"""
+    mpmath = pytest.importorskip("mpmath")
+    mpmath.mp.dps = 20
+    w, e, s, n, b, t = -30.0, 50.0, -20.0, 40.0, -80.0, -10.0
+    E, N, U = 120.0, -75.0, 60.0
+    val = mpmath.quad(lambda x, y, z: 1 / mpmath.sqrt((x - E) ** 2 + (y - N) ** 2 + (z - U) ** 2),
+                      [w, e], [s, n], [b, t])
+    want = float(val) * G * 2670.0
+    got = float(O.prism_gravity((E, N, U), [w, e, s, n, b, t], 2670.0, "potential"))
+    npt.assert_allclose(got, want, rtol=1e-10)
+
+
+def test_tensor_face_rule_is_outside_limit():
+    """gravity.py:153-158: on a face normal to a diagonal component the outside limit is returned"""
+    prism = [-30.0, 50.0, -20.0, 40.0, -80.0, -10.0]
+    eps = 1e-6
+    for field, on, off in (("g_ee", (50.0, 5.0, -40.0), (50.0 + eps, 5.0, -40.0)),
+                           ("g_ee", (-30.0, 5.0, -40.0), (-30.0 - eps, 5.0, -40.0)),
+                           ("g_nn", (7.0, 40.0, -40.0), (7.0, 40.0 + eps, -40.0)),
+                           ("g_nn", (7.0, -20.0, -40.0), (7.0, -20.0 - eps, -40.0)),
+                           ("g_zz", (7.0, 5.0, -10.0), (7.0, 5.0, -10.0 + eps)),
+                           ("g_zz", (7.0, 5.0, -80.0), (7.0, 5.0, -80.0 - eps))):  # fmt: skip
+        a = float(O.prism_gravity(on, prism, 2670.0, field))
+        b_ = float(O.prism_gravity(off, prism, 2670.0, field))
+        npt.assert_allclose(a, b_, rtol=1e-5)
+
+
+def test_tensor_nan_on_singular_points_and_warning_predicate():
+    """test/test_prism.py:380-502: vertices are singular for every tensor component"""
+    prism = np.array([[-30.0, 50.0, -20.0, 40.0, -80.0, -10.0]])
+    vertex = (50.0, 40.0, -10.0)
+    for f in GRAVITY_FIELDS[4:]:
+        assert np.isnan(O.prism_gravity(vertex, prism, 2670.0, f))
+        assert O.any_singular(vertex, prism, f)
+    for f in GRAVITY_FIELDS[:4]:
+        assert np.isfinite(O.prism_gravity(vertex, prism, 2670.0, f))
+    # mid-point of an edge parallel to upward: singular for ee, nn, en only
+    edge = (50.0, 40.0, -45.0)
+    sing = {f: bool(np.isnan(O.prism_gravity(edge, prism, 2670.0, f))) for f in GRAVITY_FIELDS[4:]}
+    assert sing == {"g_ee": True, "g_nn": True, "g_zz": False, "g_en": True, "g_ez": False, "g_nz": False}
+
+
+def test_magnetic_far_field_is_dipole():
+    """prism -> dipole with moment M*V far away (SURVEY 8a K4 far-field check)"""
+    prism = [-1.0, 1.0, -1.5, 1.5, -2.0, 2.0]
+    M = (np.array([1.3]), np.array([-0.4]), np.array([2.2]))
+    vol = 2 * 3 * 4
+    r = np.array([800.0, -500.0, 300.0])
+    b = np.array(O.prism_magnetic(tuple(r), prism, M, "b")).ravel()
+    m = np.array([M[0][0], M[1][0], M[2][0]]) * vol
+    rn = np.linalg.norm(r)
+    dip = 1e-7 * (3 * r * (m @ r) / rn**5 - m / rn**3) * 1e9
+    npt.assert_allclose(b, dip, rtol=1e-4)
+
+
+def test_magnetic_poisson_relation():
+    """B = (mu0/4pi)/(G rho) * (grad grad V) . M  ties magnetics to the pinned gravity tensor"""
+    rng = np.random.default_rng(5)
+    prism = [-30.0, 50.0, -20.0, 40.0, -80.0, -10.0]
+    c = (rng.uniform(-300, 300, 20), rng.uniform(-300, 300, 20), rng.uniform(5, 200, 20))
+    M = np.array([0.7, -1.1, 0.4])
+    T = {f: O.prism_gravity_si(tuple(np.ascontiguousarray(x) for x in c), np.array([prism]), np.array([1.0]), f) / G
+         for f in GRAVITY_FIELDS[4:]}
+    be = M[0] * T["g_ee"] + M[1] * T["g_en"] + M[2] * T["g_ez"]
+    bn = M[0] * T["g_en"] + M[1] * T["g_nn"] + M[2] * T["g_nz"]
+    bu = M[0] * T["g_ez"] + M[1] * T["g_nz"] + M[2] * T["g_zz"]
+    got = np.array(O.prism_magnetic(c, prism, tuple(np.array([m]) for m in M), "b"))
+    npt.assert_allclose(got, np.stack([be, bn, bu]) * 1e-7 * 1e9, rtol=1e-9, atol=0)
+
+
+def test_point_symmetry_and_laplace():
+    """test/test_point_gravity.py:354-395"""
+    rng = np.random.default_rng(7)
+    c = (rng.uniform(-1e3, 1e3, 40), rng.uniform(-1e3, 1e3, 40), rng.uniform(10, 500, 40))
+    pts = ([0.0, 50.0], [10.0, -30.0], [-100.0, -300.0])
+    m = [1e8, 3e8]
+    d = {f: O.point_gravity(c, pts, m, f) for f in ("g_ee", "g_nn", "g_zz", "g_en", "g_ne", "g_ez", "g_ze")}
+    npt.assert_allclose(d["g_ee"] + d["g_nn"], -d["g_zz"], atol=1e-9 * np.max(np.abs(d["g_zz"])))
+    npt.assert_array_equal(d["g_en"], d["g_ne"])
+    npt.assert_array_equal(d["g_ez"], d["g_ze"])
+
+
+def test_point_spherical_analytic():
+    """test/test_point_gravity.py:656-768: same-radial configuration has a closed form"""
+    radius_p, mass = 6.0e6, 1e12
+    radius = np.array([6.3e6, 6.5e6, 7.0e6])
+    lon, lat = np.full(3, 13.0), np.full(3, -42.0)
+    pot = O.point_gravity((lon, lat, radius), ([13.0], [-42.0], [radius_p]), [mass], "potential", "spherical")
+    gz = O.point_gravity((lon, lat, radius), ([13.0], [-42.0], [radius_p]), [mass], "g_z", "spherical")
+    npt.assert_allclose(pot, G * mass / (radius - radius_p), rtol=1e-9)
+    npt.assert_allclose(gz, 1e5 * G * mass / (radius - radius_p) ** 2, rtol=1e-8)
+
+
+def test_point_zero_distance_raises():
+    """the reference's jitted loop raises ZeroDivisionError on a coincident pair"""
+    with pytest.raises(ZeroDivisionError):
+        O.point_gravity(([0.0], [0.0], [0.0]), ([0.0], [0.0], [0.0]), [1.0], "potential")
+    with pytest.raises(ZeroDivisionError):
+        O.eqs_predict(([1.0], [2.0], [3.0]), ([1.0], [2.0], [3.0]), [1.0])

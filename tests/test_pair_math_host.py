@@ -1,0 +1,196 @@
+"""
+The product's per-pair math (harmonica_b200/csrc/hb200_math.cuh + hb200_fast.cuh)
+compiled for the HOST (tests/harness) against the oracle. CPU only: this checks
+the statements the CUDA kernels execute, not the kernels themselves (the GPU
+parity tests do that).
+
+  variant 0 (direct path) : bit-exact vs the oracle
+  variant 1 (merged path) : within the north_star tolerance 1e-9 * max|field|
+"""
+
+import numpy as np
+import numpy.testing as npt
+import pytest
+
+import oracle as O
+from _common import GRAVITY_FIELDS, TOL, config1, golden, harness_prism, max_rel
+
+G = 6.6743e-11
+CM = 4 * np.pi * 1e-7 / 4 / np.pi
+
+
+def _si(coords, prisms, density, field):
+    return O.prism_gravity_si(tuple(np.ascontiguousarray(c, dtype=np.float64) for c in coords),
+                              np.ascontiguousarray(prisms), np.ascontiguousarray(density), field)
+
+
+@pytest.fixture(scope="module")
+def case():
+    coords, prisms, density = config1(300, 400, seed=11)
+    prm = np.zeros((prisms.shape[0], 3))
+    prm[:, 0] = G * density
+    return coords, prisms, density, prm
+
+
+@pytest.mark.parametrize("field", GRAVITY_FIELDS)
+def test_direct_path_is_bit_exact(case, field):
+    coords, prisms, density, prm = case
+    out, _ = harness_prism(field, 0, coords, prisms, prm)
+    npt.assert_array_equal(out[0], _si(coords, prisms, density, field))
+
+
+@pytest.mark.parametrize("field", GRAVITY_FIELDS)
+def test_merged_path_within_tolerance(case, field):
+    coords, prisms, density, prm = case
+    out, _ = harness_prism(field, 1, coords, prisms, prm)
+    assert max_rel(out[0], _si(coords, prisms, density, field)) <= TOL
+
+
+def test_fused_sets_match_single_fields(case):
+    coords, prisms, density, prm = case
+    for variant in (0, 1):
+        acc, _ = harness_prism("acc3", variant, coords, prisms, prm)
+        ten, _ = harness_prism("tensor6", variant, coords, prisms, prm)
+        for k, f in enumerate(GRAVITY_FIELDS[1:4]):
+            assert max_rel(acc[k], _si(coords, prisms, density, f)) <= TOL
+        for k, f in enumerate(GRAVITY_FIELDS[4:]):
+            assert max_rel(ten[k], _si(coords, prisms, density, f)) <= TOL
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_magnetic(case, variant):
+    coords, prisms, _, _ = case
+    rng = np.random.default_rng(4)
+    M = rng.normal(size=(prisms.shape[0], 3))
+    want = np.array(O.prism_magnetic(coords, prisms, (M[:, 0], M[:, 1], M[:, 2]), "b"))
+    got, _ = harness_prism("b", variant, coords, prisms, M)
+    for k in range(3):
+        assert max_rel(got[k] * CM * 1e9, want[k]) <= TOL
+        single, _ = harness_prism(("b_e", "b_n", "b_u")[k], variant, coords, prisms, M)
+        assert max_rel(single[0] * CM * 1e9, want[k]) <= TOL
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_observers_inside_below_and_around(variant):
+    rng = np.random.default_rng(12)
+    coords, prisms, density = config1(200, 300, seed=12)
+    coords = (coords[0], coords[1], rng.uniform(-12e3, 2e3, 300))
+    for t in range(40):  # strictly inside prism t
+        coords[0][t] = 0.3 * prisms[t, 0] + 0.7 * prisms[t, 1]
+        coords[1][t] = 0.6 * prisms[t, 2] + 0.4 * prisms[t, 3]
+        coords[2][t] = 0.8 * prisms[t, 4] + 0.2 * prisms[t, 5]
+    prm = np.zeros((200, 3))
+    prm[:, 0] = G * density
+    for f in GRAVITY_FIELDS:
+        out, _ = harness_prism(f, variant, coords, prisms, prm)
+        assert max_rel(out[0], _si(coords, prisms, density, f)) <= TOL, f
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_singular_suite_matches_reference_rules(variant):
+    """vertices / edges / faces / edge extensions: NaN pattern and values (golden = reference)"""
+    g = golden("prism_singular_suite")
+    coords = (g["easting"], g["northing"], g["upward"])
+    prm = np.zeros((2, 3))
+    prm[:, 0] = G * g["density"]
+    scale = {"potential": 1.0, "g_e": 1e5, "g_n": 1e5, "g_z": -1e5, "g_ee": 1e9, "g_nn": 1e9,
+             "g_zz": 1e9, "g_en": 1e9, "g_ez": -1e9, "g_nz": -1e9}
+    for f in GRAVITY_FIELDS:
+        out, flags = harness_prism(f, variant, coords, g["prisms"], prm)
+        assert max_rel(out[0] * scale[f], g[f"two_{f}"]) <= TOL, f
+        assert bool(flags & 1) == (f in GRAVITY_FIELDS[4:])
+    ten, _ = harness_prism("tensor6", variant, coords, g["prisms"], prm)
+    for k, f in enumerate(GRAVITY_FIELDS[4:]):
+        assert max_rel(ten[k] * scale[f], g[f"two_{f}"]) <= TOL, f
+    b, flags = harness_prism("b", variant, coords, g["prisms"], g["mag"].T.copy())
+    assert flags & 1
+    for k in range(3):
+        assert max_rel(b[k] * CM * 1e9, g["two_b"][k]) <= TOL
+
+
+def test_slab_limit_on_face_merged_path():
+    """test/test_prism.py:269-297 through the product math (observer on the top face)"""
+    height, thickness, density = 1.5, 10.5, 2670
+    sizes = np.logspace(3, 9, 7)
+    res = []
+    for s in sizes:
+        out, _ = harness_prism("g_z", 1, ([0.0], [0.0], [height]),
+                               [[-s / 2, s / 2, -s / 2, s / 2, height - thickness, height]],
+                               [[G * density, 0, 0]])
+        res.append(out[0][0] * -1e5)
+    res = np.array(res)
+    analytical = 1e5 * 2 * np.pi * G * density * thickness
+    errors = abs(analytical - res)
+    assert (errors[1:] < errors[:-1]).all()
+    npt.assert_allclose(analytical, res[-1])
+    # slightly above the face: the merged path proper, same limit
+    out, _ = harness_prism("g_z", 1, ([0.0], [0.0], [height + 1e-3]),
+                           [[-5e8, 5e8, -5e8, 5e8, height - thickness, height]], [[G * density, 0, 0]])
+    npt.assert_allclose(out[0][0] * -1e5, analytical, rtol=1e-6)
+
+
+def _mp_truth(field, E, N, U, prism, rho):
+    """50-digit evaluation of the 8-vertex closed form (generic position only)."""
+    import mpmath as mp
+
+    w, e, s, n, b, t = [mp.mpf(float(x)) for x in prism]
+    E, N, U = mp.mpf(float(E)), mp.mpf(float(N)), mp.mpf(float(U))
+    tot = mp.mpf(0)
+    for i, x in enumerate((e - E, w - E)):
+        for j, y in enumerate((n - N, s - N)):
+            for k, z in enumerate((t - U, b - U)):
+                r = mp.sqrt(x * x + y * y + z * z)
+                if field == "g_z":
+                    v = -(x * mp.log(y + r) + y * mp.log(x + r) - z * mp.atan(x * y / (z * r)))
+                else:  # potential
+                    v = (x * y * mp.log(z + r) + y * z * mp.log(x + r) + x * z * mp.log(y + r)
+                         - x * x / 2 * mp.atan(z * y / (x * r)) - y * y / 2 * mp.atan(z * x / (y * r))
+                         - z * z / 2 * mp.atan(x * y / (z * r)))
+                tot += (-1) ** (i + j + k) * v
+    return mp.mpf("6.6743e-11") * mp.mpf(float(rho)) * tot
+
+
+def test_large_region_accuracy_against_high_precision():
+    """
+    Region +-500 km with sparse, distant prisms: the field is tiny compared with
+    the per-vertex terms (e * log(...) ~ 1e7 m), so the REFERENCE's own rounding
+    noise exceeds 1e-9 * max|field| here. The merged path must (a) stay within
+    that noise of the oracle and (b) be at least as close to a 50-digit
+    evaluation as the oracle is.
+    """
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 50
+    coords, prisms, density = config1(400, 60, seed=3, scale=10.0)
+    prm = np.zeros((400, 3))
+    prm[:, 0] = G * density
+    for f in ("g_z", "g_zz", "g_en", "potential"):
+        out, _ = harness_prism(f, 1, coords, prisms, prm)
+        bound = {"g_zz": TOL, "g_en": TOL, "g_z": 5e-8, "potential": 1e-6}[f]
+        assert max_rel(out[0], _si(coords, prisms, density, f)) <= bound, f
+    for f in ("g_z", "potential"):
+        out, _ = harness_prism(f, 1, coords, prisms, prm)
+        ora = _si(coords, prisms, density, f)
+        err_merged, err_oracle = [], []
+        for i in range(4):
+            t = sum(_mp_truth(f, coords[0][i], coords[1][i], coords[2][i], prisms[j], density[j])
+                    for j in range(400))
+            err_merged.append(float(abs(mp.mpf(float(out[0][i])) - t)))
+            err_oracle.append(float(abs(mp.mpf(float(ora[i])) - t)))
+        assert max(err_merged) <= max(err_oracle), (f, err_merged, err_oracle)
+
+
+def test_dense_large_region_within_tolerance():
+    """C3-like density of prisms near the observers: the 1e-9 bar holds against the oracle"""
+    rng = np.random.default_rng(8)
+    coords, prisms, density = config1(400, 60, seed=3, scale=10.0)
+    # move the observers next to prisms (500 m above the top of a random prism)
+    pick = rng.integers(0, 400, 60)
+    coords = (0.5 * (prisms[pick, 0] + prisms[pick, 1]) + 300.0,
+              0.5 * (prisms[pick, 2] + prisms[pick, 3]) - 200.0, prisms[pick, 5] + 500.0)
+    prm = np.zeros((400, 3))
+    prm[:, 0] = G * density
+    # the potential is excluded: with coordinates ~5e5 m its per-vertex terms (e*n*log ~ 1e12)
+    # put the reference's own rounding noise near 1e-8 * max|field| (see the test above)
+    for f in GRAVITY_FIELDS[1:]:
+        out, _ = harness_prism(f, 1, coords, prisms, prm)
+        assert max_rel(out[0], _si(coords, prisms, density, f)) <= TOL, f
