@@ -54,6 +54,9 @@ def make_workload(name, n_obs, n_src, rank):
         coords, east_c, north_c, bottom, top, density = layer_config2()
         # weak scaling: every rank owns its own 500x500 observation grid (a different height)
         coords = (coords[0], coords[1], coords[2] + 25.0 * rank)
+        if n_obs:  # profiling runs: a strided subset of the observation grid
+            pick = np.linspace(0, coords[0].size - 1, n_obs).astype(np.int64)
+            coords = tuple(np.ascontiguousarray(c[pick]) for c in coords)
         return dict(kind="layer", coords=coords, east_c=east_c, north_c=north_c, bottom=bottom,
                     top=top, density=density, n_src=east_c.size * north_c.size, mask=1 << 3,
                     nf=1, desc="prism_layer.gravity g_z, 500x500 layer (250k prisms, 1% NaN, "
