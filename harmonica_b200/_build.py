@@ -9,6 +9,8 @@ SOURCES = [os.path.join(_HERE, "csrc", "hb200_api.cu")]
 HEADERS = [
     os.path.join(_HERE, "csrc", "hb200_math.cuh"),
     os.path.join(_HERE, "csrc", "hb200_fast.cuh"),
+    os.path.join(_HERE, "csrc", "hb200_xmath.cuh"),
+    os.path.join(_HERE, "csrc", "hb200_tables.h"),
     os.path.join(_HERE, "csrc", "hb200_kernels.cuh"),
     os.path.join(os.path.dirname(_HERE), "include", "harmonica_b200.h"),
 ]

@@ -25,7 +25,7 @@ namespace {
 
 thread_local std::string g_err;
 std::mutex g_mu;
-int g_variant = 1;
+int g_variant = 2;
 
 int fail(int code, const char* fmt, ...)
 {
@@ -149,7 +149,8 @@ int choose_chunks(int64_t n_obs, int64_t n_src, int obs_per_block, int sms, int6
 template <int FS> void launch_prism_fs(const PrismArgs& a, dim3 grid, cudaStream_t st)
 {
     if (g_variant == 0) prism_kernel<FS, 0><<<grid, kBlock, 0, st>>>(a);
-    else prism_kernel<FS, 1><<<grid, kBlock, 0, st>>>(a);
+    else if (g_variant == 1) prism_kernel<FS, 1><<<grid, kBlock, 0, st>>>(a);
+    else prism_kernel<FS, 2><<<grid, kBlock, 0, st>>>(a);
 }
 
 void launch_prism_any(int fs, const PrismArgs& a, dim3 grid, cudaStream_t st)
@@ -635,7 +636,7 @@ int hb200_device_count(void)
 
 int hb200_set_variant(int variant)
 {
-    if (variant != 0 && variant != 1) return fail(HB200_EINVAL, "variant must be 0 or 1");
+    if (variant < 0 || variant > 2) return fail(HB200_EINVAL, "variant must be 0, 1 or 2");
     g_variant = variant;
     return HB200_OK;
 }

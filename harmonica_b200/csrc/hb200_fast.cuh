@@ -22,8 +22,20 @@
 // g_z: 16 log + 8 atan + 24 div per pair  ->  4 log + 4 atan2 + 4 div.
 #pragma once
 #include "hb200_math.cuh"
+#include "hb200_xmath.cuh"
 
 namespace hb {
+
+// XM = false: CUDA libm; XM = true: the sequences of hb200_xmath.cuh
+template <bool XM> HB_HD double x_sqrt(double x) { return XM ? fast_sqrt(x) : sqrt(x); }
+template <bool XM> HB_HD double x_log_ratio(double top, double bot)
+{
+    return XM ? fast_log(top * fast_rcp(bot)) : log(top / bot);
+}
+template <bool XM> HB_HD double x_atan2(double y, double x)
+{
+    return XM ? fast_atan2(y, x) : atan2(y, x);
+}
 
 HB_HD bool is_neg(double x)
 {
@@ -52,7 +64,7 @@ struct FastCtx {
     double r[2][2][2];
 };
 
-template <int FS> HB_HD void make_fast_ctx(FastCtx& c, const PairGeom& g)
+template <int FS, bool XM> HB_HD void make_fast_ctx(FastCtx& c, const PairGeom& g)
 {
     typedef Traits<FS> T;
 #pragma unroll
@@ -73,7 +85,7 @@ template <int FS> HB_HD void make_fast_ctx(FastCtx& c, const PairGeom& g)
 #pragma unroll
         for (int j = 0; j < 2; j++)
 #pragma unroll
-            for (int k = 0; k < 2; k++) c.r[i][j][k] = sqrt(add_rn(c.en2[i][j], g.su2[k]));
+            for (int k = 0; k < 2; k++) c.r[i][j][k] = x_sqrt<XM>(add_rn(c.en2[i][j], g.su2[k]));
 }
 
 // (num, den) of safe_log type X (0: x = e, 1: x = n, 2: x = u) at vertex ijk
@@ -116,24 +128,24 @@ HB_HD void log_group4_tb(const FastCtx& c, int f, double& top, double& bot)
 }
 
 // sum_{a,b} (-1)^(a+b) L^X over the 4 vertices with index f on axis F
-template <int X, int F> HB_HD double log_group4(const FastCtx& c, int f)
+template <int X, int F, bool XM> HB_HD double log_group4(const FastCtx& c, int f)
 {
     double top, bot;
     log_group4_tb<X, F>(c, f, top, bot);
-    return log(top / bot);
+    return x_log_ratio<XM>(top, bot);
 }
 
 // sum over all 8 vertices of s_ijk L^X
-template <int X> HB_HD double log_sum8(const FastCtx& c)
+template <int X, bool XM> HB_HD double log_sum8(const FastCtx& c)
 {
     double t0, b0, t1, b1;
     log_group4_tb<X, 0>(c, 0, t0, b0);
     log_group4_tb<X, 0>(c, 1, t1, b1);
-    return log((t0 * b1) / (b0 * t1));
+    return x_log_ratio<XM>(t0 * b1, b0 * t1);
 }
 
 // L^X(x_0) - L^X(x_1) along X's own axis; (a, b) = the other two indices in axis order
-template <int X> HB_HD double log_pair(const FastCtx& c, int a, int b)
+template <int X, bool XM> HB_HD double log_pair(const FastCtx& c, int a, int b)
 {
     int i, j, k;
     double n0, d0, n1, d1;
@@ -141,12 +153,12 @@ template <int X> HB_HD double log_pair(const FastCtx& c, int a, int b)
     log_nd<X>(c, i, j, k, n0, d0);
     ijk_of<X>(1, a, b, i, j, k);
     log_nd<X>(c, i, j, k, n1, d1);
-    return log((n0 * d1) / (n1 * d0));
+    return x_log_ratio<XM>(n0 * d1, n1 * d0);
 }
 
 // S[f] = sum over the 4 vertices with index f on axis X of (-1)^(b+c) A^X, where
 // A^X = atan(b c / (a r)), a = shift on axis X. Two atan2 per call.
-template <int X> HB_HD double atan_sum4(const FastCtx& c, int f)
+template <int X, bool XM> HB_HD double atan_sum4(const FastCtx& c, int f)
 {
     const double a = (X == 0) ? c.se[f] : (X == 1) ? c.sn[f] : c.su[f];
     const double a2 = (X == 0) ? c.se2[f] : (X == 1) ? c.sn2[f] : c.su2[f];
@@ -166,33 +178,34 @@ template <int X> HB_HD double atan_sum4(const FastCtx& c, int f)
         const double r1 = c.r[i][j][k];
         const double im = (cc * a) * (b0 * r1 - b1 * r0);
         const double re = a2 * (r0 * r1) + b0b1 * cc2;
-        D[m] = atan2(im, re);
+        D[m] = x_atan2<XM>(im, re);
     }
     return D[0] - D[1];
 }
 
-template <int FS> HB_HD void prism_pair_fast(const PairGeom& g, const double* prm, double* acc)
+template <int FS, bool XM>
+HB_HD void prism_pair_fast(const PairGeom& g, const double* prm, double* acc)
 {
     typedef Traits<FS> T;
     FastCtx c;
-    make_fast_ctx<FS>(c, g);
+    make_fast_ctx<FS, XM>(c, g);
     const double* e = c.se;
     const double* n = c.sn;
     const double* u = c.su;
     if (FS == F_U) {
-        const double v = e[0] * log_group4<1, 0>(c, 0) - e[1] * log_group4<1, 0>(c, 1)
-                       + n[0] * log_group4<0, 1>(c, 0) - n[1] * log_group4<0, 1>(c, 1)
-                       - (u[0] * atan_sum4<2>(c, 0) - u[1] * atan_sum4<2>(c, 1));
+        const double v = e[0] * log_group4<1, 0, XM>(c, 0) - e[1] * log_group4<1, 0, XM>(c, 1)
+                       + n[0] * log_group4<0, 1, XM>(c, 0) - n[1] * log_group4<0, 1, XM>(c, 1)
+                       - (u[0] * atan_sum4<2, XM>(c, 0) - u[1] * atan_sum4<2, XM>(c, 1));
         acc[0] += prm[0] * -v;
     } else if (FS == F_E) {
-        const double v = n[0] * log_group4<2, 1>(c, 0) - n[1] * log_group4<2, 1>(c, 1)
-                       + u[0] * log_group4<1, 2>(c, 0) - u[1] * log_group4<1, 2>(c, 1)
-                       - (e[0] * atan_sum4<0>(c, 0) - e[1] * atan_sum4<0>(c, 1));
+        const double v = n[0] * log_group4<2, 1, XM>(c, 0) - n[1] * log_group4<2, 1, XM>(c, 1)
+                       + u[0] * log_group4<1, 2, XM>(c, 0) - u[1] * log_group4<1, 2, XM>(c, 1)
+                       - (e[0] * atan_sum4<0, XM>(c, 0) - e[1] * atan_sum4<0, XM>(c, 1));
         acc[0] += prm[0] * -v;
     } else if (FS == F_N) {
-        const double v = u[0] * log_group4<0, 2>(c, 0) - u[1] * log_group4<0, 2>(c, 1)
-                       + e[0] * log_group4<2, 0>(c, 0) - e[1] * log_group4<2, 0>(c, 1)
-                       - (n[0] * atan_sum4<1>(c, 0) - n[1] * atan_sum4<1>(c, 1));
+        const double v = u[0] * log_group4<0, 2, XM>(c, 0) - u[1] * log_group4<0, 2, XM>(c, 1)
+                       + e[0] * log_group4<2, 0, XM>(c, 0) - e[1] * log_group4<2, 0, XM>(c, 1)
+                       - (n[0] * atan_sum4<1, XM>(c, 0) - n[1] * atan_sum4<1, XM>(c, 1));
         acc[0] += prm[0] * -v;
     } else if (FS == F_POT || FS == FS_ACC3) {
         double Pu[2][2], Pe[2][2], Pn[2][2], SA[3][2];
@@ -200,15 +213,15 @@ template <int FS> HB_HD void prism_pair_fast(const PairGeom& g, const double* pr
         for (int a = 0; a < 2; a++)
 #pragma unroll
             for (int b = 0; b < 2; b++) {
-                Pu[a][b] = log_pair<2>(c, a, b);  // [i][j]
-                Pe[a][b] = log_pair<0>(c, a, b);  // [j][k]
-                Pn[a][b] = log_pair<1>(c, a, b);  // [i][k]
+                Pu[a][b] = log_pair<2, XM>(c, a, b);  // [i][j]
+                Pe[a][b] = log_pair<0, XM>(c, a, b);  // [j][k]
+                Pn[a][b] = log_pair<1, XM>(c, a, b);  // [i][k]
             }
 #pragma unroll
         for (int f = 0; f < 2; f++) {
-            SA[0][f] = atan_sum4<0>(c, f);
-            SA[1][f] = atan_sum4<1>(c, f);
-            SA[2][f] = atan_sum4<2>(c, f);
+            SA[0][f] = atan_sum4<0, XM>(c, f);
+            SA[1][f] = atan_sum4<1, XM>(c, f);
+            SA[2][f] = atan_sum4<2, XM>(c, f);
         }
         if (FS == F_POT) {
             double v = 0.0;
@@ -244,12 +257,12 @@ template <int FS> HB_HD void prism_pair_fast(const PairGeom& g, const double* pr
     } else {
         // second-derivative kernels: tensor components and magnetics
         double kee = 0, knn = 0, kuu = 0, ken = 0, keu = 0, knu = 0;
-        if (T::ae) kee = -(atan_sum4<0>(c, 0) - atan_sum4<0>(c, 1));
-        if (T::an) knn = -(atan_sum4<1>(c, 0) - atan_sum4<1>(c, 1));
-        if (T::au) kuu = -(atan_sum4<2>(c, 0) - atan_sum4<2>(c, 1));
-        if (T::lu) ken = log_sum8<2>(c);
-        if (T::ln) keu = log_sum8<1>(c);
-        if (T::le) knu = log_sum8<0>(c);
+        if (T::ae) kee = -(atan_sum4<0, XM>(c, 0) - atan_sum4<0, XM>(c, 1));
+        if (T::an) knn = -(atan_sum4<1, XM>(c, 0) - atan_sum4<1, XM>(c, 1));
+        if (T::au) kuu = -(atan_sum4<2, XM>(c, 0) - atan_sum4<2, XM>(c, 1));
+        if (T::lu) ken = log_sum8<2, XM>(c);
+        if (T::ln) keu = log_sum8<1, XM>(c);
+        if (T::le) knu = log_sum8<0, XM>(c);
         if (FS == F_EE) acc[0] += prm[0] * kee;
         else if (FS == F_NN) acc[0] += prm[0] * knn;
         else if (FS == F_UU) acc[0] += prm[0] * kuu;

@@ -19,7 +19,7 @@
 #include <stdint.h>
 
 #if defined(__CUDACC__)
-#define HB_HD __host__ __device__ __forceinline__
+#define HB_HD __device__ __forceinline__
 #else
 #define HB_HD inline
 #endif
@@ -167,11 +167,10 @@ HB_HD PairPreds make_preds(const PairGeom& g)
 // exactly zero (observer in the plane of a face).
 HB_HD bool any_zero_shift(const PairGeom& g)
 {
-    // squares are zero iff the shift is zero (or underflows: harmless, the
-    // exact path is then merely slower)
-    const double m = fmin(fmin(fmin(g.se2[0], g.se2[1]), fmin(g.sn2[0], g.sn2[1])),
-                          fmin(g.su2[0], g.su2[1]));
-    return m == 0.0;
+    // the product is zero iff a shift is zero (or it underflows: harmless, the
+    // exact path is then merely slower); the pair products are reused by the
+    // merged atan terms
+    return ((g.se[0] * g.se[1]) * (g.sn[0] * g.sn[1])) * (g.su[0] * g.su[1]) == 0.0;
 }
 
 // NaN rule per field set (gravity.py:272-449 predicate sets == choclo's)

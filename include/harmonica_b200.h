@@ -77,8 +77,10 @@ int hb200_init(const int* devices, int n_devices);
 int hb200_num_devices(void);
 void hb200_shutdown(void);
 const char* hb200_last_error(void);
-/* variant 0 = rule-exact direct evaluation for every pair; 1 (default) =
- * merged-transcendental fast path with the direct path on singular pairs */
+/* variant 0 = rule-exact direct evaluation for every pair; 1 = merged
+ * transcendentals (CUDA libm) with the direct path on pairs whose observer lies
+ * in the plane of a prism face; 2 (default) = as 1 with the library's own
+ * division / sqrt / log / atan2 sequences (hb200_xmath.cuh) */
 int hb200_set_variant(int variant);
 int hb200_get_variant(void);
 

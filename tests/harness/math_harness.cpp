@@ -19,7 +19,8 @@ static void pair_fs(int variant, const double* o, const double* p, const double*
     make_geom(g, o[0], o[1], o[2], p[0], p[1], p[2], p[3], p[4], p[5]);
     unsigned f = 0;
     if (variant == 0 || any_zero_shift(g)) prism_pair_direct<FS>(g, prm, rules, acc, f);
-    else prism_pair_fast<FS>(g, prm, acc);
+    else if (variant == 1) prism_pair_fast<FS, false>(g, prm, acc);
+    else prism_pair_fast<FS, true>(g, prm, acc);
     *flags |= f;
 }
 
@@ -35,6 +36,17 @@ static void pair_any(int fs, int variant, const double* o, const double* p, cons
 }
 
 extern "C" {
+
+// element-wise checks of the xmath sequences: op 0 rcp, 1 sqrt, 2 log, 3 atan2(a, b)
+void hbt_xmath(int op, int64_t n, const double* a, const double* b, double* out)
+{
+    for (int64_t i = 0; i < n; i++) {
+        if (op == 0) out[i] = fast_rcp(a[i]);
+        else if (op == 1) out[i] = fast_sqrt(a[i]);
+        else if (op == 2) out[i] = fast_log(a[i]);
+        else out[i] = fast_atan2(a[i], b[i]);
+    }
+}
 
 int hbt_nout(int fs)
 {

@@ -21,12 +21,12 @@ pytestmark = pytest.mark.gpu
 G = 6.6743e-11
 
 
-@pytest.fixture(params=[1, 0], ids=["merged", "direct"])
+@pytest.fixture(params=[2, 1, 0], ids=["xmath", "merged", "direct"])
 def variant(request, hb):
     lib = hb._lib.load()
     lib.hb200_set_variant(request.param)
     yield request.param
-    lib.hb200_set_variant(1)
+    lib.hb200_set_variant(2)
 
 
 def quiet(fn, *a, **k):

@@ -39,16 +39,17 @@ def test_direct_path_is_bit_exact(case, field):
     npt.assert_array_equal(out[0], _si(coords, prisms, density, field))
 
 
+@pytest.mark.parametrize("variant", [1, 2])
 @pytest.mark.parametrize("field", GRAVITY_FIELDS)
-def test_merged_path_within_tolerance(case, field):
+def test_merged_path_within_tolerance(case, field, variant):
     coords, prisms, density, prm = case
-    out, _ = harness_prism(field, 1, coords, prisms, prm)
+    out, _ = harness_prism(field, variant, coords, prisms, prm)
     assert max_rel(out[0], _si(coords, prisms, density, field)) <= TOL
 
 
 def test_fused_sets_match_single_fields(case):
     coords, prisms, density, prm = case
-    for variant in (0, 1):
+    for variant in (0, 1, 2):
         acc, _ = harness_prism("acc3", variant, coords, prisms, prm)
         ten, _ = harness_prism("tensor6", variant, coords, prisms, prm)
         for k, f in enumerate(GRAVITY_FIELDS[1:4]):
@@ -57,7 +58,7 @@ def test_fused_sets_match_single_fields(case):
             assert max_rel(ten[k], _si(coords, prisms, density, f)) <= TOL
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 def test_magnetic(case, variant):
     coords, prisms, _, _ = case
     rng = np.random.default_rng(4)
@@ -70,7 +71,7 @@ def test_magnetic(case, variant):
         assert max_rel(single[0] * CM * 1e9, want[k]) <= TOL
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 def test_observers_inside_below_and_around(variant):
     rng = np.random.default_rng(12)
     coords, prisms, density = config1(200, 300, seed=12)
@@ -86,7 +87,7 @@ def test_observers_inside_below_and_around(variant):
         assert max_rel(out[0], _si(coords, prisms, density, f)) <= TOL, f
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 def test_singular_suite_matches_reference_rules(variant):
     """vertices / edges / faces / edge extensions: NaN pattern and values (golden = reference)"""
     g = golden("prism_singular_suite")
@@ -114,7 +115,7 @@ def test_slab_limit_on_face_merged_path():
     sizes = np.logspace(3, 9, 7)
     res = []
     for s in sizes:
-        out, _ = harness_prism("g_z", 1, ([0.0], [0.0], [height]),
+        out, _ = harness_prism("g_z", 2, ([0.0], [0.0], [height]),
                                [[-s / 2, s / 2, -s / 2, s / 2, height - thickness, height]],
                                [[G * density, 0, 0]])
         res.append(out[0][0] * -1e5)
@@ -124,7 +125,7 @@ def test_slab_limit_on_face_merged_path():
     assert (errors[1:] < errors[:-1]).all()
     npt.assert_allclose(analytical, res[-1])
     # slightly above the face: the merged path proper, same limit
-    out, _ = harness_prism("g_z", 1, ([0.0], [0.0], [height + 1e-3]),
+    out, _ = harness_prism("g_z", 2, ([0.0], [0.0], [height + 1e-3]),
                            [[-5e8, 5e8, -5e8, 5e8, height - thickness, height]], [[G * density, 0, 0]])
     npt.assert_allclose(out[0][0] * -1e5, analytical, rtol=1e-6)
 
@@ -164,11 +165,11 @@ def test_large_region_accuracy_against_high_precision():
     prm = np.zeros((400, 3))
     prm[:, 0] = G * density
     for f in ("g_z", "g_zz", "g_en", "potential"):
-        out, _ = harness_prism(f, 1, coords, prisms, prm)
+        out, _ = harness_prism(f, 2, coords, prisms, prm)
         bound = {"g_zz": TOL, "g_en": TOL, "g_z": 5e-8, "potential": 1e-6}[f]
         assert max_rel(out[0], _si(coords, prisms, density, f)) <= bound, f
     for f in ("g_z", "potential"):
-        out, _ = harness_prism(f, 1, coords, prisms, prm)
+        out, _ = harness_prism(f, 2, coords, prisms, prm)
         ora = _si(coords, prisms, density, f)
         err_merged, err_oracle = [], []
         for i in range(4):
@@ -192,5 +193,37 @@ def test_dense_large_region_within_tolerance():
     # the potential is excluded: with coordinates ~5e5 m its per-vertex terms (e*n*log ~ 1e12)
     # put the reference's own rounding noise near 1e-8 * max|field| (see the test above)
     for f in GRAVITY_FIELDS[1:]:
-        out, _ = harness_prism(f, 1, coords, prisms, prm)
+        out, _ = harness_prism(f, 2, coords, prisms, prm)
         assert max_rel(out[0], _si(coords, prisms, density, f)) <= TOL, f
+
+
+def test_xmath_sequences_accuracy():
+    """hb200_xmath.cuh (host build): rcp <= 1 ulp, sqrt correctly rounded, log and atan2 <= 5e-16 abs"""
+    import ctypes
+
+    from _common import harness
+
+    H = harness()
+    dp = ctypes.POINTER(ctypes.c_double)
+    H.hbt_xmath.argtypes = [ctypes.c_int, ctypes.c_int64, dp, dp, dp]
+
+    def xm(op, a, b=None):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        b = a if b is None else np.ascontiguousarray(b, dtype=np.float64)
+        out = np.empty_like(a)
+        H.hbt_xmath(op, a.size, a.ctypes.data_as(dp), b.ctypes.data_as(dp), out.ctypes.data_as(dp))
+        return out
+
+    rng = np.random.default_rng(0)
+    x = np.exp(rng.uniform(-60, 60, 400_000))
+    assert np.max(np.abs(xm(0, x) - 1 / x) / np.spacing(1 / x)) <= 1.0
+    npt.assert_array_equal(xm(1, x), np.sqrt(x))
+    lg = xm(2, x)
+    assert np.max(np.abs(lg - np.log(x)) / np.maximum(np.abs(np.log(x)), 1.0)) <= 4e-16
+    near = 1 + rng.uniform(-2e-2, 2e-2, 400_000)
+    assert np.max(np.abs(xm(2, near) - np.log(near))) <= 4e-18
+    y, x2 = rng.normal(size=400_000) * 1e8, rng.normal(size=400_000) * 1e8
+    assert np.max(np.abs(xm(3, y, x2) - np.arctan2(y, x2))) <= 5e-16
+    small = rng.uniform(-1e-3, 1e-3, 400_000)  # far-field regime: tiny angles keep RELATIVE accuracy
+    got = xm(3, small, np.ones_like(small))
+    assert np.max(np.abs(got - np.arctan(small)) / np.abs(np.arctan(small))) <= 5e-16
