@@ -156,31 +156,68 @@ template <int X, bool XM> HB_HD double log_pair(const FastCtx& c, int a, int b)
     return x_log_ratio<XM>(n0 * d1, n1 * d0);
 }
 
-// S[f] = sum over the 4 vertices with index f on axis X of (-1)^(b+c) A^X, where
-// A^X = atan(b c / (a r)), a = shift on axis X. Two atan2 per call.
-template <int X, bool XM> HB_HD double atan_sum4(const FastCtx& c, int f)
+// re > |im| (both finite), i.e. the angle of (re, im) lies inside (-pi/4, pi/4); integer pipe
+HB_HD bool angle_below_quarter_pi(double im, double re)
+{
+#if defined(__CUDA_ARCH__)
+    return __double_as_longlong(re) > (__double_as_longlong(im) & 0x7fffffffffffffffLL);
+#else
+    return re > fabs(im);
+#endif
+}
+
+// (im, re) with atan2(im, re) = A^X(b_0) - A^X(b_1) at fixed index f on axis X and index m on the
+// remaining axis, A^X = atan(b c / (a r)), a = shift on axis X:
+//   im = c a (b0 r1 - b1 r0),  re = a^2 r0 r1 + b0 b1 c^2
+template <int X> HB_HD void atan_pair_terms(const FastCtx& c, int f, int m, double& im, double& re)
 {
     const double a = (X == 0) ? c.se[f] : (X == 1) ? c.sn[f] : c.su[f];
     const double a2 = (X == 0) ? c.se2[f] : (X == 1) ? c.sn2[f] : c.su2[f];
     // paired variable b (first remaining axis), remaining variable cc (second remaining axis)
     const double b0 = (X == 0) ? c.sn[0] : c.se[0];
     const double b1 = (X == 0) ? c.sn[1] : c.se[1];
-    const double b0b1 = b0 * b1;
-    double D[2];
-#pragma unroll
-    for (int m = 0; m < 2; m++) {
-        const double cc = (X == 2) ? c.sn[m] : c.su[m];
-        const double cc2 = (X == 2) ? c.sn2[m] : c.su2[m];
-        int i, j, k;
-        ijk_of<X>(f, 0, m, i, j, k);
-        const double r0 = c.r[i][j][k];
-        ijk_of<X>(f, 1, m, i, j, k);
-        const double r1 = c.r[i][j][k];
-        const double im = (cc * a) * (b0 * r1 - b1 * r0);
-        const double re = a2 * (r0 * r1) + b0b1 * cc2;
-        D[m] = x_atan2<XM>(im, re);
+    const double cc = (X == 2) ? c.sn[m] : c.su[m];
+    const double cc2 = (X == 2) ? c.sn2[m] : c.su2[m];
+    int i, j, k;
+    ijk_of<X>(f, 0, m, i, j, k);
+    const double r0 = c.r[i][j][k];
+    ijk_of<X>(f, 1, m, i, j, k);
+    const double r1 = c.r[i][j][k];
+    im = (cc * a) * (b0 * r1 - b1 * r0);
+    re = a2 * (r0 * r1) + (b0 * b1) * cc2;
+}
+
+// S[f] = sum over the 4 vertices with index f on axis X of (-1)^(b+c) A^X = D_0 - D_1.
+// Far from the prism both D are small and their difference is one more complex product:
+// one atan2 instead of two (valid while |D_0|, |D_1| < pi/4, checked per pair).
+template <int X, bool XM> HB_HD double atan_sum4(const FastCtx& c, int f)
+{
+    double im0, re0, im1, re1;
+    atan_pair_terms<X>(c, f, 0, im0, re0);
+    atan_pair_terms<X>(c, f, 1, im1, re1);
+    if (XM && angle_below_quarter_pi(im0, re0) && angle_below_quarter_pi(im1, re1))
+        return fast_atan2(im0 * re1 - re0 * im1, re0 * re1 + im0 * im1);
+    return x_atan2<XM>(im0, re0) - x_atan2<XM>(im1, re1);
+}
+
+// sum over all 8 vertices of s_ijk A^X = (D_00 - D_01) - (D_10 - D_11): one atan2 of the product
+// z_00 conj(z_01) conj(z_10) z_11 while every |D| < pi/4 (then |sum| < pi), else pairwise.
+template <int X, bool XM> HB_HD double atan_sum8(const FastCtx& c)
+{
+    if (XM) {
+        double im00, re00, im01, re01, im10, re10, im11, re11;
+        atan_pair_terms<X>(c, 0, 0, im00, re00);
+        atan_pair_terms<X>(c, 0, 1, im01, re01);
+        atan_pair_terms<X>(c, 1, 0, im10, re10);
+        atan_pair_terms<X>(c, 1, 1, im11, re11);
+        if (angle_below_quarter_pi(im00, re00) && angle_below_quarter_pi(im01, re01)
+            && angle_below_quarter_pi(im10, re10) && angle_below_quarter_pi(im11, re11)) {
+            const double are = re00 * re01 + im00 * im01, aim = im00 * re01 - re00 * im01;
+            const double bre = re11 * re10 + im11 * im10, bim = im11 * re10 - re11 * im10;
+            return fast_atan2(aim * bre + are * bim, are * bre - aim * bim);
+        }
     }
-    return D[0] - D[1];
+    return atan_sum4<X, XM>(c, 0) - atan_sum4<X, XM>(c, 1);
 }
 
 template <int FS, bool XM>
@@ -257,9 +294,9 @@ HB_HD void prism_pair_fast(const PairGeom& g, const double* prm, double* acc)
     } else {
         // second-derivative kernels: tensor components and magnetics
         double kee = 0, knn = 0, kuu = 0, ken = 0, keu = 0, knu = 0;
-        if (T::ae) kee = -(atan_sum4<0, XM>(c, 0) - atan_sum4<0, XM>(c, 1));
-        if (T::an) knn = -(atan_sum4<1, XM>(c, 0) - atan_sum4<1, XM>(c, 1));
-        if (T::au) kuu = -(atan_sum4<2, XM>(c, 0) - atan_sum4<2, XM>(c, 1));
+        if (T::ae) kee = -atan_sum8<0, XM>(c);
+        if (T::an) knn = -atan_sum8<1, XM>(c);
+        if (T::au) kuu = -atan_sum8<2, XM>(c);
         if (T::lu) ken = log_sum8<2, XM>(c);
         if (T::ln) keu = log_sum8<1, XM>(c);
         if (T::le) knu = log_sum8<0, XM>(c);

@@ -270,7 +270,7 @@ struct PointArgs {
     unsigned* flags;
 };
 
-constexpr int kPointObs = 2;  // observers per thread (amortises the record loads)
+constexpr int kPointObs = 4;  // observers per thread (amortises the record loads)
 
 template <int FIELD>
 __global__ void __launch_bounds__(kBlock) point_kernel_cart(const PointArgs a)

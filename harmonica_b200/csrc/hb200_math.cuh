@@ -294,15 +294,25 @@ HB_HD void prism_pair_direct(const PairGeom& g, const double* prm, unsigned mag_
 }
 
 // -------------------------------------------------------------- point masses
+// d2 is a sum of squares: zero means +0.0 exactly; tested on the integer pipe
+HB_HD bool is_pos_zero(double x)
+{
+#if defined(__CUDA_ARCH__)
+    return (__double2hiint(x) | __double2loint(x)) == 0;
+#else
+    return x == 0.0;
+#endif
+}
+HB_HD double point_rsqrt(double d2);  // defined in hb200_xmath.cuh (MUFU.RSQ64H + one cubic step)
+
 // choclo.point kernels (K5) without the G*mass factor; d = observer - source.
 // returns kernel value(s); zero distance reported through flags.
 template <int FIELD>
 HB_HD double point_kernel(double de, double dn, double du, unsigned& flags)
 {
     const double d2 = de * de + dn * dn + du * du;
-    if (d2 == 0.0) flags |= FLAG_ZERO_DIV;
-    const double d = sqrt(d2);
-    const double inv = 1.0 / d;
+    if (is_pos_zero(d2)) flags |= FLAG_ZERO_DIV;
+    const double inv = point_rsqrt(d2);
     if (FIELD == F_POT) return inv;
     const double inv3 = inv * inv * inv;
     if (FIELD == F_E) return -de * inv3;

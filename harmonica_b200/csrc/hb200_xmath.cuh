@@ -122,6 +122,19 @@ HB_HD double fast_sqrt(double x)
     return fma(d, h, g);
 }
 
+// 1/sqrt(x) for finite normal x > 0: seed error e ~ 2^-20, y = y0 (1 + e/2 + 3e^2/8), error O(e^3)
+HB_HD double fast_rsqrt(double x)
+{
+    const double y0 = rsqrt_seed(x);
+    const double t = x * y0;
+    const double e = fma(-t, y0, 1.0);
+    double p = fma(e, 0.375, 0.5);
+    p = p * e;
+    return fma(y0, p, y0);
+}
+
+HB_HD double point_rsqrt(double d2) { return fast_rsqrt(d2); }
+
 // log1p Taylor coefficients z^2 .. z^7
 HB_COEF double kLogC[6] = {-0.5, 1.0 / 3.0, -0.25, 0.2, -1.0 / 6.0, 1.0 / 7.0};
 // atan Taylor coefficients s^1 .. s^5 (s = t^2)
