@@ -233,7 +233,7 @@ def run_b200(args):
     lib = hb._lib.load()
     hb.init([local])
 
-    wl = make_workload(args.workload, args.n_obs, args.n_src, rank)
+    wl = make_workload(args.workload, args.n_obs, args.n_src, 0 if args.shard == "sources" else rank)
     coords = wl["coords"]
     if args.scaling == "strong" and world > 1:
         n = coords[0].size
@@ -246,7 +246,21 @@ def run_b200(args):
     oe, on, ou = (t(c) for c in coords)
     out = torch.empty((nf, n_obs), dtype=torch.float64, device=dev)
     flags = torch.zeros(1, dtype=torch.int32, device=dev)
-    ws_bytes = lib.hb200_prism_ws_bytes(n_obs, n_src, nf)
+    src_sharded = args.shard == "sources" and world > 1
+    if src_sharded:
+        if wl["kind"] != "eqs":
+            raise SystemExit("--shard sources is implemented for the eqs workload")
+        # BASELINE config 5: every rank owns a slice of the sources and ALL observers; the
+        # partial fields are summed with an NCCL reduce (float64) inside the timed region
+        s_lo, s_hi = n_src * rank // world, n_src * (rank + 1) // world
+        wl["points"] = tuple(np.ascontiguousarray(p[s_lo:s_hi]) for p in wl["points"])
+        wl["coefs"] = np.ascontiguousarray(wl["coefs"][s_lo:s_hi])
+        n_src = s_hi - s_lo
+        pairs_per_step_rank = float(n_obs) * float(n_src)
+    if wl["kind"] == "eqs":
+        ws_bytes = lib.hb200_point_ws_bytes(n_obs, n_src)
+    else:
+        ws_bytes = lib.hb200_prism_ws_bytes(n_obs, n_src, nf)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     P = lambda x: ctypes.c_void_p(x.data_ptr())  # noqa: E731
@@ -298,14 +312,22 @@ def run_b200(args):
         cf = t(wl["coefs"])
 
         def step_dev():
-            return lib.hb200_point_gravity_dev(P(oe), P(on), P(ou), n_obs, P(pts[0]), P(pts[1]),
-                                               P(pts[2]), P(cf), n_src, 1, 0, 0, P(out), P(flags),
-                                               P(ws), ws_bytes, stream)
+            rc = lib.hb200_point_gravity_dev(P(oe), P(on), P(ou), n_obs, P(pts[0]), P(pts[1]),
+                                             P(pts[2]), P(cf), n_src, 1, 0, 0, P(out), P(flags),
+                                             P(ws), ws_bytes, stream)
+            if src_sharded:  # reduce-sum of the partial fields over NVLink (NCCL)
+                dist.reduce(out, dst=0, op=dist.ReduceOp.SUM)
+            return rc
 
         def step_host():
-            return hb.eqs_predict(coords, wl["points"], wl["coefs"])
+            res = hb.eqs_predict(coords, wl["points"], wl["coefs"])
+            if src_sharded:
+                part = torch.from_numpy(res).to(dev)
+                dist.reduce(part, dst=0, op=dist.ReduceOp.SUM)
+                res = part.cpu().numpy()
+            return res
         h2d = 8 * (3 * n_obs + 4 * n_src)
-        launches_per_step = 2
+        launches_per_step = 2 + (1 if n_obs < 512 * 148 * 120 else 0)  # + chunk reduce
     d2h = 8 * nf * n_obs
 
     def barrier():
@@ -329,12 +351,14 @@ def run_b200(args):
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     barrier()
+    launches_before = lib.hb200_launch_count()
     for k in range(args.steps):
         l2_flush.fill_(k)  # flush L2 between timed iterations (outside the events)
         starts[k].record()
         hb._lib.check(step_dev())
         ends[k].record()
     barrier()
+    gpu_launches = int(lib.hb200_launch_count() - launches_before)  # counted by the library
     clocks = sampler.stop() if rank == 0 else None
     step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
@@ -383,14 +407,16 @@ def run_b200(args):
             "metric": "prism-observer pair evals/sec", "value": value, "unit": "pair/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True,
-            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong" if src_sharded else args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl["desc"], "name": args.workload, "pairs_per_step_per_gpu":
                        pairs_per_step_rank, "l2": "flushed between timed iterations (256 MiB write)",
-                       "kernel_variant": int(lib.hb200_get_variant())},
+                       "kernel_variant": int(lib.hb200_get_variant()),
+                       "sharding": "sources + NCCL reduce-sum" if src_sharded else
+                       ("observers, no collective" if world > 1 else "single GPU")},
             "e2e": {"value": pairs_total / e2e_s, "unit": "pair/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps,
                     "api": "harmonica_b200 public API on numpy buffers (ctypes -> C ABI), blocking"},
-            "gpu_launches": launches_per_step * args.steps,
+            "gpu_launches": gpu_launches,
             "clocks": clocks,
             "roofline": {
                 "bound": "fp64", "achieved": achieved, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
@@ -419,6 +445,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="layer_gz", choices=sorted(I_PAIR))
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--shard", default="observers", choices=["observers", "sources"])
     ap.add_argument("--n-obs", type=int, default=0)
     ap.add_argument("--n-src", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

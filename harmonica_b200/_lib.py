@@ -45,6 +45,7 @@ SIGNATURES = {
     "hb200_last_error": (ctypes.c_char_p, []),
     "hb200_set_variant": (_int, [_int]),
     "hb200_get_variant": (_int, []),
+    "hb200_launch_count": (ctypes.c_uint64, []),
     "hb200_prism_gravity": (
         _int, [_dp, _dp, _dp, _i64, _dp, _dp, _i64, _u32, _int, _dp, _u32p]),
     "hb200_prism_singular_scan": (_int, [_dp, _dp, _dp, _i64, _dp, _i64, _int, _u32p]),
@@ -58,6 +59,7 @@ SIGNATURES = {
     "hb200_eqs_predict": (_int, [_dp, _dp, _dp, _i64, _dp, _dp, _dp, _dp, _i64, _int, _dp, _u32p]),
     "hb200_eqs_jacobian": (_int, [_dp, _dp, _dp, _i64, _dp, _dp, _dp, _i64, _dp]),
     "hb200_prism_ws_bytes": (_sz, [_i64, _i64, _int]),
+    "hb200_point_ws_bytes": (_sz, [_i64, _i64]),
     "hb200_prism_gravity_dev": (
         _int, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _u32, _vp, _vp, _vp, _sz, _vp]),
     "hb200_prism_magnetic_dev": (

@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -26,6 +27,7 @@ namespace {
 thread_local std::string g_err;
 std::mutex g_mu;
 int g_variant = 2;
+std::atomic<uint64_t> g_launches{0};  // kernels launched by this library (hb200_launch_count)
 
 int fail(int code, const char* fmt, ...)
 {
@@ -204,6 +206,7 @@ int run_prism_pass(int fs, int nout, const double* oe, const double* on, const d
     dim3 grid((unsigned)((n_obs + kBlock - 1) / kBlock), (unsigned)chunks);
     launch_prism_any(fs, a, grid, st);
     CU(cudaGetLastError());
+    g_launches += chunks > 1 ? 2 : 1;
     if (chunks > 1) {
         const int64_t total = (int64_t)nout * n_obs;
         reduce_partials_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(partial, chunks, nout,
@@ -266,6 +269,7 @@ int run_point_pass(int field, int spherical, const double* oe, const double* on,
         }
     }
     CU(cudaGetLastError());
+    g_launches += chunks > 1 ? 2 : 1;
     if (chunks > 1) {
         Scales sc;
         sc.s[0] = scale;
@@ -333,6 +337,7 @@ int prism_gravity_dev_impl(const double* oe, const double* on, const double* ou,
         pack_prisms_kernel<<<(unsigned)((n_prisms + 255) / 256), 256, 0, st>>>(prisms, density,
                                                                               n_prisms, packed);
         CU(cudaGetLastError());
+        g_launches += 1;
     }
     return gravity_passes(oe, on, ou, n_obs, packed, n_prisms, mask, raw, out, d_flags, ws, sms, st);
 }
@@ -351,6 +356,7 @@ int prism_layer_dev_impl(const double* oe, const double* on, const double* ou, i
         pack_layer_kernel<<<(unsigned)((n_src + 255) / 256), 256, 0, st>>>(
             east_c, north_c, n_east, n_north, bottom, top, density, thr, packed);
         CU(cudaGetLastError());
+        g_launches += 1;
     }
     return gravity_passes(oe, on, ou, n_obs, packed, n_src, mask, raw, out, d_flags, ws, sms, st);
 }
@@ -368,6 +374,7 @@ int prism_magnetic_dev_impl(const double* oe, const double* on, const double* ou
         pack_mag_kernel<<<(unsigned)((n_prisms + 255) / 256), 256, 0, st>>>(prisms, me, mn, mu,
                                                                            n_prisms, packed);
         CU(cudaGetLastError());
+        g_launches += 1;
     }
     double* partial = (double*)(ws.base + ws.used);
     const size_t partial_bytes = ws.left();
@@ -399,8 +406,10 @@ double point_scale(int field)
 
 size_t point_ws_bytes(int64_t n_obs, int64_t n_src, int sms)
 {
+    // the spherical kernel has kBlock observers per CTA, the Cartesian one kBlock * kPointObs
     return align_up((size_t)n_src * kSphStride * sizeof(double))
-         + partial_bytes_for(n_obs, n_src, 1, kBlock, sms) + 256;
+         + std::max(partial_bytes_for(n_obs, n_src, 1, kBlock, sms),
+                    partial_bytes_for(n_obs, n_src, 1, kBlock * kPointObs, sms)) + 256;
 }
 
 int point_gravity_dev_impl(const double* oe, const double* on, const double* ou, int64_t n_obs,
@@ -418,6 +427,7 @@ int point_gravity_dev_impl(const double* oe, const double* on, const double* ou,
         if (spherical) pack_points_sph_kernel<<<nb, 256, 0, st>>>(pe, pn, pu, w, n_src, packed);
         else pack_points_kernel<<<nb, 256, 0, st>>>(pe, pn, pu, w, n_src, scale_by_G, packed);
         CU(cudaGetLastError());
+        g_launches += 1;
     }
     double* partial = (double*)(ws.base + ws.used);
     const size_t partial_bytes = ws.left();
@@ -644,6 +654,7 @@ int hb200_set_variant(int variant)
     return HB200_OK;
 }
 int hb200_get_variant(void) { return g_variant; }
+uint64_t hb200_launch_count(void) { return g_launches.load(); }
 
 void hb200_shutdown(void)
 {
@@ -743,6 +754,7 @@ int hb200_prism_singular_scan(const double* easting, const double* northing,
         dim3 grid((unsigned)((no + kBlock - 1) / kBlock), (unsigned)chunks);
         singular_scan_kernel<<<grid, kBlock, 0, dev.st>>>(a, field);
         CU(cudaGetLastError());
+        g_launches += 2;
         return HB200_OK;
     };
     Scales sc;
@@ -885,6 +897,7 @@ int hb200_eqs_jacobian(const double* easting, const double* northing, const doub
         eqs_jacobian_kernel<<<grid, 256, 0, dev.st>>>(d_o[0] + i0, d_o[1] + i0, d_o[2] + i0, rows,
                                                      d_p[0], d_p[1], d_p[2], n_src, d_jac);
         CU(cudaGetLastError());
+        g_launches += 1;
         CU(cudaMemcpyAsync(jac + i0 * n_src, d_jac, (size_t)rows * n_src * 8, cudaMemcpyDeviceToHost,
                            dev.st));
         CU(cudaStreamSynchronize(dev.st));
@@ -896,6 +909,11 @@ int hb200_eqs_jacobian(const double* easting, const double* northing, const doub
 size_t hb200_prism_ws_bytes(int64_t n_obs, int64_t n_sources, int n_fields)
 {
     return prism_ws_bytes(n_obs, n_sources, n_fields, 148);
+}
+
+size_t hb200_point_ws_bytes(int64_t n_obs, int64_t n_sources)
+{
+    return point_ws_bytes(n_obs, n_sources, 148);
 }
 
 int hb200_prism_gravity_dev(const double* easting, const double* northing, const double* upward,
@@ -965,6 +983,7 @@ int hb200_fp64_peak(int iters, double* flops, double* seconds)
     fp64_peak_kernel<<<blocks, threads>>>(d_out, 16, 0.999999, 1e-9);  // warm-up
     CU(cudaEventRecord(e0));
     fp64_peak_kernel<<<blocks, threads>>>(d_out, iters, 0.999999, 1e-9);
+    g_launches += 2;
     CU(cudaEventRecord(e1));
     CU(cudaEventSynchronize(e1));
     float ms = 0;

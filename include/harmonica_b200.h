@@ -83,6 +83,8 @@ const char* hb200_last_error(void);
  * division / sqrt / log / atan2 sequences (hb200_xmath.cuh) */
 int hb200_set_variant(int variant);
 int hb200_get_variant(void);
+/* number of CUDA kernels this library has launched so far (all entry points) */
+uint64_t hb200_launch_count(void);
 
 /* ---- host-buffer entry points ------------------------------------------- */
 /* replaces jit_prism_gravity, _forward/prisms/gravity.py:489-545, with the
@@ -140,6 +142,7 @@ int hb200_eqs_jacobian(const double* easting, const double* northing, const doub
 
 /* ---- device-buffer entry points (current device, async on stream) -------- */
 size_t hb200_prism_ws_bytes(int64_t n_obs, int64_t n_sources, int n_fields);
+size_t hb200_point_ws_bytes(int64_t n_obs, int64_t n_sources);
 int hb200_prism_gravity_dev(const double* easting, const double* northing, const double* upward,
                             int64_t n_obs, const double* prisms, const double* density,
                             int64_t n_prisms, uint32_t field_mask, double* out,
