@@ -9,10 +9,11 @@
 // alternating sum. Here vertex terms that share their prefactor are merged
 // BEFORE the transcendental:
 //   * logs:  sum_v s_v log(num_v/den_v) = log(prod num^s / prod den^s)
-//            with (num, den) chosen per vertex by the safe_log rule
-//              x >= 0:            (x + r, 1)
-//              x <  0:            (y^2 + z^2, r - x)
-//              x <  0, r == -x:   (1, -2x)
+//            with (num, den) chosen by the safe_log rule (T = r + |x|)
+//              x >= 0:  (T, 1)        [log(x + r)]
+//              x <  0:  (y^2 + z^2, T) [log((y^2 + z^2) / (r - x))]
+//            (the r == 0 and on-axis r == -x rules only fire on pairs that
+//            needs_exact_path() routes to the direct path)
 //   * atans: atan(y0/x0) - atan(y1/x1) = atan2(y0 x1 - x0 y1, x0 x1 + y0 y1)
 //            for the two vertices that differ in one factor of y; x0 and x1
 //            then have the same sign, so the identity is exact, and it
@@ -43,17 +44,6 @@ HB_HD bool is_neg(double x)
     return __double2hiint(x) < 0;
 #else
     return signbit(x);
-#endif
-}
-
-// r == |x| for r >= 0, on the integer pipe
-HB_HD bool eq_abs(double r, double x)
-{
-#if defined(__CUDA_ARCH__)
-    return ((((unsigned)__double2hiint(r) ^ (unsigned)__double2hiint(x)) & 0x7fffffffu)
-            | ((unsigned)__double2loint(r) ^ (unsigned)__double2loint(x))) == 0u;
-#else
-    return r == fabs(x);
 #endif
 }
 
@@ -88,18 +78,18 @@ template <int FS, bool XM> HB_HD void make_fast_ctx(FastCtx& c, const PairGeom& 
             for (int k = 0; k < 2; k++) c.r[i][j][k] = x_sqrt<XM>(add_rn(c.en2[i][j], g.su2[k]));
 }
 
-// (num, den) of safe_log type X (0: x = e, 1: x = n, 2: x = u) at vertex ijk
-template <int X>
-HB_HD void log_nd(const FastCtx& c, int i, int j, int k, double& num, double& den)
+// T = r + |x| and Y = y^2 + z^2 of safe_log type X (0: x = e, 1: x = n, 2: x = u) at vertex
+// ijk. safe_log(x, y, z, r) = log(T) for x >= 0 and log(Y / T) for x < 0; the on-axis and r == 0
+// branches cannot occur on this path (needs_exact_path() sends such pairs to the direct path).
+template <int X> HB_HD double log_x(const FastCtx& c, int xi)
+{
+    return (X == 0) ? c.se[xi] : (X == 1) ? c.sn[xi] : c.su[xi];
+}
+template <int X> HB_HD void log_TY(const FastCtx& c, int i, int j, int k, double& T, double& Y)
 {
     const double x = (X == 0) ? c.se[i] : (X == 1) ? c.sn[j] : c.su[k];
-    const double Y = (X == 0) ? c.nu2[j][k] : (X == 1) ? c.eu2[i][k] : c.en2[i][j];
-    const double rr = c.r[i][j][k];
-    const double T = rr + fabs(x);
-    const bool neg = is_neg(x);
-    const bool axis = eq_abs(rr, x);
-    num = neg ? (axis ? 1.0 : Y) : T;
-    den = neg ? T : 1.0;
+    Y = (X == 0) ? c.nu2[j][k] : (X == 1) ? c.eu2[i][k] : c.en2[i][j];
+    T = c.r[i][j][k] + fabs(x);
 }
 
 // map (fixed axis F with index f, the other two indices a, b in axis order) -> ijk
@@ -110,21 +100,30 @@ template <int F> HB_HD void ijk_of(int f, int a, int b, int& i, int& j, int& k)
     else { i = a; j = b; k = f; }
 }
 
-// top/bot products of the 4 vertices with index f fixed on axis F, signs (-1)^(a+b)
+// top/bot products of the 4 vertices with index f fixed on axis F (F != X), signs (-1)^(a+b).
+// The sign of x depends only on the X index xi, so the safe_log branch is selected once per
+// xi on products of two vertices (o = the remaining index):
+//   x >= 0: (T[xi][0], T[xi][1]);   x < 0: (Y[xi][0] T[xi][1], T[xi][0] Y[xi][1])
 template <int X, int F>
 HB_HD void log_group4_tb(const FastCtx& c, int f, double& top, double& bot)
 {
-    double n[2][2], d[2][2];
+    constexpr bool x_first = (X == (F == 0 ? 1 : 0));
+    double P[2], Q[2];
 #pragma unroll
-    for (int a = 0; a < 2; a++)
+    for (int xi = 0; xi < 2; xi++) {
+        double T[2], Y[2];
 #pragma unroll
-        for (int b = 0; b < 2; b++) {
+        for (int o = 0; o < 2; o++) {
             int i, j, k;
-            ijk_of<F>(f, a, b, i, j, k);
-            log_nd<X>(c, i, j, k, n[a][b], d[a][b]);
+            ijk_of<F>(f, x_first ? xi : o, x_first ? o : xi, i, j, k);
+            log_TY<X>(c, i, j, k, T[o], Y[o]);
         }
-    top = (n[0][0] * n[1][1]) * (d[0][1] * d[1][0]);
-    bot = (n[0][1] * n[1][0]) * (d[0][0] * d[1][1]);
+        const bool neg = is_neg(log_x<X>(c, xi));
+        P[xi] = neg ? Y[0] * T[1] : T[0];
+        Q[xi] = neg ? T[0] * Y[1] : T[1];
+    }
+    top = P[0] * Q[1];
+    bot = Q[0] * P[1];
 }
 
 // sum_{a,b} (-1)^(a+b) L^X over the 4 vertices with index f on axis F
@@ -135,24 +134,44 @@ template <int X, int F, bool XM> HB_HD double log_group4(const FastCtx& c, int f
     return x_log_ratio<XM>(top, bot);
 }
 
-// sum over all 8 vertices of s_ijk L^X
+// sum over all 8 vertices of s_ijk L^X: per X index xi the four vertices split by parity of
+// the other two indices into side A (00, 11) and side B (01, 10)
 template <int X, bool XM> HB_HD double log_sum8(const FastCtx& c)
 {
-    double t0, b0, t1, b1;
-    log_group4_tb<X, 0>(c, 0, t0, b0);
-    log_group4_tb<X, 0>(c, 1, t1, b1);
-    return x_log_ratio<XM>(t0 * b1, b0 * t1);
+    double P[2], Q[2];
+#pragma unroll
+    for (int xi = 0; xi < 2; xi++) {
+        double T[2][2], Y[2][2];
+#pragma unroll
+        for (int a = 0; a < 2; a++)
+#pragma unroll
+            for (int b = 0; b < 2; b++) {
+                int i, j, k;
+                ijk_of<X>(xi, a, b, i, j, k);
+                log_TY<X>(c, i, j, k, T[a][b], Y[a][b]);
+            }
+        const double TA = T[0][0] * T[1][1], TB = T[0][1] * T[1][0];
+        const double YA = Y[0][0] * Y[1][1], YB = Y[0][1] * Y[1][0];
+        const bool neg = is_neg(log_x<X>(c, xi));
+        P[xi] = neg ? YA * TB : TA;
+        Q[xi] = neg ? TA * YB : TB;
+    }
+    return x_log_ratio<XM>(P[0] * Q[1], Q[0] * P[1]);
 }
 
-// L^X(x_0) - L^X(x_1) along X's own axis; (a, b) = the other two indices in axis order
+// L^X(x_0) - L^X(x_1) along X's own axis; (a, b) = the other two indices in axis order.
+// Y does not depend on the X index.
 template <int X, bool XM> HB_HD double log_pair(const FastCtx& c, int a, int b)
 {
     int i, j, k;
-    double n0, d0, n1, d1;
+    double T0, T1, Y;
     ijk_of<X>(0, a, b, i, j, k);
-    log_nd<X>(c, i, j, k, n0, d0);
+    log_TY<X>(c, i, j, k, T0, Y);
     ijk_of<X>(1, a, b, i, j, k);
-    log_nd<X>(c, i, j, k, n1, d1);
+    log_TY<X>(c, i, j, k, T1, Y);
+    const bool neg0 = is_neg(log_x<X>(c, 0)), neg1 = is_neg(log_x<X>(c, 1));
+    const double n0 = neg0 ? Y : T0, d0 = neg0 ? T0 : 1.0;
+    const double n1 = neg1 ? Y : T1, d1 = neg1 ? T1 : 1.0;
     return x_log_ratio<XM>(n0 * d1, n1 * d0);
 }
 

@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(kBlock) prism_kernel(const PrismArgs a)
             if (VARIANT == 0) {
                 prism_pair_direct<FS>(g, prm, a.rules, acc, flags);
             } else {
-                if (any_zero_shift(g)) prism_pair_direct<FS>(g, prm, a.rules, acc, flags);
+                if (needs_exact_path(g)) prism_pair_direct<FS>(g, prm, a.rules, acc, flags);
                 else prism_pair_fast<FS, (VARIANT == 2)>(g, prm, acc);
             }
         }

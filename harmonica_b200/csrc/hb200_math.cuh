@@ -17,6 +17,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define HB_HD __device__ __forceinline__
@@ -75,6 +76,38 @@ HB_TRAITS(FS_MAG_N,   1, 1, 0, 1, 0, 1, 0);
 HB_TRAITS(FS_MAG_U,   1, 1, 1, 0, 0, 0, 1);
 #undef HB_TRAITS
 
+// ------------------------------------------------------------ bit helpers
+HB_HD int hi_word(double x)
+{
+#if defined(__CUDA_ARCH__)
+    return __double2hiint(x);
+#else
+    int64_t b;
+    memcpy(&b, &x, 8);
+    return (int)(b >> 32);
+#endif
+}
+HB_HD int lo_word(double x)
+{
+#if defined(__CUDA_ARCH__)
+    return __double2loint(x);
+#else
+    int64_t b;
+    memcpy(&b, &x, 8);
+    return (int)(b & 0xffffffff);
+#endif
+}
+HB_HD double make_double(int hi, int lo)
+{
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(hi, lo);
+#else
+    int64_t b = ((int64_t)hi << 32) | (uint32_t)lo;
+    double x;
+    memcpy(&x, &b, 8);
+    return x;
+#endif
+}
 // ------------------------------------------------- exact (uncontracted) ops
 // r and y^2+z^2 decide which branch of safe_log is taken (r == 0, r == -x), so
 // they are computed with the reference's rounding sequence: separately rounded
@@ -163,14 +196,24 @@ HB_HD PairPreds make_preds(const PairGeom& g)
     return p;
 }
 
-// true when the pair needs the rule-exact path: some shifted coordinate is
-// exactly zero (observer in the plane of a face).
-HB_HD bool any_zero_shift(const PairGeom& g)
+// true when the pair must take the rule-exact (direct) path: the smallest of the six
+// squared shifts is zero or more than 2^50 times smaller than the largest one. This covers
+//  * an exactly-zero shift (observer in the plane of a face: all singular-point rules), and
+//  * every pair on which the reference's on-axis safe_log branch (r == -x) can fire: that
+//    needs y^2 + z^2 < 2^-52 x^2, so when all squares are within 2^50 of each other r != |x|.
+// Non-negative doubles order like their bit patterns, so this runs on the integer pipe.
+HB_HD bool needs_exact_path(const PairGeom& g)
 {
-    // the product is zero iff a shift is zero (or it underflows: harmless, the
-    // exact path is then merely slower); the pair products are reused by the
-    // merged atan terms
-    return ((g.se[0] * g.se[1]) * (g.sn[0] * g.sn[1])) * (g.su[0] * g.su[1]) == 0.0;
+    const unsigned h[6] = {(unsigned)hi_word(g.se2[0]), (unsigned)hi_word(g.se2[1]),
+                           (unsigned)hi_word(g.sn2[0]), (unsigned)hi_word(g.sn2[1]),
+                           (unsigned)hi_word(g.su2[0]), (unsigned)hi_word(g.su2[1])};
+    unsigned lo = h[0], hi = h[0];
+#pragma unroll
+    for (int q = 1; q < 6; q++) {
+        lo = h[q] < lo ? h[q] : lo;
+        hi = h[q] > hi ? h[q] : hi;
+    }
+    return lo + (50u << 20) < hi;
 }
 
 // NaN rule per field set (gravity.py:272-449 predicate sets == choclo's)

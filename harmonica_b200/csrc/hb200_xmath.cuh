@@ -36,38 +36,6 @@
 
 namespace hb {
 
-// ------------------------------------------------------------ bit helpers
-HB_HD int hi_word(double x)
-{
-#if defined(__CUDA_ARCH__)
-    return __double2hiint(x);
-#else
-    int64_t b;
-    memcpy(&b, &x, 8);
-    return (int)(b >> 32);
-#endif
-}
-HB_HD int lo_word(double x)
-{
-#if defined(__CUDA_ARCH__)
-    return __double2loint(x);
-#else
-    int64_t b;
-    memcpy(&b, &x, 8);
-    return (int)(b & 0xffffffff);
-#endif
-}
-HB_HD double make_double(int hi, int lo)
-{
-#if defined(__CUDA_ARCH__)
-    return __hiloint2double(hi, lo);
-#else
-    int64_t b = ((int64_t)hi << 32) | (uint32_t)lo;
-    double x;
-    memcpy(&x, &b, 8);
-    return x;
-#endif
-}
 HB_HD double flip_sign_if(double x, bool neg)
 {
     return make_double(hi_word(x) ^ (neg ? (int)0x80000000 : 0), lo_word(x));

@@ -227,3 +227,21 @@ def test_xmath_sequences_accuracy():
     small = rng.uniform(-1e-3, 1e-3, 400_000)  # far-field regime: tiny angles keep RELATIVE accuracy
     got = xm(3, small, np.ones_like(small))
     assert np.max(np.abs(got - np.arctan(small)) / np.abs(np.arctan(small))) <= 5e-16
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_near_axis_and_near_face_observers(variant):
+    """observers ALMOST on the extension of an edge / almost in a face plane (offsets 1e-9 .. 1 m):
+    the on-axis safe_log branch and the face rules must switch exactly where the reference's do"""
+    prism = np.array([[-30.0, 50.0, -20.0, 40.0, -80.0, -10.0]])
+    pts = []
+    for off in (0.0, 1e-9, 1e-7, 1e-5, 1e-3, 1e-1, 1.0):
+        pts += [(50.0 + 100.0, 40.0 + off, -10.0 + off), (-30.0 - 70.0, -20.0 - off, -80.0 + off),
+                (50.0 + off, 40.0 + 250.0, -10.0 - off), (50.0 - off, 40.0 + off, -10.0 + 500.0),
+                (10.0, 5.0, -10.0 + off), (50.0 + off, 5.0, -40.0), (10.0 + off, 40.0 + off, -10.0 + off)]
+    a = np.array(pts)
+    coords = (a[:, 0].copy(), a[:, 1].copy(), a[:, 2].copy())
+    prm = np.array([[G * 2670.0, 0, 0]])
+    for f in GRAVITY_FIELDS:
+        out, _ = harness_prism(f, variant, coords, prism, prm)
+        assert max_rel(out[0], _si(coords, prism, np.array([2670.0]), f)) <= TOL, f
