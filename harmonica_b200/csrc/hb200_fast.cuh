@@ -28,7 +28,7 @@
 namespace hb {
 
 // XM = false: CUDA libm; XM = true: the sequences of hb200_xmath.cuh
-template <bool XM> HB_HD double x_sqrt(double x) { return XM ? fast_sqrt(x) : sqrt(x); }
+template <bool XM> HB_HD double x_sqrt(double x) { return XM ? fast_sqrt_1ulp(x) : sqrt(x); }
 template <bool XM> HB_HD double x_log_ratio(double top, double bot)
 {
     return XM ? fast_log(top * fast_rcp(bot)) : log(top / bot);

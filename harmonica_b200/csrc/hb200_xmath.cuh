@@ -11,7 +11,8 @@
 // the constant bank (operands of DFMA, no MOV), and use table-driven argument
 // reduction so that the polynomials are short:
 //   fast_div   MUFU.RCP64H seed + one cubic Newton step         4 FP64 instr
-//   fast_sqrt  MUFU.RSQ64H seed + 2 Goldschmidt steps + fix-up   9 FP64 instr
+//   fast_sqrt  MUFU.RSQ64H seed + 2 Goldschmidt steps + fix-up   9 FP64 instr (correctly rounded)
+//   fast_sqrt_1ulp  MUFU.RSQ64H seed + one cubic step            5 FP64 instr
 //   fast_log   128-bucket reciprocal table, degree-7 log1p     ~11 FP64 instr
 //   fast_atan2 17-entry atan table, one division, degree-11     ~20 FP64 instr
 // (CUDA 12.9 libm: div 8, sqrt 8, log ~30, atan2 ~45 FP64 instr + ~2x as many
@@ -88,6 +89,19 @@ HB_HD double fast_sqrt(double x)
     h = fma(h, r, h);
     const double d = fma(-g, g, x);
     return fma(d, h, g);
+}
+
+// sqrt(x) for finite normal x > 0 to within 1 ulp: g = g0 (1 + e/2 + 3 e^2/8), g0 = x y0,
+// e = 1 - g0 y0 (5 FP64 instructions). Enough for the merged path, where r no longer decides
+// a branch (needs_exact_path() has already diverted every pair on which r == |x| could hold).
+HB_HD double fast_sqrt_1ulp(double x)
+{
+    const double y0 = rsqrt_seed(x);
+    const double g0 = x * y0;
+    const double e = fma(-g0, y0, 1.0);
+    double p = fma(e, 0.375, 0.5);
+    p = p * e;
+    return fma(g0, p, g0);
 }
 
 // 1/sqrt(x) for finite normal x > 0: seed error e ~ 2^-20, y = y0 (1 + e/2 + 3e^2/8), error O(e^3)

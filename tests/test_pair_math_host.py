@@ -218,6 +218,8 @@ def test_xmath_sequences_accuracy():
     x = np.exp(rng.uniform(-60, 60, 400_000))
     assert np.max(np.abs(xm(0, x) - 1 / x) / np.spacing(1 / x)) <= 1.0
     npt.assert_array_equal(xm(1, x), np.sqrt(x))
+    assert np.max(np.abs(xm(4, x) - np.sqrt(x)) / np.spacing(np.sqrt(x))) <= 1.0
+    assert np.max(np.abs(xm(5, x) - 1 / np.sqrt(x)) / np.spacing(1 / np.sqrt(x))) <= 2.5  # the numpy reference has two roundings itself
     lg = xm(2, x)
     assert np.max(np.abs(lg - np.log(x)) / np.maximum(np.abs(np.log(x)), 1.0)) <= 4e-16
     near = 1 + rng.uniform(-2e-2, 2e-2, 400_000)
