@@ -29,13 +29,36 @@ namespace hb {
 
 // XM = false: CUDA libm; XM = true: the sequences of hb200_xmath.cuh
 template <bool XM> HB_HD double x_sqrt(double x) { return XM ? fast_sqrt_1ulp(x) : sqrt(x); }
+
+// true when the predicate holds for every lane that is executing this code together: used to
+// pick a shorter far-field sequence without any divergence (the general sequence is valid
+// everywhere, so the choice never changes which formula applies, only its cost)
+HB_HD bool warp_all(bool p)
+{
+#if defined(__CUDA_ARCH__)
+    return __all_sync(__activemask(), p);
+#else
+    return p;
+#endif
+}
+
+// log(top / bot): far from the prism the merged ratio is 1 + z with |z| < 2^-8 and the table
+// reduction of fast_log is not needed (degree-7 log1p directly)
 template <bool XM> HB_HD double x_log_ratio(double top, double bot)
 {
-    return XM ? fast_log(top * fast_rcp(bot)) : log(top / bot);
+    if (!XM) return log(top / bot);
+    const double y = fast_rcp(bot);
+    const double z = fma(top, y, -1.0);
+    if (warp_all((hi_word(z) & 0x7fffffff) < 0x3f700000)) return log1p_small(z);
+    return fast_log(top * y);
 }
+
+// atan2(y, x): far from the prism x > 0 and |y| < x / 32, no quadrant or table reduction
 template <bool XM> HB_HD double x_atan2(double y, double x)
 {
-    return XM ? fast_atan2(y, x) : atan2(y, x);
+    if (!XM) return atan2(y, x);
+    if (warp_all(small_angle(y, x))) return atan_small(y, x);
+    return fast_atan2(y, x);
 }
 
 HB_HD bool is_neg(double x)
@@ -215,7 +238,7 @@ template <int X, bool XM> HB_HD double atan_sum4(const FastCtx& c, int f)
     atan_pair_terms<X>(c, f, 0, im0, re0);
     atan_pair_terms<X>(c, f, 1, im1, re1);
     if (XM && angle_below_quarter_pi(im0, re0) && angle_below_quarter_pi(im1, re1))
-        return fast_atan2(im0 * re1 - re0 * im1, re0 * re1 + im0 * im1);
+        return x_atan2<XM>(im0 * re1 - re0 * im1, re0 * re1 + im0 * im1);
     return x_atan2<XM>(im0, re0) - x_atan2<XM>(im1, re1);
 }
 
@@ -233,7 +256,7 @@ template <int X, bool XM> HB_HD double atan_sum8(const FastCtx& c)
             && angle_below_quarter_pi(im10, re10) && angle_below_quarter_pi(im11, re11)) {
             const double are = re00 * re01 + im00 * im01, aim = im00 * re01 - re00 * im01;
             const double bre = re11 * re10 + im11 * im10, bim = im11 * re10 - re11 * im10;
-            return fast_atan2(aim * bre + are * bim, are * bre - aim * bim);
+            return x_atan2<XM>(aim * bre + are * bim, are * bre - aim * bim);
         }
     }
     return atan_sum4<X, XM>(c, 0) - atan_sum4<X, XM>(c, 1);
@@ -315,7 +338,21 @@ HB_HD void prism_pair_fast(const PairGeom& g, const double* prm, double* acc)
         double kee = 0, knn = 0, kuu = 0, ken = 0, keu = 0, knu = 0;
         if (T::ae) kee = -atan_sum8<0, XM>(c);
         if (T::an) knn = -atan_sum8<1, XM>(c);
-        if (T::au) kuu = -atan_sum8<2, XM>(c);
+        if (T::au) {
+            if (XM && T::ae && T::an) {
+                // all three diagonal kernels wanted: the 8-vertex sums satisfy Laplace/Poisson
+                // identically, k_ee + k_nn + k_uu = 0 outside and -4 pi inside the prism
+                // (+4 pi per inverted axis), so the third one costs two additions instead of
+                // four atan pair terms and an atan2. Boundary points never get here.
+                const bool inside = (is_neg(e[0]) != is_neg(e[1])) && (is_neg(n[0]) != is_neg(n[1]))
+                                    && (is_neg(u[0]) != is_neg(u[1]));
+                const bool flipped = (is_neg(e[0]) != is_neg(n[0])) != is_neg(u[0]);
+                const double trace = inside ? (flipped ? 4 * kPi : -4 * kPi) : 0.0;
+                kuu = trace - (kee + knn);
+            } else {
+                kuu = -atan_sum8<2, XM>(c);
+            }
+        }
         if (T::lu) ken = log_sum8<2, XM>(c);
         if (T::ln) keu = log_sum8<1, XM>(c);
         if (T::le) knu = log_sum8<0, XM>(c);

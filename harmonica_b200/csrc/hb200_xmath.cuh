@@ -147,6 +147,45 @@ HB_HD double fast_log(double a)
     return fma((double)k, kLn2, lc) + l1p;
 }
 
+// log1p(z) for |z| < 2^-8 (the polynomial of fast_log without the table reduction)
+HB_HD double log1p_small(double z)
+{
+    const double z2 = z * z;
+    double p = fma(kLogC[5], z, kLogC[4]);
+    p = fma(p, z, kLogC[3]);
+    p = fma(p, z, kLogC[2]);
+    p = fma(p, z, kLogC[1]);
+    p = fma(p, z, kLogC[0]);
+    return fma(z2, p, z);
+}
+
+// x > 0 and |y| < x / 32, decided on the integer pipe (positive doubles order like integers;
+// subtracting 5 from the exponent field divides by 32)
+HB_HD bool small_angle(double y, double x)
+{
+    int64_t bx, by;
+#if defined(__CUDA_ARCH__)
+    bx = __double_as_longlong(x);
+    by = __double_as_longlong(y);
+#else
+    memcpy(&bx, &x, 8);
+    memcpy(&by, &y, 8);
+#endif
+    return bx - (5LL << 52) > (by & 0x7fffffffffffffffLL);
+}
+
+// atan(y / x) for x > 0, |y| < x / 32: same polynomial as fast_atan2 after its reduction
+HB_HD double atan_small(double y, double x)
+{
+    const double a = y * fast_rcp(x);
+    const double s = a * a;
+    double p = fma(kAtanC[4], s, kAtanC[3]);
+    p = fma(p, s, kAtanC[2]);
+    p = fma(p, s, kAtanC[1]);
+    p = fma(p, s, kAtanC[0]);
+    return fma(a * s, p, a);
+}
+
 // atan2(y, x) in (-pi, pi] for finite x, y not both zero.
 // q = min/max in [0, 1]; c = round(16 q)/16 from a 20-bit estimate;
 // atan q = atan c + atan((min - c max)/(max + c min)), |argument| <= 1/32.
