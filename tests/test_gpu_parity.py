@@ -297,7 +297,11 @@ def test_progressbar_gives_identical_results(hb, medium):
     coords, prisms, density = medium
     a = hb.prism_gravity(coords, prisms[:200], density[:200], "g_z")
     b = hb.prism_gravity(coords, prisms[:200], density[:200], "g_z", progressbar=True)
-    npt.assert_array_equal(a, b)
+    # the reference asserts allclose here too (test/test_prism.py:325-377); the progress bar
+    # splits the observers into chunks, which regroups lanes into warps and source chunks, so
+    # the warp-uniform choice of far-field sequences may differ at rounding level
+    npt.assert_allclose(a, b, rtol=0, atol=1e-11 * np.max(np.abs(a)))
+    npt.assert_array_equal(a, hb.prism_gravity(coords, prisms[:200], density[:200], "g_z"))
 
 
 def test_few_observers_many_sources_uses_source_chunks(hb, variant):
