@@ -43,6 +43,10 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 # FP64-pipe instruction equivalents per pair of the REFERENCE algorithm
 I_PAIR = {"layer_gz": 1068, "c1_gz": 1068, "tensor": 2020, "mag_b": 2100, "eqs": 26.5}
 NOMINAL_FP64_FLOPS = 148 * 64 * 2 * 1.965e9  # 37.2 TFLOP/s
+# executed thread-instructions per pair of the CURRENT kernels, from the committed ncu source
+# pages (profiles/r1_opmix_*_v7.txt, profiles/r1_ncu_eqs_v3.txt): (FP64 pipe, all other pipes)
+EXECUTED_PER_PAIR = {"layer_gz": (224.1, 167.3), "c1_gz": (224.1, 167.3), "tensor": (288.1, 182.8),
+                     "eqs": (12.0, 5.1)}
 
 
 # ------------------------------------------------------------------ workloads
@@ -403,6 +407,18 @@ def run_b200(args):
         per_gpu = value / world
         f_pair = 2.0 * I_PAIR[args.workload]
         achieved = per_gpu * f_pair / 1e12
+        executed = None
+        if args.workload in EXECUTED_PER_PAIR and clocks and clocks.get("sm_mhz"):
+            f64, other = EXECUTED_PER_PAIR[args.workload]
+            slots = 148 * 4 * clocks["sm_mhz"] * 1e6 * 32  # thread-level issue slots / s
+            executed = {
+                "fp64_instr_per_pair": f64, "other_instr_per_pair": other,
+                "source": "ncu source-page counts of this kernel build, profiles/r1_opmix_*",
+                "fp64_pipe_frac": per_gpu * f64 * 2 / fp64_peak,
+                "issue_bound_frac": per_gpu * (2 * f64 + other) / slots,
+                "note": "an FP64 warp instruction occupies 2 issue slots on this part: time ~ "
+                        "(2*FP64 + other) / issue rate (DESIGN.md section 4)",
+            }
         line = {
             "metric": "prism-observer pair evals/sec", "value": value, "unit": "pair/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -429,6 +445,7 @@ def run_b200(args):
                         "the merged-transcendental kernel executes fewer instructions per pair, "
                         "pipe utilisation is in profiles/",
                 "traffic": None,
+                "executed": executed,
             },
             "cpu_baseline": cpu_baseline,
         }  # fmt: skip

@@ -200,7 +200,8 @@ HB_HD PairPreds make_preds(const PairGeom& g)
 // squared shifts is zero or more than 2^50 times smaller than the largest one. This covers
 //  * an exactly-zero shift (observer in the plane of a face: all singular-point rules), and
 //  * every pair on which the reference's on-axis safe_log branch (r == -x) can fire: that
-//    needs y^2 + z^2 < 2^-52 x^2, so when all squares are within 2^50 of each other r != |x|.
+//    needs y^2 + z^2 < 2^-52 x^2, so when all squares are within 2^50 of each other r != |x|,
+//  * pairs at absurd length scales (see below).
 // Non-negative doubles order like their bit patterns, so this runs on the integer pipe.
 HB_HD bool needs_exact_path(const PairGeom& g)
 {
@@ -213,7 +214,10 @@ HB_HD bool needs_exact_path(const PairGeom& g)
         lo = h[q] < lo ? h[q] : lo;
         hi = h[q] > hi ? h[q] : hi;
     }
-    return lo + (50u << 20) < hi;
+    // The third clause keeps the merged products (up to the 16th power of a length) inside the
+    // float64 range: pairs whose largest squared shift is outside [2^-119, 2^119] m^2 (lengths
+    // beyond ~1e-18 .. 1e18 m) use the reference's formulation as well.
+    return (lo + (50u << 20) < hi) | (hi - 0x38800000u > 0x47600000u - 0x38800000u);
 }
 
 // NaN rule per field set (gravity.py:272-449 predicate sets == choclo's)

@@ -275,3 +275,19 @@ def test_fused_diagonal_components_inside_and_inverted_prisms(variant):
         want = np.array(O.prism_magnetic(coords, p, (M[:, 0], M[:, 1], M[:, 2]), "b"))
         for k in range(3):
             assert max_rel(b[k] * CM * 1e9, want[k]) <= TOL
+
+
+@pytest.mark.parametrize("scale", [1e-24, 1e-12, 1e12, 1e24, 1e60])
+def test_extreme_length_scales_fall_back_to_the_reference_formulation(scale):
+    """the merged products would leave the float64 range at absurd length scales; such pairs use
+    the direct path, so the result is whatever the reference gives (no spurious inf/nan)"""
+    coords, prisms, density = config1(40, 50, seed=15)
+    coords = tuple(c * scale for c in coords)
+    prisms = prisms * scale
+    prm = np.zeros((40, 3))
+    prm[:, 0] = G * density
+    for f in ("g_z", "g_zz", "g_en", "potential"):
+        out, _ = harness_prism(f, 2, coords, prisms, prm)
+        want = _si(coords, prisms, density, f)
+        assert np.isfinite(out[0]).all() == np.isfinite(want).all()
+        assert max_rel(out[0], want) <= 1e-8, f
