@@ -9,8 +9,10 @@ function signatures, checks, messages, units and sign conventions over a thin
 ctypes binding. There is no CPU fallback.
 """
 
+from ._dipole import dipole_magnetic
 from ._eqs import (
     EquivalentSources,
+    EquivalentSourcesSph,
     eqs_jacobian,
     eqs_predict,
     predict_numba_parallel,
@@ -27,6 +29,8 @@ __version__ = "0.1.0"
 __all__ = [
     "DatasetAccessorPrismLayer",
     "EquivalentSources",
+    "EquivalentSourcesSph",
+    "dipole_magnetic",
     "HarmonicaB200Error",
     "PrismLayer",
     "eqs_jacobian",

@@ -57,6 +57,10 @@ SIGNATURES = {
     "hb200_point_gravity": (
         _int, [_dp, _dp, _dp, _i64, _dp, _dp, _dp, _dp, _i64, _u32, _int, _int, _dp, _u32p]),
     "hb200_eqs_predict": (_int, [_dp, _dp, _dp, _i64, _dp, _dp, _dp, _dp, _i64, _int, _dp, _u32p]),
+    "hb200_eqs_predict_spherical": (
+        _int, [_dp, _dp, _dp, _i64, _dp, _dp, _dp, _dp, _i64, _int, _dp, _u32p]),
+    "hb200_dipole_magnetic": (
+        _int, [_dp, _dp, _dp, _i64, _dp, _dp, _dp, _dp, _dp, _dp, _i64, _u32, _int, _dp, _u32p]),
     "hb200_eqs_jacobian": (_int, [_dp, _dp, _dp, _i64, _dp, _dp, _dp, _i64, _dp]),
     "hb200_prism_ws_bytes": (_sz, [_i64, _i64, _int]),
     "hb200_point_ws_bytes": (_sz, [_i64, _i64]),

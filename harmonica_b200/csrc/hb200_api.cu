@@ -231,7 +231,7 @@ template <int FIELD> void launch_point_cart(const PointArgs& a, dim3 grid, cudaS
 int run_point_pass(int field, int spherical, const double* oe, const double* on, const double* ou,
                    int64_t n_obs, const double* packed, int64_t n_src, double scale, double* out,
                    double* partial, size_t partial_bytes, unsigned* d_flags, int sms,
-                   cudaStream_t st)
+                   cudaStream_t st, double gconst = kG)
 {
     if (n_obs == 0) return HB200_OK;
     if (n_src == 0) {
@@ -249,7 +249,7 @@ int run_point_pass(int field, int spherical, const double* oe, const double* on,
     a.oe = oe; a.on = on; a.ou = ou; a.n_obs = n_obs;
     a.packed = packed; a.n_src = n_src; a.chunk_len = chunk_len;
     a.out = chunks > 1 ? partial : out;
-    a.scale = scale; a.flags = d_flags;
+    a.scale = scale; a.flags = d_flags; a.gconst = gconst;
     dim3 grid((unsigned)((n_obs + opb - 1) / opb), (unsigned)chunks);
     if (spherical) {
         if (field == F_POT) point_kernel_sph<F_POT><<<grid, kBlock, 0, st>>>(a);
@@ -437,9 +437,83 @@ int point_gravity_dev_impl(const double* oe, const double* on, const double* ou,
         const double scale = (raw || !scale_by_G) ? 1.0 : point_scale(f);
         int rc = run_point_pass(f, spherical, oe, on, ou, n_obs, packed, n_src, scale,
                                 out + (int64_t)slot * n_obs, partial, partial_bytes, d_flags, sms,
-                                st);
+                                st, scale_by_G ? kG : 1.0);
         if (rc) return rc;
         slot++;
+    }
+    return HB200_OK;
+}
+
+// dipole_magnetic: component_mask 7 = fused b, else single components one pass each
+size_t dipole_ws_bytes(int64_t n_obs, int64_t n_src, int sms)
+{
+    return align_up((size_t)n_src * kDipoleStride * sizeof(double))
+         + partial_bytes_for(n_obs, n_src, 3, kBlock * kDipoleObs, sms) + 256;
+}
+
+int dipole_magnetic_dev_impl(const double* oe, const double* on, const double* ou, int64_t n_obs,
+                             const double* pe, const double* pn, const double* pu,
+                             const double* me, const double* mn, const double* mu, int64_t n_src,
+                             uint32_t cmask, bool raw, double* out, unsigned* d_flags, void* wsp,
+                             size_t ws_bytes, int sms, cudaStream_t st)
+{
+    if (n_obs == 0) return HB200_OK;
+    const int nf = popcount(cmask);
+    if (n_src == 0) {
+        CU(cudaMemsetAsync(out, 0, sizeof(double) * nf * n_obs, st));
+        return HB200_OK;
+    }
+    Ws ws(wsp, ws_bytes);
+    double* packed = ws.take((size_t)n_src * kDipoleStride * sizeof(double));
+    if (!packed) return fail(HB200_EINVAL, "workspace too small");
+    pack_dipoles_kernel<<<(unsigned)((n_src + 255) / 256), 256, 0, st>>>(pe, pn, pu, me, mn, mu, n_src,
+                                                                        packed);
+    CU(cudaGetLastError());
+    g_launches += 1;
+    double* partial = (double*)(ws.base + ws.used);
+    const size_t partial_bytes = ws.left();
+    // dipole.py:195-197, :270: T -> nT; mu0/4pi as choclo
+    const double mu0 = 4 * kPi * 1e-7;
+    const double scale = raw ? 1.0 : mu0 / 4 / kPi * 1e9;
+    const int opb = kBlock * kDipoleObs;
+    int slot = 0;
+    for (int pass = 0; pass < 3; pass++) {
+        int comp, nout;
+        if (cmask == HB200_B_ALL) {
+            if (pass > 0) break;
+            comp = -1; nout = 3;
+        } else {
+            if (!(cmask >> pass & 1u)) continue;
+            comp = pass; nout = 1;
+        }
+        int64_t chunk_len = 0;
+        int chunks = choose_chunks(n_obs, n_src, opb, sms, &chunk_len);
+        if (chunks > 1 && (size_t)chunks * nout * n_obs * sizeof(double) > partial_bytes) {
+            chunks = 1;
+            chunk_len = n_src;
+        }
+        PointArgs a;
+        a.oe = oe; a.on = on; a.ou = ou; a.n_obs = n_obs;
+        a.packed = packed; a.n_src = n_src; a.chunk_len = chunk_len;
+        double* dst = out + (int64_t)slot * n_obs;
+        a.out = chunks > 1 ? partial : dst;
+        a.scale = scale; a.flags = d_flags; a.gconst = 1.0;
+        dim3 grid((unsigned)((n_obs + opb - 1) / opb), (unsigned)chunks);
+        if (comp < 0) dipole_kernel<-1><<<grid, kBlock, 0, st>>>(a);
+        else if (comp == 0) dipole_kernel<0><<<grid, kBlock, 0, st>>>(a);
+        else if (comp == 1) dipole_kernel<1><<<grid, kBlock, 0, st>>>(a);
+        else dipole_kernel<2><<<grid, kBlock, 0, st>>>(a);
+        CU(cudaGetLastError());
+        g_launches += chunks > 1 ? 2 : 1;
+        if (chunks > 1) {
+            Scales sc;
+            for (int c = 0; c < 6; c++) sc.s[c] = scale;
+            const int64_t total = (int64_t)nout * n_obs;
+            reduce_partials_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(partial, chunks,
+                                                                                   nout, n_obs, sc, dst);
+            CU(cudaGetLastError());
+        }
+        slot += nout;
     }
     return HB200_OK;
 }
@@ -610,6 +684,11 @@ size_t ws_point(int64_t no, int64_t ns, int nf, int sms)
 {
     (void)nf;
     return point_ws_bytes(no, ns, sms);
+}
+size_t ws_dipole(int64_t no, int64_t ns, int nf, int sms)
+{
+    (void)nf;
+    return dipole_ws_bytes(no, ns, sms);
 }
 
 Scales gravity_scales_for_mask(uint32_t mask)
@@ -863,6 +942,53 @@ int hb200_eqs_predict(const double* easting, const double* northing, const doubl
     for (int c = 0; c < 6; c++) sc.s[c] = 1.0;
     return run_host_job(easting, northing, upward, n_obs, arrays, n_src, 1, 0, shard_mode, true, sc,
                         out, flags, launch, ws_point);
+}
+
+int hb200_eqs_predict_spherical(const double* longitude, const double* latitude,
+                                const double* radius, int64_t n_obs, const double* src_longitude,
+                                const double* src_latitude, const double* src_radius,
+                                const double* coefs, int64_t n_src, int shard_mode, double* out,
+                                uint32_t* flags)
+{
+    std::vector<HostArray> arrays = {{src_longitude, n_src, 1, true}, {src_latitude, n_src, 1, true},
+                                     {src_radius, n_src, 1, true}, {coefs, n_src, 1, true}};
+    auto launch = [=](Dev& dev, const double* oe, const double* on, const double* ou, int64_t no,
+                      std::vector<double*>& arr, int64_t ns, bool raw, double* d_out, void* ws,
+                      size_t wsb) {
+        return point_gravity_dev_impl(oe, on, ou, no, arr[0], arr[1], arr[2], arr[3], ns,
+                                      1u << F_POT, 1, 0, raw, d_out, dev.d_flags, ws, wsb, dev.sms,
+                                      dev.st);
+    };
+    Scales sc;
+    for (int c = 0; c < 6; c++) sc.s[c] = 1.0;
+    return run_host_job(longitude, latitude, radius, n_obs, arrays, n_src, 1, 0, shard_mode, true, sc,
+                        out, flags, launch, ws_point);
+}
+
+int hb200_dipole_magnetic(const double* easting, const double* northing, const double* upward,
+                          int64_t n_obs, const double* src_easting, const double* src_northing,
+                          const double* src_upward, const double* moment_e, const double* moment_n,
+                          const double* moment_u, int64_t n_src, uint32_t component_mask,
+                          int shard_mode, double* out, uint32_t* flags)
+{
+    if (!component_mask || (component_mask >> 3))
+        return fail(HB200_EINVAL, "bad component_mask 0x%x", component_mask);
+    const int nf = popcount(component_mask);
+    std::vector<HostArray> arrays = {{src_easting, n_src, 1, true}, {src_northing, n_src, 1, true},
+                                     {src_upward, n_src, 1, true}, {moment_e, n_src, 1, true},
+                                     {moment_n, n_src, 1, true}, {moment_u, n_src, 1, true}};
+    auto launch = [=](Dev& dev, const double* oe, const double* on, const double* ou, int64_t no,
+                      std::vector<double*>& arr, int64_t ns, bool raw, double* d_out, void* ws,
+                      size_t wsb) {
+        return dipole_magnetic_dev_impl(oe, on, ou, no, arr[0], arr[1], arr[2], arr[3], arr[4],
+                                        arr[5], ns, component_mask, raw, d_out, dev.d_flags, ws, wsb,
+                                        dev.sms, dev.st);
+    };
+    const double mu0 = 4 * kPi * 1e-7;
+    Scales sc;
+    for (int c = 0; c < 6; c++) sc.s[c] = mu0 / 4 / kPi * 1e9;
+    return run_host_job(easting, northing, upward, n_obs, arrays, n_src, nf, 0, shard_mode, true, sc,
+                        out, flags, launch, ws_dipole);
 }
 
 int hb200_eqs_jacobian(const double* easting, const double* northing, const double* upward,

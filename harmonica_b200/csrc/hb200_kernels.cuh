@@ -268,6 +268,7 @@ struct PointArgs {
     double* out;
     double scale;
     unsigned* flags;
+    double gconst;  // spherical kernels: G (point masses) or 1 (equivalent sources)
 };
 
 constexpr int kPointObs = 4;  // observers per thread (amortises the record loads)
@@ -347,10 +348,10 @@ __global__ void __launch_bounds__(kBlock) point_kernel_sph(const PointArgs a)
             const double dist = sqrt(d2);
             double k;
             if (FIELD == F_POT) {
-                k = 1 / dist * kG;
+                k = 1 / dist * a.gconst;
             } else {
                 const double delta_z = rad - q1.y * cospsi;
-                k = -kG * delta_z / (dist * dist * dist);
+                k = -a.gconst * delta_z / (dist * dist * dist);
             }
             acc += q2.x * k;
         }
@@ -358,6 +359,89 @@ __global__ void __launch_bounds__(kBlock) point_kernel_sph(const PointArgs a)
     if (i < a.n_obs) {
         if (gridDim.y == 1) a.out[i] = acc * a.scale;
         else a.out[(int64_t)blockIdx.y * a.n_obs + i] = acc;
+    }
+    if (flags && a.flags) atomicOr(a.flags, flags);
+}
+
+// ----------------------------------------------------------- dipole kernel
+// dipole.py:329-347 / :386-400 with choclo.dipole.magnetic_*:
+//   B = mu0/4pi (3 (m.r) r / d^5 - m / d^3),  r = observer - dipole.
+// Records: 6 doubles  e n u | m_e m_n m_u. COMP < 0: all three components.
+constexpr int kDipoleStride = 6;
+
+__global__ void pack_dipoles_kernel(const double* __restrict__ pe, const double* __restrict__ pn,
+                                    const double* __restrict__ pu, const double* __restrict__ me,
+                                    const double* __restrict__ mn, const double* __restrict__ mu,
+                                    int64_t n, double* __restrict__ packed)
+{
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    double* q = packed + j * kDipoleStride;
+    q[0] = pe[j]; q[1] = pn[j]; q[2] = pu[j];
+    q[3] = me[j]; q[4] = mn[j]; q[5] = mu[j];
+}
+
+constexpr int kDipoleObs = 2;
+
+template <int COMP>
+__global__ void __launch_bounds__(kBlock) dipole_kernel(const PointArgs a)
+{
+    constexpr int NOUT = COMP < 0 ? 3 : 1;
+    __shared__ double2 tile[kTile * kDipoleStride / 2];
+    double E[kDipoleObs], N[kDipoleObs], U[kDipoleObs], acc[kDipoleObs][NOUT];
+    int64_t idx[kDipoleObs];
+#pragma unroll
+    for (int o = 0; o < kDipoleObs; o++) {
+        idx[o] = ((int64_t)blockIdx.x * kDipoleObs + o) * kBlock + threadIdx.x;
+        const int64_t ic = idx[o] < a.n_obs ? idx[o] : a.n_obs - 1;
+        E[o] = a.oe[ic]; N[o] = a.on[ic]; U[o] = a.ou[ic];
+#pragma unroll
+        for (int c = 0; c < NOUT; c++) acc[o][c] = 0.0;
+    }
+    unsigned flags = 0;
+    const int64_t begin = (int64_t)blockIdx.y * a.chunk_len;
+    const int64_t end = begin + a.chunk_len < a.n_src ? begin + a.chunk_len : a.n_src;
+    const double2* src = reinterpret_cast<const double2*>(a.packed);
+    for (int64_t t0 = begin; t0 < end; t0 += kTile) {
+        const int cnt = (int)((end - t0) < kTile ? (end - t0) : kTile);
+        __syncthreads();
+        for (int x = threadIdx.x; x < cnt * (kDipoleStride / 2); x += kBlock)
+            tile[x] = src[t0 * (kDipoleStride / 2) + x];
+        __syncthreads();
+#pragma unroll 2
+        for (int s = 0; s < cnt; s++) {
+            const double2 q0 = tile[3 * s], q1 = tile[3 * s + 1], q2 = tile[3 * s + 2];
+            const double me = q1.y, mn = q2.x, mu = q2.y;
+#pragma unroll
+            for (int o = 0; o < kDipoleObs; o++) {
+                const double re = E[o] - q0.x, rn = N[o] - q0.y, ru = U[o] - q1.x;
+                const double d2 = re * re + rn * rn + ru * ru;
+                if (is_pos_zero(d2)) flags |= FLAG_ZERO_DIV;
+                const double inv = point_rsqrt(d2);
+                const double inv2 = inv * inv;
+                const double inv3 = inv2 * inv;
+                const double t = 3.0 * (me * re + mn * rn + mu * ru) * inv2;
+                if (COMP < 0) {
+                    acc[o][0] = fma(fma(t, re, -me), inv3, acc[o][0]);
+                    acc[o][1] = fma(fma(t, rn, -mn), inv3, acc[o][1]);
+                    acc[o][2] = fma(fma(t, ru, -mu), inv3, acc[o][2]);
+                } else {
+                    const double r = COMP == 0 ? re : COMP == 1 ? rn : ru;
+                    const double m = COMP == 0 ? me : COMP == 1 ? mn : mu;
+                    acc[o][0] = fma(fma(t, r, -m), inv3, acc[o][0]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < kDipoleObs; o++) {
+        if (idx[o] < a.n_obs) {
+#pragma unroll
+            for (int c = 0; c < NOUT; c++) {
+                if (gridDim.y == 1) a.out[c * a.n_obs + idx[o]] = acc[o][c] * a.scale;
+                else a.out[((int64_t)blockIdx.y * NOUT + c) * a.n_obs + idx[o]] = acc[o][c];
+            }
+        }
     }
     if (flags && a.flags) atomicOr(a.flags, flags);
 }

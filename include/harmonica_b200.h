@@ -135,6 +135,24 @@ int hb200_eqs_predict(const double* easting, const double* northing, const doubl
                       const double* src_upward, const double* coefs, int64_t n_src,
                       int shard_mode, double* out, uint32_t* flags);
 
+/* replaces predict with greens_func_spherical (EquivalentSourcesSph.predict,
+ * _equivalent_sources/spherical.py:219-248, 412-424): longitude, latitude in
+ * degrees, radius in metres; out[i] = sum_j coefs[j] / distance_spherical */
+int hb200_eqs_predict_spherical(const double* longitude, const double* latitude,
+                                const double* radius, int64_t n_obs, const double* src_longitude,
+                                const double* src_latitude, const double* src_radius,
+                                const double* coefs, int64_t n_src, int shard_mode, double* out,
+                                uint32_t* flags);
+
+/* replaces _jit_dipole_magnetic_field_cartesian / _jit_dipole_magnetic_component_cartesian,
+ * _forward/dipole.py:292-415 (choclo.dipole.magnetic_*), output in nT. component_mask as for
+ * hb200_prism_magnetic (HB200_B_ALL = one fused pass). */
+int hb200_dipole_magnetic(const double* easting, const double* northing, const double* upward,
+                          int64_t n_obs, const double* src_easting, const double* src_northing,
+                          const double* src_upward, const double* moment_e, const double* moment_n,
+                          const double* moment_u, int64_t n_src, uint32_t component_mask,
+                          int shard_mode, double* out, uint32_t* flags);
+
 /* replaces jacobian, _equivalent_sources/utils.py:54-74: jac[i*n_src+j] = 1/dist */
 int hb200_eqs_jacobian(const double* easting, const double* northing, const double* upward,
                        int64_t n_obs, const double* src_easting, const double* src_northing,

@@ -318,6 +318,37 @@ def _point(which):
     return gravity
 
 
+# -------------------------------------------------------------------- dipoles
+@jit(nopython=True)
+def dipole_magnetic_field(E, N, U, eq, nq, uq, me, mn, mu):
+    re, rn, ru = E - eq, N - nq, U - uq
+    d = np.sqrt(re * re + rn * rn + ru * ru)
+    dot = me * re + mn * rn + mu * ru
+    cm = VACUUM_MAGNETIC_PERMEABILITY / 4 / np.pi
+    d3 = d * d * d
+    d5 = d3 * d * d
+    return (
+        cm * (3 * dot * re / d5 - me / d3),
+        cm * (3 * dot * rn / d5 - mn / d3),
+        cm * (3 * dot * ru / d5 - mu / d3),
+    )
+
+
+@jit(nopython=True)
+def dipole_magnetic_e(E, N, U, eq, nq, uq, me, mn, mu):
+    return dipole_magnetic_field(E, N, U, eq, nq, uq, me, mn, mu)[0]
+
+
+@jit(nopython=True)
+def dipole_magnetic_n(E, N, U, eq, nq, uq, me, mn, mu):
+    return dipole_magnetic_field(E, N, U, eq, nq, uq, me, mn, mu)[1]
+
+
+@jit(nopython=True)
+def dipole_magnetic_u(E, N, U, eq, nq, uq, me, mn, mu):
+    return dipole_magnetic_field(E, N, U, eq, nq, uq, me, mn, mu)[2]
+
+
 def install_fake_choclo():
     """Register fake ``choclo`` modules in sys.modules (idempotent)."""
     if "choclo" in sys.modules and getattr(sys.modules["choclo"], "__hb200_fake__", False):
@@ -348,7 +379,12 @@ def install_fake_choclo():
     point = types.ModuleType("choclo.point")
     for idx, name in enumerate(("pot", "e", "n", "u", "ee", "nn", "uu", "en", "eu", "nu")):
         setattr(point, f"gravity_{name}", _point(idx))
-    choclo.constants, choclo.prism, choclo.point = constants, prism, point
+    dipole = types.ModuleType("choclo.dipole")
+    dipole.magnetic_field = dipole_magnetic_field
+    dipole.magnetic_e = dipole_magnetic_e
+    dipole.magnetic_n = dipole_magnetic_n
+    dipole.magnetic_u = dipole_magnetic_u
+    choclo.constants, choclo.prism, choclo.point, choclo.dipole = constants, prism, point, dipole
     sys.modules.update(
         {
             "choclo": choclo,
@@ -356,6 +392,7 @@ def install_fake_choclo():
             "choclo.prism": prism,
             "choclo.prism._utils": utils,
             "choclo.point": point,
+            "choclo.dipole": dipole,
         }
     )
     return choclo

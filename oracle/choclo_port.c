@@ -486,3 +486,98 @@ void hbo_eqs_jacobian_loop(int64_t n_obs, const double* oe, const double* on, co
             jac[i * n_src + j] = 1 / sqrt(de * de + dn * dn + du * du);
         }
 }
+
+/* ------------------------------------------------------------ dipoles ---- */
+/* choclo.dipole.magnetic_field [RECALL; the dipole formula itself is the pin]:
+ * B = mu0/4pi * (3 (m.r) r / d^5 - m / d^3), r = observer - dipole. Reference
+ * loop: src/harmonica/_forward/dipole.py:329-347 (vector), :386-400 (component).
+ * *zero_div is set for a coincident observer/dipole (the reference raises). */
+void hbo_dipole_magnetic_field(double E, double N, double U, double eq, double nq, double uq,
+                               double me, double mn, double mu, double out[3], int* zero_div)
+{
+    const double re = E - eq, rn = N - nq, ru = U - uq;
+    const double d = sqrt(re * re + rn * rn + ru * ru);
+    if (d == 0.0 && zero_div) *zero_div = 1;
+    const double dot = me * re + mn * rn + mu * ru;
+    const double mu0 = 4 * HBO_PI * 1e-7;
+    const double cm = mu0 / 4 / HBO_PI;
+    const double d3 = d * d * d, d5 = d3 * d * d;
+    out[0] = cm * (3 * dot * re / d5 - me / d3);
+    out[1] = cm * (3 * dot * rn / d5 - mn / d3);
+    out[2] = cm * (3 * dot * ru / d5 - mu / d3);
+}
+
+int hbo_dipole_magnetic_loop(int component, int64_t n_obs, const double* oe, const double* on,
+                             const double* ou, int64_t n_src, const double* pe, const double* pn,
+                             const double* pu, const double* me, const double* mn,
+                             const double* mu, double* out, int nthreads)
+{
+    int zero_div = 0;
+    set_threads(nthreads);
+#pragma omp parallel for schedule(static) reduction(| : zero_div)
+    for (int64_t i = 0; i < n_obs; i++) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, b[3];
+        int zd = 0;
+        for (int64_t j = 0; j < n_src; j++) {
+            hbo_dipole_magnetic_field(oe[i], on[i], ou[i], pe[j], pn[j], pu[j], me[j], mn[j], mu[j],
+                                      b, &zd);
+            a0 += b[0];
+            a1 += b[1];
+            a2 += b[2];
+        }
+        zero_div |= zd;
+        if (component < 0) {
+            out[i] += a0;
+            out[n_obs + i] += a1;
+            out[2 * n_obs + i] += a2;
+        } else {
+            out[i] += (component == 0 ? a0 : component == 1 ? a1 : a2);
+        }
+    }
+    return zero_div;
+}
+
+/* EquivalentSourcesSph.predict: _equivalent_sources/utils.py:86-97 with
+ * greens_func_spherical (spherical.py:412-424) = 1 / distance_spherical
+ * (_forward/utils.py:121-160, 198-201); angles in degrees. The per-point
+ * radians/cos/sin the reference recomputes for every pair are hoisted (same
+ * values). scratch: 3 * (n_obs + n_src) doubles. */
+int hbo_eqs_predict_spherical_loop(int64_t n_obs, const double* lon, const double* lat,
+                                   const double* rad, int64_t n_src, const double* lon_p,
+                                   const double* lat_p, const double* rad_p, const double* coefs,
+                                   double* out, double* scratch, int nthreads)
+{
+    const double d2r = HBO_PI / 180.0;
+    double* lam = scratch;
+    double* cphi = lam + n_obs;
+    double* sphi = cphi + n_obs;
+    double* lam_p = sphi + n_obs;
+    double* cphi_p = lam_p + n_src;
+    double* sphi_p = cphi_p + n_src;
+    for (int64_t i = 0; i < n_obs; i++) {
+        lam[i] = lon[i] * d2r;
+        cphi[i] = cos(lat[i] * d2r);
+        sphi[i] = sin(lat[i] * d2r);
+    }
+    for (int64_t j = 0; j < n_src; j++) {
+        lam_p[j] = lon_p[j] * d2r;
+        cphi_p[j] = cos(lat_p[j] * d2r);
+        sphi_p[j] = sin(lat_p[j] * d2r);
+    }
+    int zero_div = 0;
+    set_threads(nthreads);
+#pragma omp parallel for schedule(static) reduction(| : zero_div)
+    for (int64_t i = 0; i < n_obs; i++) {
+        double acc = out[i];
+        for (int64_t j = 0; j < n_src; j++) {
+            double coslambda = cos(lam_p[j] - lam[i]);
+            double cospsi = sphi_p[j] * sphi[i] + cphi_p[j] * cphi[i] * coslambda;
+            double dr = rad[i] - rad_p[j];
+            double dist = sqrt(dr * dr + 2 * rad[i] * rad_p[j] * (1 - cospsi));
+            if (dist == 0.0) zero_div = 1;
+            acc += coefs[j] * (1 / dist);
+        }
+        out[i] = acc;
+    }
+    return zero_div;
+}

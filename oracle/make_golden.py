@@ -173,6 +173,22 @@ def main():
     np.savez(os.path.join(OUT, "eqs_predict.npz"), points=np.stack(pts), coefs=coefs,
              easting=obs_above[0], northing=obs_above[1], upward=obs_above[2], predicted=res,
              jacobian=jac)
+    # ---- 8. dipole magnetic (reference wrapper + loops, restated choclo.dipole kernels)
+    dip = (rng.uniform(-5e3, 5e3, 70), rng.uniform(-5e3, 5e3, 70), rng.uniform(-3e3, -100, 70))
+    moments = tuple(rng.normal(size=70) * 1e6 for _ in range(3))
+    data = dict(dipoles=np.stack(dip), moments=np.stack(moments), easting=obs_above[0],
+                northing=obs_above[1], upward=obs_above[2])
+    data["b"] = np.stack(ref.dipole.dipole_magnetic(obs_above, dip, moments, "b"))
+    for f in ("b_e", "b_n", "b_u"):
+        data[f] = ref.dipole.dipole_magnetic(obs_above, dip, moments, f)
+    np.savez(os.path.join(OUT, "dipole_magnetic.npz"), **data)
+
+    # ---- 9. spherical equivalent sources predict: the reference's loop + distance_spherical
+    greens_sph = ref_shim.greens_func_spherical()
+    res = np.zeros(80)
+    ref.eqs_utils.predict_numba_parallel((olon, olat, orad), (lon, lat, rad), coefs, res, greens_sph)
+    np.savez(os.path.join(OUT, "eqs_predict_spherical.npz"), points=np.stack([lon, lat, rad]),
+             coefs=coefs, obs=np.stack([olon, olat, orad]), predicted=res)
     print("golden fixtures written to", OUT)
     for name in sorted(os.listdir(OUT)):
         print(" ", name, os.path.getsize(os.path.join(OUT, name)), "bytes")

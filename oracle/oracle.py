@@ -95,6 +95,14 @@ def lib():
         L.hbo_eqs_jacobian_loop.argtypes = [
             _i64, _dp, _dp, _dp, _i64, _dp, _dp, _dp, _dp, ctypes.c_int,
         ]  # fmt: skip
+        L.hbo_dipole_magnetic_loop.restype = ctypes.c_int
+        L.hbo_dipole_magnetic_loop.argtypes = [
+            ctypes.c_int, _i64, _dp, _dp, _dp, _i64, _dp, _dp, _dp, _dp, _dp, _dp, _dp, ctypes.c_int,
+        ]  # fmt: skip
+        L.hbo_eqs_predict_spherical_loop.restype = ctypes.c_int
+        L.hbo_eqs_predict_spherical_loop.argtypes = [
+            _i64, _dp, _dp, _dp, _i64, _dp, _dp, _dp, _dp, _dp, _dp, ctypes.c_int,
+        ]  # fmt: skip
         _LIB = L
     return _LIB
 
@@ -275,3 +283,40 @@ def eqs_jacobian(coordinates, points, nthreads=0):
         oe.size, _p(oe), _p(on), _p(ou), pe.size, _p(pe), _p(pn), _p(pu), _p(jac), nthreads
     )
     return jac
+
+
+def dipole_magnetic(coordinates, dipoles, magnetic_moments, field, nthreads=0):
+    """Restatement of the reference's ``dipole_magnetic`` (dipole.py:97-137, 186-200, 252-271)."""
+    if field not in ("b", "b_e", "b_n", "b_u"):
+        raise ValueError(f"Invalid field '{field}'. Please choose one of 'b, b_e, b_n, b_u'.")
+    cast, (oe, on, ou) = _coords(coordinates)
+    pe, pn, pu = (_f64(np.atleast_1d(p).ravel()) for p in dipoles[:3])
+    me, mn, mu = (_f64(np.atleast_1d(m).ravel()) for m in magnetic_moments)
+    comp = {"b": -1, "b_e": 0, "b_n": 1, "b_u": 2}[field]
+    out = np.zeros((3 if comp < 0 else 1) * oe.size, dtype=np.float64)
+    zd = lib().hbo_dipole_magnetic_loop(
+        comp, oe.size, _p(oe), _p(on), _p(ou), pe.size, _p(pe), _p(pn), _p(pu), _p(me), _p(mn),
+        _p(mu), _p(out), nthreads,
+    )  # fmt: skip
+    if zd:
+        raise ZeroDivisionError("division by zero")
+    out *= 1e9
+    if comp < 0:
+        return tuple(out[i * oe.size:(i + 1) * oe.size].reshape(cast.shape) for i in range(3))
+    return out.reshape(cast.shape)
+
+
+def eqs_predict_spherical(coordinates, points, coefs, nthreads=0):
+    """Restatement of ``EquivalentSourcesSph.predict`` (spherical.py:219-248), float64."""
+    cast, (oe, on, ou) = _coords(coordinates)
+    pe, pn, pu = (_f64(np.atleast_1d(p).ravel()) for p in points[:3])
+    coefs = _f64(np.atleast_1d(coefs).ravel())
+    out = np.zeros(oe.size, dtype=np.float64)
+    scratch = np.empty(3 * (oe.size + pe.size), dtype=np.float64)
+    zd = lib().hbo_eqs_predict_spherical_loop(
+        oe.size, _p(oe), _p(on), _p(ou), pe.size, _p(pe), _p(pn), _p(pu), _p(coefs), _p(out),
+        _p(scratch), nthreads,
+    )  # fmt: skip
+    if zd:
+        raise ZeroDivisionError("division by zero")
+    return out.reshape(cast.shape)

@@ -20,6 +20,7 @@ Modules loaded (reference file):
   harmonica._forward.prisms.layer     src/harmonica/_forward/prisms/layer.py
   harmonica._forward.point            src/harmonica/_forward/point.py
   harmonica._equivalent_sources.utils src/harmonica/_equivalent_sources/utils.py
+  harmonica._forward.dipole           src/harmonica/_forward/dipole.py
 """
 
 import importlib
@@ -88,6 +89,7 @@ def load():
     _loaded["layer"] = importlib.import_module("harmonica._forward.prisms.layer")
     _loaded["point"] = importlib.import_module("harmonica._forward.point")
     _loaded["eqs_utils"] = importlib.import_module("harmonica._equivalent_sources.utils")
+    _loaded["dipole"] = importlib.import_module("harmonica._forward.dipole")
     return types.SimpleNamespace(**_loaded)
 
 
@@ -103,6 +105,24 @@ def greens_func_cartesian():
     @jit(nopython=True)
     def greens(east, north, upward, point_east, point_north, point_upward):
         distance = distance_cartesian((east, north, upward), (point_east, point_north, point_upward))
+        return 1 / distance
+
+    return greens
+
+
+def greens_func_spherical():
+    """The Green's function of spherical.py:412-424, re-typed for the same reason; it calls the
+    reference's own ``distance_spherical``."""
+    from numba import jit
+
+    ref = load()
+    distance_spherical = ref.utils.distance_spherical
+
+    @jit(nopython=True)
+    def greens(longitude, latitude, radius, point_longitude, point_latitude, point_radius):
+        distance = distance_spherical(
+            (longitude, latitude, radius), (point_longitude, point_latitude, point_radius)
+        )
         return 1 / distance
 
     return greens

@@ -371,3 +371,49 @@ def test_fp64_peak_probe(hb):
     flops, secs = ctypes.c_double(0), ctypes.c_double(0)
     assert lib.hb200_fp64_peak(2000, ctypes.byref(flops), ctypes.byref(secs)) == 0
     assert 5e12 < flops.value < 1e14
+
+
+# ------------------------------------------- next rows of SURVEY 8f: dipoles, spherical EQS
+@pytest.mark.parametrize("field", ["b", "b_e", "b_n", "b_u"])
+def test_golden_dipole_magnetic(hb, field):
+    g = golden("dipole_magnetic")
+    coords = (g["easting"], g["northing"], g["upward"])
+    got = hb.dipole_magnetic(coords, tuple(g["dipoles"]), tuple(g["moments"]), field)
+    if field == "b":
+        assert isinstance(got, tuple) and len(got) == 3
+    assert max_rel(np.array(got), g[field]) <= TOL
+
+
+def test_dipole_vs_oracle_and_zero_distance(hb):
+    rng = np.random.default_rng(61)
+    n_src, n_obs = 2500, 4099
+    dip = (rng.uniform(-5e4, 5e4, n_src), rng.uniform(-5e4, 5e4, n_src), rng.uniform(-5e3, -1e2, n_src))
+    mom = tuple(rng.normal(size=n_src) * 1e7 for _ in range(3))
+    coords = (rng.uniform(-5e4, 5e4, n_obs), rng.uniform(-5e4, 5e4, n_obs), rng.uniform(0, 500, n_obs))
+    want = np.array(O.dipole_magnetic(coords, dip, mom, "b"))
+    assert max_rel(np.array(hb.dipole_magnetic(coords, dip, mom, "b")), want) <= TOL
+    for k, f in enumerate(("b_e", "b_n", "b_u")):
+        assert max_rel(hb.dipole_magnetic(coords, dip, mom, f), want[k]) <= TOL
+    few = tuple(c[:11] for c in coords)  # few observers: chunked sources + reduce
+    assert max_rel(np.array(hb.dipole_magnetic(few, dip, mom, "b")), want[:, :11]) <= TOL
+    with pytest.raises(ZeroDivisionError):
+        hb.dipole_magnetic(([dip[0][3]], [dip[1][3]], [dip[2][3]]), dip, mom, "b_u")
+
+
+def test_golden_and_oracle_eqs_predict_spherical(hb):
+    g = golden("eqs_predict_spherical")
+    got = hb.eqs_predict(tuple(g["obs"]), tuple(g["points"]), g["coefs"], coordinate_system="spherical")
+    assert max_rel(got, g["predicted"]) <= TOL
+    eqs = hb.EquivalentSourcesSph(points=tuple(g["points"]), coefs=g["coefs"])
+    assert max_rel(eqs.predict(tuple(g["obs"])), g["predicted"]) <= TOL
+    res = np.zeros(80)
+    hb.predict_numba_parallel(tuple(g["obs"]), tuple(g["points"]), g["coefs"], res,
+                              hb._eqs.greens_func_spherical)
+    assert max_rel(res, g["predicted"]) <= TOL
+    rng = np.random.default_rng(62)
+    n_src, n_obs = 3000, 5000
+    pts = (rng.uniform(-40, 40, n_src), rng.uniform(-60, 60, n_src), rng.uniform(6.2e6, 6.3e6, n_src))
+    obs = (rng.uniform(-45, 45, n_obs), rng.uniform(-65, 65, n_obs), rng.uniform(6.4e6, 6.5e6, n_obs))
+    coefs = rng.normal(size=n_src)
+    want = O.eqs_predict_spherical(obs, pts, coefs)
+    assert max_rel(hb.eqs_predict(obs, pts, coefs, coordinate_system="spherical"), want) <= TOL

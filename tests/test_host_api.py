@@ -138,3 +138,17 @@ def test_shard_argument():
     with pytest.raises(ValueError, match="Invalid shard"):
         _lib.shard_mode("rows")
     assert _lib.shard_mode("sources") == _lib.SHARD_SOURCES
+
+
+def test_dipole_errors():
+    """dipole.py:99-104, :278-289"""
+    dip, mom = ([0.0], [0.0], [-10.0]), ([1.0], [0.0], [2.0])
+    with pytest.raises(ValueError, match="Invalid field 'bz'. Please choose one of 'b, b_e, b_n, b_u'."):
+        hb.dipole_magnetic(COORDS, dip, mom, "bz")
+    with pytest.raises(ValueError, match="Invalid magnetic moments with '2' elements"):
+        hb.dipole_magnetic(COORDS, dip, ([1.0], [2.0]), "b")
+    with pytest.raises(ValueError, match=r"Number of elements in magnetic_moments \(2\) mismatch the number of dipoles \(1\)."):
+        hb.dipole_magnetic(COORDS, dip, ([1.0, 1.0], [0.0, 1.0], [2.0, 1.0]), "b")
+    assert list(inspect.signature(hb.dipole_magnetic).parameters)[:8] == [
+        "coordinates", "dipoles", "magnetic_moments", "field", "parallel", "dtype", "progressbar",
+        "disable_checks"]

@@ -74,3 +74,18 @@ def test_eqs_predict_and_jacobian():
     coords = (g["easting"], g["northing"], g["upward"])
     npt.assert_array_equal(O.eqs_predict(coords, tuple(g["points"]), g["coefs"]), g["predicted"])
     npt.assert_array_equal(O.eqs_jacobian(coords, tuple(g["points"])), g["jacobian"])
+
+
+@pytest.mark.parametrize("field", ["b", "b_e", "b_n", "b_u"])
+def test_dipole_magnetic(field):
+    g = golden("dipole_magnetic")
+    coords = (g["easting"], g["northing"], g["upward"])
+    got = np.array(O.dipole_magnetic(coords, tuple(g["dipoles"]), tuple(g["moments"]), field))
+    npt.assert_array_equal(got, g[field])
+
+
+def test_eqs_predict_spherical():
+    g = golden("eqs_predict_spherical")
+    got = O.eqs_predict_spherical(tuple(g["obs"]), tuple(g["points"]), g["coefs"])
+    # numpy's SIMD cos/sin inside numba may differ from glibc's scalar ones in the last ulp
+    npt.assert_allclose(got, g["predicted"], rtol=1e-11)

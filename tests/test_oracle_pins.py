@@ -193,3 +193,15 @@ def test_point_zero_distance_raises():
         O.point_gravity(([0.0], [0.0], [0.0]), ([0.0], [0.0], [0.0]), [1.0], "potential")
     with pytest.raises(ZeroDivisionError):
         O.eqs_predict(([1.0], [2.0], [3.0]), ([1.0], [2.0], [3.0]), [1.0])
+
+
+def test_dipole_closed_forms():
+    """dipole formula pins: on the dipole axis B = mu0/4pi * 2 m / d^3 along m; in the equatorial
+    plane B = -mu0/4pi * m / d^3 (the reference's tests only compare against choclo)"""
+    m = 3.5e6
+    b = np.array(O.dipole_magnetic(([0.0], [0.0], [200.0]), ([0.0], [0.0], [0.0]), ([0.0], [0.0], [m]), "b")).ravel()
+    npt.assert_allclose(b, [0.0, 0.0, 1e-7 * 2 * m / 200.0**3 * 1e9], rtol=1e-14, atol=1e-20)
+    b = np.array(O.dipole_magnetic(([150.0], [0.0], [0.0]), ([0.0], [0.0], [0.0]), ([0.0], [0.0], [m]), "b")).ravel()
+    npt.assert_allclose(b, [0.0, 0.0, -1e-7 * m / 150.0**3 * 1e9], rtol=1e-14, atol=1e-20)
+    with pytest.raises(ZeroDivisionError):
+        O.dipole_magnetic(([1.0], [2.0], [3.0]), ([1.0], [2.0], [3.0]), ([1.0], [0.0], [0.0]), "b")
