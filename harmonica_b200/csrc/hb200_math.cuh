@@ -196,27 +196,41 @@ HB_HD PairPreds make_preds(const PairGeom& g)
     return p;
 }
 
-// true when the pair must take the rule-exact (direct) path: the smallest of the six
-// squared shifts is zero or more than 2^50 times smaller than the largest one. This covers
-//  * an exactly-zero shift (observer in the plane of a face: all singular-point rules), and
-//  * every pair on which the reference's on-axis safe_log branch (r == -x) can fire: that
-//    needs y^2 + z^2 < 2^-52 x^2, so when all squares are within 2^50 of each other r != |x|,
-//  * pairs at absurd length scales (see below).
-// Non-negative doubles order like their bit patterns, so this runs on the integer pipe.
-HB_HD bool needs_exact_path(const PairGeom& g)
+// true when the pair must take the rule-exact (direct) path. With h = exponent bits of the six
+// squared shifts (non-negative doubles order like their bit patterns: integer pipe only):
+//
+//  * tensor and magnetic sets: the smallest square is zero or > 2^50 times smaller than the
+//    largest. An exactly-zero shift puts the observer in the plane of a face (NaN and +4 pi
+//    rules); and the reference's on-axis safe_log branch (r == -x) needs y^2 + z^2 < 2^-52 x^2,
+//    so when all squares are within 2^50 of each other it cannot fire.
+//  * potential and accelerations have no NaN / face rules, and every term that is special at a
+//    zero shift carries that shift as a factor (u * atan(e n / (u r)) etc.), so ONE axis may hold
+//    a zero (or arbitrarily small) shift: only the two axes with the larger minima must satisfy
+//    the 2^50 rule. Then for every vertex and every safe_log type y^2 + z^2 contains a square of
+//    a constrained axis, hence >= 2^-50 x^2: no on-axis branch, r > 0, all merged products
+//    positive. (Observers level with the prism tops, or sharing an easting with a prism edge,
+//    stay on the merged path.)
+//  * pairs at absurd length scales (third clause): the merged products reach the 16th power of
+//    a length; beyond ~1e-18 .. 1e18 m the reference's formulation is used as well.
+template <int FS> HB_HD bool needs_exact_path(const PairGeom& g)
 {
-    const unsigned h[6] = {(unsigned)hi_word(g.se2[0]), (unsigned)hi_word(g.se2[1]),
-                           (unsigned)hi_word(g.sn2[0]), (unsigned)hi_word(g.sn2[1]),
-                           (unsigned)hi_word(g.su2[0]), (unsigned)hi_word(g.su2[1])};
-    unsigned lo = h[0], hi = h[0];
-#pragma unroll
-    for (int q = 1; q < 6; q++) {
-        lo = h[q] < lo ? h[q] : lo;
-        hi = h[q] > hi ? h[q] : hi;
+    const unsigned e0 = (unsigned)hi_word(g.se2[0]), e1 = (unsigned)hi_word(g.se2[1]);
+    const unsigned n0 = (unsigned)hi_word(g.sn2[0]), n1 = (unsigned)hi_word(g.sn2[1]);
+    const unsigned u0 = (unsigned)hi_word(g.su2[0]), u1 = (unsigned)hi_word(g.su2[1]);
+    const unsigned he = e0 < e1 ? e0 : e1, hn = n0 < n1 ? n0 : n1, hu = u0 < u1 ? u0 : u1;
+    const unsigned me = e0 < e1 ? e1 : e0, mn = n0 < n1 ? n1 : n0, mu = u0 < u1 ? u1 : u0;
+    const unsigned men = me > mn ? me : mn;
+    const unsigned hi = men > mu ? men : mu;
+    constexpr bool one_axis_free =
+        (FS == F_POT || FS == F_E || FS == F_N || FS == F_U || FS == FS_ACC3);
+    const unsigned lo_en = he < hn ? he : hn, hi_en = he < hn ? hn : he;
+    unsigned lo;
+    if (one_axis_free) {
+        const unsigned t = hi_en < hu ? hi_en : hu;
+        lo = lo_en > t ? lo_en : t;  // median of (he, hn, hu)
+    } else {
+        lo = lo_en < hu ? lo_en : hu;  // minimum
     }
-    // The third clause keeps the merged products (up to the 16th power of a length) inside the
-    // float64 range: pairs whose largest squared shift is outside [2^-119, 2^119] m^2 (lengths
-    // beyond ~1e-18 .. 1e18 m) use the reference's formulation as well.
     return (lo + (50u << 20) < hi) | (hi - 0x38800000u > 0x47600000u - 0x38800000u);
 }
 
