@@ -141,7 +141,7 @@ struct PrismArgs {
 };
 
 template <int FS, int VARIANT>
-__global__ void __launch_bounds__(kBlock) prism_kernel(const PrismArgs a)
+__global__ void __launch_bounds__(kBlock, 4) prism_kernel(const PrismArgs a)
 {
     typedef Traits<FS> T;
     constexpr int STRIDE = T::mag ? kMagStride : kPrismStride;
