@@ -107,23 +107,112 @@ def eqs_jacobian(coordinates, points, dtype="float64"):
     return jac.astype(dtype, copy=False)
 
 
+def _least_squares(jacobian, data, weights, damping):
+    """
+    ``verde.base.least_squares`` restated with the same scikit-learn calls (column scaling with
+    ``StandardScaler(with_mean=False)``, then ``LinearRegression`` or ``Ridge(alpha=damping)``
+    without intercept); the reference calls it at ``cartesian.py:279-280``. Host side: the dense
+    solve is not part of the pairwise hot path.
+    """
+    from sklearn.linear_model import LinearRegression, Ridge  # noqa: PLC0415
+    from sklearn.preprocessing import StandardScaler  # noqa: PLC0415
+
+    if jacobian.shape[0] < jacobian.shape[1]:
+        import warnings  # noqa: PLC0415
+
+        warnings.warn(
+            "Under-determined problem detected (ndata, nparams)={}.".format(jacobian.shape),
+            stacklevel=2,
+        )
+    scaler = StandardScaler(copy=False, with_mean=False, with_std=True)
+    jacobian = scaler.fit_transform(jacobian)
+    regr = LinearRegression(fit_intercept=False) if damping is None else Ridge(
+        alpha=damping, fit_intercept=False)  # fmt: skip
+    regr.fit(jacobian, data.ravel(), sample_weight=weights)
+    return regr.coef_ / scaler.scale_
+
+
 class EquivalentSources:
     """
-    Prediction half of ``harmonica.EquivalentSources`` (``cartesian.py:33, 353-383``).
+    ``harmonica.EquivalentSources`` (``cartesian.py:33-644``) with the pair loops on the GPU:
+    ``predict`` (:353-383) and the Jacobian of ``fit`` (:385-415) run in
+    ``libharmonica_b200.so``; the least-squares solve of ``fit`` (:279-280) stays on the host and
+    uses the same scikit-learn calls as verde. Same constructor signature as the reference.
 
-    Holds fitted ``points_`` and ``coefs_`` and evaluates ``predict`` on the
-    GPU. Fitting (dense Jacobian + least squares) is outside this
-    package's scope; pass sources fitted elsewhere.
+    Not provided here: ``block_size`` (verde's ``BlockReduce``), ``grid``/``profile``/``scatter``
+    (verde's ``BaseGridder``); use :meth:`from_fitted` to evaluate sources fitted elsewhere.
     """
 
     coordinate_system = "cartesian"
 
-    def __init__(self, points=None, coefs=None, dtype="float64"):
+    def __init__(self, damping=None, points=None, depth="default", block_size=None, parallel=True,
+                 dtype="float64"):  # fmt: skip
+        if isinstance(depth, str) and depth != "default":
+            raise ValueError(
+                f"Found invalid 'depth' value equal to '{depth}'. "
+                "It should be 'default' or a numeric value."
+            )
+        if not isinstance(depth, str) and depth == 0:
+            raise ValueError("Depth value cannot be zero. It should be a non-zero numeric value.")
+        self.damping = damping
+        self.points = points
+        self.depth = depth
+        self.block_size = block_size
+        self.parallel = parallel
         self.dtype = dtype
-        if points is not None:
-            self.points_ = tuple(np.asarray(p).astype(dtype).ravel() for p in points[:3])
-        if coefs is not None:
-            self.coefs_ = np.asarray(coefs).ravel()
+        self.greens_function = greens_func_cartesian
+
+    @classmethod
+    def from_fitted(cls, points, coefs, dtype="float64"):
+        """Equivalent sources whose locations and coefficients are already known."""
+        self = cls(points=points, dtype=dtype)
+        self.points_ = tuple(np.asarray(p).astype(dtype).ravel() for p in points[:3])
+        self.coefs_ = np.asarray(coefs).ravel()
+        return self
+
+    def _build_points(self, coordinates):
+        """Relative-depth sources below the data points (``cartesian.py:283-324``)."""
+        if self.block_size is not None:
+            raise NotImplementedError("block-averaged sources need verde.BlockReduce")
+        if isinstance(self.depth, str):
+            # 4.5 x the mean distance to the first neighbour
+            # (bordado.neighbor_distance_statistics(coordinates[:2], "median", k=1))
+            from scipy.spatial import cKDTree  # noqa: PLC0415
+
+            xy = np.transpose([coordinates[0], coordinates[1]])
+            nearest = cKDTree(xy).query(xy, k=2)[0][:, 1]
+            self.depth_ = 4.5 * np.mean(nearest)
+        else:
+            self.depth_ = self.depth
+        return coordinates[0], coordinates[1], coordinates[2] - self.depth_
+
+    def fit(self, coordinates, data, weights=None):
+        """Fit the coefficients of the equivalent sources (``cartesian.py:236-281``)."""
+        coordinates = tuple(np.asarray(c) for c in coordinates[:3])
+        data = np.asarray(data)
+        if any(c.shape != data.shape for c in coordinates):
+            raise ValueError(
+                "Coordinate and data arrays must have the same shape. "
+                f"Coordinates: {[c.shape for c in coordinates]}, data: {data.shape}."
+            )
+        if weights is not None:
+            weights = np.asarray(weights)
+            if weights.shape != data.shape:
+                raise ValueError("Weights must have the same shape as the data array.")
+            weights = weights.ravel().astype(self.dtype)
+        # utils.py:16-39 (cast_fit_input), then 1-D views
+        coordinates = tuple(c.astype(self.dtype).ravel() for c in coordinates)
+        data = data.astype(self.dtype).ravel()
+        self.region_ = (coordinates[0].min(), coordinates[0].max(),
+                        coordinates[1].min(), coordinates[1].max())  # fmt: skip
+        if self.points is None:
+            self.points_ = tuple(p.astype(self.dtype) for p in self._build_points(coordinates))
+        else:
+            self.depth_ = None
+            self.points_ = tuple(np.asarray(p).astype(self.dtype).ravel() for p in self.points[:3])
+        jacobian = self.jacobian(coordinates, self.points_, dtype=self.dtype)
+        self.coefs_ = _least_squares(jacobian, data, weights, self.damping)
+        return self
 
     def predict(self, coordinates):
         if not hasattr(self, "coefs_"):
@@ -146,10 +235,25 @@ class EquivalentSourcesSph(EquivalentSources):
     """
     Prediction half of ``harmonica.EquivalentSourcesSph`` (``spherical.py:219-248``):
     coordinates are (longitude, latitude, radius); the result has the dtype of the
-    coordinates (``spherical.py:241-244``).
+    coordinates (``spherical.py:241-244``). Build it with :meth:`from_fitted`.
     """
 
     coordinate_system = "spherical"
+
+    def __init__(self, damping=None, points=None, relative_depth=500, parallel=True):
+        super().__init__(damping=damping, points=points, depth=relative_depth, parallel=parallel)
+        self.relative_depth = relative_depth
+        self.greens_function = greens_func_spherical
+
+    @classmethod
+    def from_fitted(cls, points, coefs, dtype="float64"):
+        self = cls(points=points)
+        self.points_ = tuple(np.asarray(p).astype(dtype).ravel() for p in points[:3])
+        self.coefs_ = np.asarray(coefs).ravel()
+        return self
+
+    def fit(self, coordinates, data, weights=None):
+        raise NotImplementedError("fitting spherical equivalent sources is not part of this package")
 
     def predict(self, coordinates):
         if not hasattr(self, "coefs_"):

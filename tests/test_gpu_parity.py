@@ -115,9 +115,9 @@ def test_golden_eqs(hb):
     res = np.ones(80)
     hb.predict_numba_parallel(coords, tuple(g["points"]), g["coefs"], res)
     assert max_rel(res - 1.0, g["predicted"]) <= 10 * TOL
-    eqs = hb.EquivalentSources(points=tuple(g["points"]), coefs=g["coefs"])
+    eqs = hb.EquivalentSources.from_fitted(tuple(g["points"]), g["coefs"])
     assert max_rel(eqs.predict(coords), g["predicted"]) <= TOL
-    eqs32 = hb.EquivalentSources(points=tuple(g["points"]), coefs=g["coefs"], dtype="float32")
+    eqs32 = hb.EquivalentSources.from_fitted(tuple(g["points"]), g["coefs"], dtype="float32")
     out32 = eqs32.predict(coords)
     assert out32.dtype == np.float32
     npt.assert_allclose(out32, g["predicted"], rtol=2e-4)
@@ -404,7 +404,7 @@ def test_golden_and_oracle_eqs_predict_spherical(hb):
     g = golden("eqs_predict_spherical")
     got = hb.eqs_predict(tuple(g["obs"]), tuple(g["points"]), g["coefs"], coordinate_system="spherical")
     assert max_rel(got, g["predicted"]) <= TOL
-    eqs = hb.EquivalentSourcesSph(points=tuple(g["points"]), coefs=g["coefs"])
+    eqs = hb.EquivalentSourcesSph.from_fitted(tuple(g["points"]), g["coefs"])
     assert max_rel(eqs.predict(tuple(g["obs"])), g["predicted"]) <= TOL
     res = np.zeros(80)
     hb.predict_numba_parallel(tuple(g["obs"]), tuple(g["points"]), g["coefs"], res,
@@ -417,3 +417,23 @@ def test_golden_and_oracle_eqs_predict_spherical(hb):
     coefs = rng.normal(size=n_src)
     want = O.eqs_predict_spherical(obs, pts, coefs)
     assert max_rel(hb.eqs_predict(obs, pts, coefs, coordinate_system="spherical"), want) <= TOL
+
+
+def test_equivalent_sources_fit_predict_round_trip(hb):
+    """test/test_eq_sources_cartesian.py:157-199: fit on synthetic point-mass data, predict it back
+    (GPU Jacobian + host least squares, GPU predict)"""
+    rng = np.random.default_rng(63)
+    e, n = np.meshgrid(np.linspace(-5e3, 5e3, 35), np.linspace(-5e3, 5e3, 35))
+    coords = (e.ravel(), n.ravel(), np.full(e.size, 0.0))
+    pts = (rng.uniform(-4e3, 4e3, 6), rng.uniform(-4e3, 4e3, 6), rng.uniform(-7e3, -5e3, 6))
+    masses = rng.uniform(1e10, 5e10, 6)
+    data = hb.point_gravity(coords, pts, masses, "g_z")
+    eqs = hb.EquivalentSources(depth=1500.0).fit(coords, data)
+    assert eqs.depth_ == 1500.0 and eqs.coefs_.shape == (e.size,)
+    npt.assert_allclose(eqs.predict(coords), data, rtol=1e-5)
+    damped = hb.EquivalentSources(damping=1e-6).fit(coords, data)   # default depth: 4.5 x spacing
+    npt.assert_allclose(damped.depth_, 4.5 * (1e4 / 34), rtol=1e-12)
+    npt.assert_allclose(damped.predict(coords), data, atol=1e-3 * np.max(np.abs(data)))
+    upward = (coords[0], coords[1], np.full(e.size, 300.0))
+    npt.assert_allclose(eqs.predict(upward), hb.point_gravity(upward, pts, masses, "g_z"),
+                        atol=2e-2 * np.max(np.abs(data)))

@@ -132,6 +132,13 @@ def test_eqs_host_logic():
         hb.eqs_predict(COORDS, ([0.0], [0.0], [-1.0]), [1.0, 2.0])
     with pytest.raises(RuntimeError, match="not fitted"):
         hb.EquivalentSources().predict(COORDS)
+    # cartesian.py:164-186: constructor signature and depth validation
+    assert list(inspect.signature(hb.EquivalentSources.__init__).parameters)[1:] == [
+        "damping", "points", "depth", "block_size", "parallel", "dtype"]
+    with pytest.raises(ValueError, match="Found invalid 'depth' value equal to 'deep'"):
+        hb.EquivalentSources(depth="deep")
+    with pytest.raises(ValueError, match="Depth value cannot be zero"):
+        hb.EquivalentSources(depth=0)
 
 
 def test_shard_argument():
