@@ -420,20 +420,35 @@ def test_golden_and_oracle_eqs_predict_spherical(hb):
 
 
 def test_equivalent_sources_fit_predict_round_trip(hb):
-    """test/test_eq_sources_cartesian.py:157-199: fit on synthetic point-mass data, predict it back
-    (GPU Jacobian + host least squares, GPU predict)"""
-    rng = np.random.default_rng(63)
-    e, n = np.meshgrid(np.linspace(-5e3, 5e3, 35), np.linspace(-5e3, 5e3, 35))
-    coords = (e.ravel(), n.ravel(), np.full(e.size, 0.0))
-    pts = (rng.uniform(-4e3, 4e3, 6), rng.uniform(-4e3, 4e3, 6), rng.uniform(-7e3, -5e3, 6))
-    masses = rng.uniform(1e10, 5e10, 6)
+    """test/test_eq_sources_cartesian.py:157-183 (small data, Cartesian): fit on synthetic
+    point-mass data and predict it back: GPU Jacobian + host least squares, GPU predict"""
+    region = (-3e3, -1e3, 5e3, 7e3)
+
+    def grid(shape, upward):
+        e, n = np.meshgrid(np.linspace(region[0], region[1], shape[1]),
+                           np.linspace(region[2], region[3], shape[0]))
+        return e, n, np.full_like(e, float(upward))
+
+    pts = grid((6, 6), -1e3)
+    # checkerboard masses like verde.synthetic.CheckerBoard(amplitude=1e13, region=region)
+    w_e, w_n = (region[1] - region[0]) / 2, (region[3] - region[2]) / 2
+    masses = 1e13 * np.sin((2 * np.pi / w_e) * (pts[0] - region[0])) * np.cos(
+        (2 * np.pi / w_n) * (pts[1] - region[2]))
+    coords = grid((8, 8), 0)
     data = hb.point_gravity(coords, pts, masses, "g_z")
-    eqs = hb.EquivalentSources(depth=1500.0).fit(coords, data)
-    assert eqs.depth_ == 1500.0 and eqs.coefs_.shape == (e.size,)
-    npt.assert_allclose(eqs.predict(coords), data, rtol=1e-5)
-    damped = hb.EquivalentSources(damping=1e-6).fit(coords, data)   # default depth: 4.5 x spacing
-    npt.assert_allclose(damped.depth_, 4.5 * (1e4 / 34), rtol=1e-12)
-    npt.assert_allclose(damped.predict(coords), data, atol=1e-3 * np.max(np.abs(data)))
-    upward = (coords[0], coords[1], np.full(e.size, 300.0))
-    npt.assert_allclose(eqs.predict(upward), hb.point_gravity(upward, pts, masses, "g_z"),
-                        atol=2e-2 * np.max(np.abs(data)))
+    eqs = hb.EquivalentSources(depth=500).fit(coords, data)
+    # the interpolation should be perfect on the data points
+    npt.assert_allclose(data, eqs.predict(coords), rtol=1e-5)
+    npt.assert_allclose([c.ravel() for c in coords[:2]], eqs.points_[:2], rtol=1e-5)
+    npt.assert_allclose(coords[2].ravel() - 500, eqs.points_[2], rtol=1e-5)
+    assert eqs.depth_ == 500 and eqs.region_ == region
+    up = grid((8, 8), 20)
+    npt.assert_allclose(hb.point_gravity(up, pts, masses, "g_z"), eqs.predict(up), rtol=0.08)
+    # default depth = 4.5 x mean first-neighbour distance; damped fit stays close to the data
+    damped = hb.EquivalentSources(damping=1e-10).fit(coords, data)
+    npt.assert_allclose(damped.depth_, 4.5 * (2e3 / 7), rtol=1e-12)
+    npt.assert_allclose(damped.predict(coords), data, atol=1e-2 * np.max(np.abs(data)))
+    # sources given explicitly (cartesian.py:270-275)
+    fixed = hb.EquivalentSources(points=tuple(p.ravel() for p in pts)).fit(coords, data)
+    assert fixed.depth_ is None
+    npt.assert_allclose(fixed.predict(coords), data, rtol=1e-5)
