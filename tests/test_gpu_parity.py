@@ -450,5 +450,7 @@ def test_equivalent_sources_fit_predict_round_trip(hb):
     npt.assert_allclose(damped.predict(coords), data, atol=1e-2 * np.max(np.abs(data)))
     # sources given explicitly (cartesian.py:270-275)
     fixed = hb.EquivalentSources(points=tuple(p.ravel() for p in pts)).fit(coords, data)
-    assert fixed.depth_ is None
-    npt.assert_allclose(fixed.predict(coords), data, rtol=1e-5)
+    assert fixed.depth_ is None and fixed.coefs_.shape == (36,)
+    npt.assert_array_equal(fixed.points_[2], np.full(36, -1e3))
+    # 36 sources with the 1/r kernel cannot reproduce 64 g_z values exactly: least-squares misfit
+    assert np.max(np.abs(fixed.predict(coords) - data)) < 0.1 * np.max(np.abs(data))
