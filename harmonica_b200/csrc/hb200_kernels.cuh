@@ -140,12 +140,55 @@ struct PrismArgs {
     unsigned* flags;
 };
 
+// ---- TMA bulk-copy staging (cp.async.bulk + mbarrier; SASS: UBLKCP / SYNCS) --------------
+// One elected thread asks the copy engine for the next tile of packed records while the CTA
+// computes on the current one (two shared-memory buffers, one mbarrier each); the other 127
+// threads never touch global memory inside the source loop.
+__device__ __forceinline__ unsigned smem_addr(const void* p)
+{
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)),
+                 "r"(bytes)
+                 : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_addr(dst)),
+        "l"(src), "r"(bytes), "r"(smem_addr(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_addr(bar)),
+        "r"(parity)
+        : "memory");
+}
+
 template <int FS, int VARIANT>
 __global__ void __launch_bounds__(kBlock, 4) prism_kernel(const PrismArgs a)
 {
     typedef Traits<FS> T;
     constexpr int STRIDE = T::mag ? kMagStride : kPrismStride;
-    __shared__ double2 tile[kTile * STRIDE / 2];
+    __shared__ alignas(128) double2 tiles[2][kTile * STRIDE / 2];
+    __shared__ alignas(8) uint64_t bars[2];
 
     const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     const int64_t ic = i < a.n_obs ? i : a.n_obs - 1;
@@ -158,14 +201,33 @@ __global__ void __launch_bounds__(kBlock, 4) prism_kernel(const PrismArgs a)
 
     const int64_t begin = (int64_t)blockIdx.y * a.chunk_len;
     const int64_t end = begin + a.chunk_len < a.n_src ? begin + a.chunk_len : a.n_src;
-    const double2* src = reinterpret_cast<const double2*>(a.packed);
+    const double* src = a.packed;
 
-    for (int64_t t0 = begin; t0 < end; t0 += kTile) {
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && begin < end) {
+        const int cnt0 = (int)((end - begin) < kTile ? (end - begin) : kTile);
+        bulk_load(tiles[0], src + begin * STRIDE, (unsigned)(cnt0 * STRIDE * sizeof(double)), &bars[0]);
+    }
+    unsigned phase0 = 0, phase1 = 0;
+    int buf = 0;
+    for (int64_t t0 = begin; t0 < end; t0 += kTile, buf ^= 1) {
         const int cnt = (int)((end - t0) < kTile ? (end - t0) : kTile);
-        __syncthreads();
-        for (int x = threadIdx.x; x < cnt * (STRIDE / 2); x += kBlock)
-            tile[x] = src[t0 * (STRIDE / 2) + x];
-        __syncthreads();
+        // prefetch the next tile into the other buffer (every thread finished reading it at the
+        // __syncthreads() that closed the previous iteration)
+        const int64_t t1 = t0 + kTile;
+        if (threadIdx.x == 0 && t1 < end) {
+            const int cnt1 = (int)((end - t1) < kTile ? (end - t1) : kTile);
+            bulk_load(tiles[buf ^ 1], src + t1 * STRIDE, (unsigned)(cnt1 * STRIDE * sizeof(double)),
+                      &bars[buf ^ 1]);
+        }
+        if (buf == 0) { mbar_wait(&bars[0], phase0); phase0 ^= 1; }
+        else { mbar_wait(&bars[1], phase1); phase1 ^= 1; }
+        const double2* tile = tiles[buf];
 #pragma unroll 1
         for (int s = 0; s < cnt; s++) {
             const double2* p = tile + s * (STRIDE / 2);
@@ -188,6 +250,7 @@ __global__ void __launch_bounds__(kBlock, 4) prism_kernel(const PrismArgs a)
                 else prism_pair_fast<FS, (VARIANT == 2)>(g, prm, acc);
             }
         }
+        __syncthreads();  // the buffer just read may be refilled in the next iteration
     }
     if (i < a.n_obs) {
         if (gridDim.y == 1) {
