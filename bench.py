@@ -44,8 +44,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 I_PAIR = {"layer_gz": 1068, "c1_gz": 1068, "tensor": 2020, "mag_b": 2100, "eqs": 26.5}
 NOMINAL_FP64_FLOPS = 148 * 64 * 2 * 1.965e9  # 37.2 TFLOP/s
 # executed thread-instructions per pair of the CURRENT kernels, from the committed ncu source
-# pages (profiles/r1_opmix_*_v7.txt, profiles/r1_ncu_eqs_v3.txt): (FP64 pipe, all other pipes)
-EXECUTED_PER_PAIR = {"layer_gz": (224.1, 167.3), "c1_gz": (224.1, 167.3), "tensor": (288.1, 182.8),
+# pages (profiles/r1_opmix_*_final.txt): (FP64 pipe, all other pipes)
+EXECUTED_PER_PAIR = {"layer_gz": (224.1, 169.0), "c1_gz": (224.1, 169.0), "tensor": (288.1, 181.6),
                      "eqs": (12.0, 5.1)}
 
 
