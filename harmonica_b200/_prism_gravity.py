@@ -36,19 +36,25 @@ def _run(lib, coords, prisms, density, mask, shard, n_fields, progress_proxy=Non
     n_obs = coords[0].size
     out = np.empty((n_fields, n_obs), dtype=np.float64)
     flags_all = 0
+    # the C entry point takes at most 6 fields per call: potential + accelerations, then tensor
+    masks = [mask] if n_fields <= 6 else [mask & 0x00F, mask & _lib.MASK_TENSOR]
     for lo, hi in observer_chunks(n_obs, progress_proxy):
         sub = tuple(np.ascontiguousarray(c[lo:hi]) for c in coords)
-        res = np.empty((n_fields, hi - lo), dtype=np.float64)
-        flags = ctypes.c_uint32(0)
-        _lib.check(
-            lib.hb200_prism_gravity(
-                _lib.ptr(sub[0]), _lib.ptr(sub[1]), _lib.ptr(sub[2]), hi - lo,
-                _lib.ptr(prisms), _lib.ptr(density), prisms.shape[0], mask, shard,
-                _lib.ptr(res), ctypes.byref(flags),
-            )  # fmt: skip
-        )
-        out[:, lo:hi] = res
-        flags_all |= flags.value
+        row = 0
+        for part in masks:
+            n_part = bin(part).count("1")
+            res = np.empty((n_part, hi - lo), dtype=np.float64)
+            flags = ctypes.c_uint32(0)
+            _lib.check(
+                lib.hb200_prism_gravity(
+                    _lib.ptr(sub[0]), _lib.ptr(sub[1]), _lib.ptr(sub[2]), hi - lo,
+                    _lib.ptr(prisms), _lib.ptr(density), prisms.shape[0], part, shard,
+                    _lib.ptr(res), ctypes.byref(flags),
+                )  # fmt: skip
+            )
+            out[row:row + n_part, lo:hi] = res
+            row += n_part
+            flags_all |= flags.value
         if progress_proxy is not None:
             progress_proxy.update(hi - lo)
     return out, flags_all

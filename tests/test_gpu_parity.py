@@ -170,6 +170,10 @@ def test_fused_multi_field(hb, variant, medium):
         assert max_rel(got, O.prism_gravity(coords, prisms, density, f)) <= TOL
     mixed = hb.prism_gravity(coords, prisms, density, ("potential", "g_zz"))
     assert max_rel(mixed[1], O.prism_gravity(coords, prisms, density, "g_zz")) <= TOL
+    everything = hb.prism_gravity(coords, prisms, density, GRAVITY_FIELDS)  # 10 fields: two calls
+    assert len(everything) == 10
+    for f, got in zip(GRAVITY_FIELDS, everything):
+        assert max_rel(got, O.prism_gravity(coords, prisms, density, f)) <= TOL, f
 
 
 def test_prism_magnetic_vs_oracle(hb, variant, medium):
