@@ -159,7 +159,7 @@ template <int X, int F, bool XM> HB_HD double log_group4(const FastCtx& c, int f
 
 // sum over all 8 vertices of s_ijk L^X: per X index xi the four vertices split by parity of
 // the other two indices into side A (00, 11) and side B (01, 10)
-template <int X, bool XM> HB_HD double log_sum8(const FastCtx& c)
+template <int X> HB_HD void log_sum8_tb(const FastCtx& c, double& top, double& bot)
 {
     double P[2], Q[2];
 #pragma unroll
@@ -179,7 +179,14 @@ template <int X, bool XM> HB_HD double log_sum8(const FastCtx& c)
         P[xi] = neg ? YA * TB : TA;
         Q[xi] = neg ? TA * YB : TB;
     }
-    return x_log_ratio<XM>(P[0] * Q[1], Q[0] * P[1]);
+    top = P[0] * Q[1];
+    bot = Q[0] * P[1];
+}
+template <int X, bool XM> HB_HD double log_sum8(const FastCtx& c)
+{
+    double top, bot;
+    log_sum8_tb<X>(c, top, bot);
+    return x_log_ratio<XM>(top, bot);
 }
 
 // L^X(x_0) - L^X(x_1) along X's own axis; (a, b) = the other two indices in axis order.
@@ -262,6 +269,128 @@ template <int X, bool XM> HB_HD double atan_sum8(const FastCtx& c)
     return atan_sum4<X, XM>(c, 0) - atan_sum4<X, XM>(c, 1);
 }
 
+// NQ merged log ratios with ONE warp vote: log(top[q] / bot[q]).
+template <bool XM, int NQ>
+HB_HD void x_log_ratio4(const double (&top)[NQ], const double (&bot)[NQ], double (&out)[NQ])
+{
+    if (!XM) {
+#pragma unroll
+        for (int q = 0; q < NQ; q++) out[q] = log(top[q] / bot[q]);
+        return;
+    }
+    double y[NQ], z[NQ];
+    int worst = 0;
+#pragma unroll
+    for (int q = 0; q < NQ; q++) {
+        y[q] = fast_rcp(bot[q]);
+        z[q] = fma(top[q], y[q], -1.0);
+        const int m = hi_word(z[q]) & 0x7fffffff;
+        worst = m > worst ? m : worst;
+    }
+    if (warp_all(worst < 0x3f700000)) {  // every |z| < 2^-8
+#pragma unroll
+        for (int q = 0; q < NQ; q++) out[q] = log1p_small(z[q]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < NQ; q++) out[q] = fast_log(top[q] * y[q]);
+    }
+}
+
+// The 8-vertex atan sums of two diagonal kernels (types XA, XB) with one branch for the merge
+// test and one warp vote for the far-field sequence.
+template <int XA, int XB, bool XM> HB_HD void atan_sum8_two(const FastCtx& c, double& sa, double& sb)
+{
+    if (!XM) {
+        sa = atan_sum8<XA, XM>(c);
+        sb = atan_sum8<XB, XM>(c);
+        return;
+    }
+    double im[2][4], re[2][4];
+    bool ok = true;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        atan_pair_terms<XA>(c, q >> 1, q & 1, im[0][q], re[0][q]);
+        atan_pair_terms<XB>(c, q >> 1, q & 1, im[1][q], re[1][q]);
+        ok = ok && angle_below_quarter_pi(im[0][q], re[0][q]) && angle_below_quarter_pi(im[1][q], re[1][q]);
+    }
+    if (ok) {
+        double y[2], x[2];
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+            // z_00 conj(z_01) conj(z_10) z_11 (q = 2 f + m)
+            const double are = re[t][0] * re[t][1] + im[t][0] * im[t][1];
+            const double aim = im[t][0] * re[t][1] - re[t][0] * im[t][1];
+            const double bre = re[t][3] * re[t][2] + im[t][3] * im[t][2];
+            const double bim = im[t][3] * re[t][2] - re[t][3] * im[t][2];
+            y[t] = aim * bre + are * bim;
+            x[t] = are * bre - aim * bim;
+        }
+        if (warp_all(small_angle(y[0], x[0]) && small_angle(y[1], x[1]))) {
+            sa = atan_small(y[0], x[0]);
+            sb = atan_small(y[1], x[1]);
+        } else {
+            sa = fast_atan2(y[0], x[0]);
+            sb = fast_atan2(y[1], x[1]);
+        }
+    } else {
+        sa = atan_sum8<XA, XM>(c);
+        sb = atan_sum8<XB, XM>(c);
+    }
+}
+
+// S[0], S[1] of atan_sum4 (both indices of axis X) with one branch for the merge test and one
+// warp vote for the far-field sequence.
+template <int X, bool XM> HB_HD void atan_sum4_both(const FastCtx& c, double (&S)[2])
+{
+    if (!XM) {
+        S[0] = atan_sum4<X, XM>(c, 0);
+        S[1] = atan_sum4<X, XM>(c, 1);
+        return;
+    }
+    double im[2][2], re[2][2];
+    bool ok = true;
+#pragma unroll
+    for (int f = 0; f < 2; f++)
+#pragma unroll
+        for (int m = 0; m < 2; m++) {
+            atan_pair_terms<X>(c, f, m, im[f][m], re[f][m]);
+            ok = ok && angle_below_quarter_pi(im[f][m], re[f][m]);
+        }
+    if (ok) {
+        double y[2], x[2];
+#pragma unroll
+        for (int f = 0; f < 2; f++) {
+            y[f] = im[f][0] * re[f][1] - re[f][0] * im[f][1];
+            x[f] = re[f][0] * re[f][1] + im[f][0] * im[f][1];
+        }
+        if (warp_all(small_angle(y[0], x[0]) && small_angle(y[1], x[1]))) {
+            S[0] = atan_small(y[0], x[0]);
+            S[1] = atan_small(y[1], x[1]);
+        } else {
+            S[0] = fast_atan2(y[0], x[0]);
+            S[1] = fast_atan2(y[1], x[1]);
+        }
+    } else {
+#pragma unroll
+        for (int f = 0; f < 2; f++) S[f] = fast_atan2(im[f][0], re[f][0]) - fast_atan2(im[f][1], re[f][1]);
+    }
+}
+
+// One acceleration component: LA, LB = the two safe_log types with the axes FA, FB their
+// prefactors run over (pa, pb), AX = the atan type with prefactor px.
+template <int LA, int FA, int LB, int FB, int AX, bool XM>
+HB_HD double accel_component(const FastCtx& c, const double* pa, const double* pb, const double* px)
+{
+    double top[4], bot[4], L[4], S[2];
+    log_group4_tb<LA, FA>(c, 0, top[0], bot[0]);
+    log_group4_tb<LA, FA>(c, 1, top[1], bot[1]);
+    log_group4_tb<LB, FB>(c, 0, top[2], bot[2]);
+    log_group4_tb<LB, FB>(c, 1, top[3], bot[3]);
+    x_log_ratio4<XM, 4>(top, bot, L);
+    atan_sum4_both<AX, XM>(c, S);
+    return pa[0] * L[0] - pa[1] * L[1] + pb[0] * L[2] - pb[1] * L[3] - (px[0] * S[0] - px[1] * S[1]);
+}
+
 template <int FS, bool XM>
 HB_HD void prism_pair_fast(const PairGeom& g, const double* prm, double* acc)
 {
@@ -272,20 +401,11 @@ HB_HD void prism_pair_fast(const PairGeom& g, const double* prm, double* acc)
     const double* n = c.sn;
     const double* u = c.su;
     if (FS == F_U) {
-        const double v = e[0] * log_group4<1, 0, XM>(c, 0) - e[1] * log_group4<1, 0, XM>(c, 1)
-                       + n[0] * log_group4<0, 1, XM>(c, 0) - n[1] * log_group4<0, 1, XM>(c, 1)
-                       - (u[0] * atan_sum4<2, XM>(c, 0) - u[1] * atan_sum4<2, XM>(c, 1));
-        acc[0] += prm[0] * -v;
+        acc[0] += prm[0] * -accel_component<1, 0, 0, 1, 2, XM>(c, e, n, u);
     } else if (FS == F_E) {
-        const double v = n[0] * log_group4<2, 1, XM>(c, 0) - n[1] * log_group4<2, 1, XM>(c, 1)
-                       + u[0] * log_group4<1, 2, XM>(c, 0) - u[1] * log_group4<1, 2, XM>(c, 1)
-                       - (e[0] * atan_sum4<0, XM>(c, 0) - e[1] * atan_sum4<0, XM>(c, 1));
-        acc[0] += prm[0] * -v;
+        acc[0] += prm[0] * -accel_component<2, 1, 1, 2, 0, XM>(c, n, u, e);
     } else if (FS == F_N) {
-        const double v = u[0] * log_group4<0, 2, XM>(c, 0) - u[1] * log_group4<0, 2, XM>(c, 1)
-                       + e[0] * log_group4<2, 0, XM>(c, 0) - e[1] * log_group4<2, 0, XM>(c, 1)
-                       - (n[0] * atan_sum4<1, XM>(c, 0) - n[1] * atan_sum4<1, XM>(c, 1));
-        acc[0] += prm[0] * -v;
+        acc[0] += prm[0] * -accel_component<0, 2, 2, 0, 1, XM>(c, u, e, n);
     } else if (FS == F_POT || FS == FS_ACC3) {
         double Pu[2][2], Pe[2][2], Pn[2][2], SA[3][2];
 #pragma unroll
@@ -336,8 +456,15 @@ HB_HD void prism_pair_fast(const PairGeom& g, const double* prm, double* acc)
     } else {
         // second-derivative kernels: tensor components and magnetics
         double kee = 0, knn = 0, kuu = 0, ken = 0, keu = 0, knu = 0;
-        if (T::ae) kee = -atan_sum8<0, XM>(c);
-        if (T::an) knn = -atan_sum8<1, XM>(c);
+        constexpr bool fused = (FS == FS_TENSOR6 || FS == FS_MAG_B);
+        if (XM && fused) {
+            atan_sum8_two<0, 1, XM>(c, kee, knn);
+            kee = -kee;
+            knn = -knn;
+        } else {
+            if (T::ae) kee = -atan_sum8<0, XM>(c);
+            if (T::an) knn = -atan_sum8<1, XM>(c);
+        }
         if (T::au) {
             if (XM && T::ae && T::an) {
                 // all three diagonal kernels wanted: the 8-vertex sums satisfy Laplace/Poisson
@@ -353,9 +480,20 @@ HB_HD void prism_pair_fast(const PairGeom& g, const double* prm, double* acc)
                 kuu = -atan_sum8<2, XM>(c);
             }
         }
-        if (T::lu) ken = log_sum8<2, XM>(c);
-        if (T::ln) keu = log_sum8<1, XM>(c);
-        if (T::le) knu = log_sum8<0, XM>(c);
+        if (XM && fused) {
+            double top[3], bot[3], L[3];
+            log_sum8_tb<2>(c, top[0], bot[0]);
+            log_sum8_tb<1>(c, top[1], bot[1]);
+            log_sum8_tb<0>(c, top[2], bot[2]);
+            x_log_ratio4<XM, 3>(top, bot, L);
+            ken = L[0];
+            keu = L[1];
+            knu = L[2];
+        } else {
+            if (T::lu) ken = log_sum8<2, XM>(c);
+            if (T::ln) keu = log_sum8<1, XM>(c);
+            if (T::le) knu = log_sum8<0, XM>(c);
+        }
         if (FS == F_EE) acc[0] += prm[0] * kee;
         else if (FS == F_NN) acc[0] += prm[0] * knn;
         else if (FS == F_UU) acc[0] += prm[0] * kuu;
