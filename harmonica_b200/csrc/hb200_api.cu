@@ -15,6 +15,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/harmonica_b200.h"
@@ -591,8 +592,11 @@ int run_host_job(const double* oe, const double* on, const double* ou, int64_t n
             p.slo = 0; p.shi = n_src;
         }
     }
-    // phase 1: allocate + upload + launch on every device (async per device)
-    for (int d = 0; d < nd; d++) {
+    // phase 1: allocate + upload + launch on every device. Uploads from pageable numpy buffers
+    // block the issuing host thread, so each device gets its own host thread: all devices are
+    // fed (and start computing) concurrently.
+    auto feed = [&](int d) -> int {
+        int rc = HB200_OK;
         Dev& dev = g_devs[d];
         Part& p = parts[d];
         CU(cudaSetDevice(dev.id));
@@ -631,7 +635,26 @@ int run_host_job(const double* oe, const double* on, const double* ou, int64_t n
         CU(cudaMemsetAsync(dev.d_flags, 0, sizeof(unsigned), dev.st));
         rc = launch(dev, p.d_oe, p.d_on, p.d_ou, no, p.d_arr, ns, /*raw=*/plan.by_sources, p.d_out,
                     p.ws, p.ws_bytes);
+        return rc;
+    };
+    if (nd == 1) {
+        rc = feed(0);
         if (rc) return rc;
+    } else {
+        std::vector<int> rcs(nd, HB200_OK);
+        std::vector<std::string> errs(nd);
+        std::vector<std::thread> threads;
+        for (int d = 0; d < nd; d++)
+            threads.emplace_back([&, d]() {
+                rcs[d] = feed(d);
+                if (rcs[d]) errs[d] = g_err;  // g_err is thread-local: hand the text back
+            });
+        for (std::thread& t : threads) t.join();
+        for (int d = 0; d < nd; d++)
+            if (rcs[d]) {
+                g_err = errs[d];
+                return rcs[d];
+            }
     }
     // phase 2: collect
     unsigned all_flags = 0;
