@@ -45,7 +45,7 @@ I_PAIR = {"layer_gz": 1068, "c1_gz": 1068, "tensor": 2020, "mag_b": 2100, "eqs":
 NOMINAL_FP64_FLOPS = 148 * 64 * 2 * 1.965e9  # 37.2 TFLOP/s
 # executed thread-instructions per pair of the CURRENT kernels, from the committed ncu source
 # pages (profiles/r1_opmix_*_final.txt): (FP64 pipe, all other pipes)
-EXECUTED_PER_PAIR = {"layer_gz": (224.1, 169.0), "c1_gz": (224.1, 169.0), "tensor": (288.1, 181.6),
+EXECUTED_PER_PAIR = {"layer_gz": (224.7, 147.4), "c1_gz": (224.7, 147.4), "tensor": (284.1, 171.6),
                      "eqs": (12.0, 5.1)}
 
 
@@ -417,7 +417,9 @@ def run_b200(args):
                 "fp64_pipe_frac": per_gpu * f64 * 2 / fp64_peak,
                 "issue_bound_frac": per_gpu * (2 * f64 + other) / slots,
                 "note": "an FP64 warp instruction occupies 2 issue slots on this part: time ~ "
-                        "(2*FP64 + other) / issue rate (DESIGN.md section 4)",
+                        "(2*FP64 + other) / issue rate (DESIGN.md section 4); the slot rate uses "
+                        "nvidia-smi's SM clock, ncu's cycle counter runs ~1.3 % faster (1.99 GHz), "
+                        "so ~1.0 means: at the issue bound",
             }
         line = {
             "metric": "prism-observer pair evals/sec", "value": value, "unit": "pair/s",
