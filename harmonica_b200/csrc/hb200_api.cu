@@ -560,12 +560,11 @@ ShardPlan plan_shards(int64_t n_obs, int64_t n_src, int shard_mode, bool src_sha
 // range and source range that device owns.
 template <typename Launch>
 int run_host_job(const double* oe, const double* on, const double* ou, int64_t n_obs,
-                 std::vector<HostArray> arrays, int64_t n_src, int nf, size_t ws_bytes_per_dev_hint,
+                 std::vector<HostArray> arrays, int64_t n_src, int nf,
                  int shard_mode, bool src_shardable, const Scales& final_scales, double* out,
                  uint32_t* flags, Launch launch,
                  size_t (*ws_fn)(int64_t, int64_t, int, int))
 {
-    (void)ws_bytes_per_dev_hint;
     std::lock_guard<std::mutex> lock(g_mu);
     int rc = lazy_init();
     if (rc) return rc;
@@ -827,7 +826,7 @@ int hb200_prism_gravity(const double* easting, const double* northing, const dou
         return prism_gravity_dev_impl(oe, on, ou, no, arr[0], arr[1], ns, field_mask, raw, d_out,
                                       dev.d_flags, ws, wsb, dev.sms, dev.st);
     };
-    return run_host_job(easting, northing, upward, n_obs, arrays, n_prisms, nf, 0, shard_mode, true,
+    return run_host_job(easting, northing, upward, n_obs, arrays, n_prisms, nf, shard_mode, true,
                         gravity_scales_for_mask(field_mask), out, flags, launch, ws_prism);
 }
 
@@ -862,7 +861,7 @@ int hb200_prism_singular_scan(const double* easting, const double* northing,
     Scales sc;
     for (int c = 0; c < 6; c++) sc.s[c] = 1.0;
     std::vector<double> dummy((size_t)n_obs);
-    return run_host_job(easting, northing, upward, n_obs, arrays, n_prisms, 1, 0,
+    return run_host_job(easting, northing, upward, n_obs, arrays, n_prisms, 1,
                         HB200_SHARD_OBSERVERS, false, sc, dummy.data(), flags, launch, ws_prism);
 }
 
@@ -887,7 +886,7 @@ int hb200_prism_magnetic(const double* easting, const double* northing, const do
     const double mu0 = 4 * kPi * 1e-7;
     Scales sc;
     for (int c = 0; c < 6; c++) sc.s[c] = mu0 / 4 / kPi * 1e9;
-    return run_host_job(easting, northing, upward, n_obs, arrays, n_prisms, nf, 0, shard_mode, true,
+    return run_host_job(easting, northing, upward, n_obs, arrays, n_prisms, nf, shard_mode, true,
                         sc, out, flags, launch, ws_prism);
 }
 
@@ -918,7 +917,7 @@ int hb200_prism_layer_gravity(const double* easting, const double* northing,
                                     arr[4], thickness_threshold, field_mask, raw, d_out, dev.d_flags,
                                     ws, wsb, dev.sms, dev.st);
     };
-    return run_host_job(easting, northing, upward, n_obs, arrays, n_src, nf, 0,
+    return run_host_job(easting, northing, upward, n_obs, arrays, n_src, nf,
                         HB200_SHARD_OBSERVERS, false, gravity_scales_for_mask(field_mask), out,
                         flags, launch, ws_prism);
 }
@@ -943,7 +942,7 @@ int hb200_point_gravity(const double* easting, const double* northing, const dou
                                       spherical, 1, raw, d_out, dev.d_flags, ws, wsb, dev.sms,
                                       dev.st);
     };
-    return run_host_job(easting, northing, upward, n_obs, arrays, n_src, nf, 0, shard_mode, true,
+    return run_host_job(easting, northing, upward, n_obs, arrays, n_src, nf, shard_mode, true,
                         gravity_scales_for_mask(field_mask), out, flags, launch, ws_point);
 }
 
@@ -963,7 +962,7 @@ int hb200_eqs_predict(const double* easting, const double* northing, const doubl
     };
     Scales sc;
     for (int c = 0; c < 6; c++) sc.s[c] = 1.0;
-    return run_host_job(easting, northing, upward, n_obs, arrays, n_src, 1, 0, shard_mode, true, sc,
+    return run_host_job(easting, northing, upward, n_obs, arrays, n_src, 1, shard_mode, true, sc,
                         out, flags, launch, ws_point);
 }
 
@@ -984,7 +983,7 @@ int hb200_eqs_predict_spherical(const double* longitude, const double* latitude,
     };
     Scales sc;
     for (int c = 0; c < 6; c++) sc.s[c] = 1.0;
-    return run_host_job(longitude, latitude, radius, n_obs, arrays, n_src, 1, 0, shard_mode, true, sc,
+    return run_host_job(longitude, latitude, radius, n_obs, arrays, n_src, 1, shard_mode, true, sc,
                         out, flags, launch, ws_point);
 }
 
@@ -1010,7 +1009,7 @@ int hb200_dipole_magnetic(const double* easting, const double* northing, const d
     const double mu0 = 4 * kPi * 1e-7;
     Scales sc;
     for (int c = 0; c < 6; c++) sc.s[c] = mu0 / 4 / kPi * 1e9;
-    return run_host_job(easting, northing, upward, n_obs, arrays, n_src, nf, 0, shard_mode, true, sc,
+    return run_host_job(easting, northing, upward, n_obs, arrays, n_src, nf, shard_mode, true, sc,
                         out, flags, launch, ws_dipole);
 }
 
