@@ -406,6 +406,32 @@ HB_HD void prism_pair_fast(const PairGeom& g, const double* prm, double* acc)
         acc[0] += prm[0] * -accel_component<2, 1, 1, 2, 0, XM>(c, n, u, e);
     } else if (FS == F_N) {
         acc[0] += prm[0] * -accel_component<0, 2, 2, 0, 1, XM>(c, u, e, n);
+    } else if (FS == FS_ACC3 && XM) {
+        // the three single-component formulas on one shared context: second differences
+        // (4-vertex groups), so the far-field log1p shortcut applies; one vote for all 12 logs
+        double top[12], bot[12], L[12], Se[2], Sn[2], Su[2];
+#pragma unroll
+        for (int f = 0; f < 2; f++) {
+            log_group4_tb<2, 1>(c, f, top[0 + f], bot[0 + f]);    // E: n * L^u over (i, k)
+            log_group4_tb<1, 2>(c, f, top[2 + f], bot[2 + f]);    // E: u * L^n over (i, j)
+            log_group4_tb<0, 2>(c, f, top[4 + f], bot[4 + f]);    // N: u * L^e over (i, j)
+            log_group4_tb<2, 0>(c, f, top[6 + f], bot[6 + f]);    // N: e * L^u over (j, k)
+            log_group4_tb<1, 0>(c, f, top[8 + f], bot[8 + f]);    // U: e * L^n over (j, k)
+            log_group4_tb<0, 1>(c, f, top[10 + f], bot[10 + f]);  // U: n * L^e over (i, k)
+        }
+        x_log_ratio4<XM, 12>(top, bot, L);
+        atan_sum4_both<0, XM>(c, Se);
+        atan_sum4_both<1, XM>(c, Sn);
+        atan_sum4_both<2, XM>(c, Su);
+        const double ve = n[0] * L[0] - n[1] * L[1] + u[0] * L[2] - u[1] * L[3]
+                        - (e[0] * Se[0] - e[1] * Se[1]);
+        const double vn = u[0] * L[4] - u[1] * L[5] + e[0] * L[6] - e[1] * L[7]
+                        - (n[0] * Sn[0] - n[1] * Sn[1]);
+        const double vu = e[0] * L[8] - e[1] * L[9] + n[0] * L[10] - n[1] * L[11]
+                        - (u[0] * Su[0] - u[1] * Su[1]);
+        acc[0] += prm[0] * -ve;
+        acc[1] += prm[0] * -vn;
+        acc[2] += prm[0] * -vu;
     } else if (FS == F_POT || FS == FS_ACC3) {
         double Pu[2][2], Pe[2][2], Pn[2][2], SA[3][2];
 #pragma unroll

@@ -149,6 +149,30 @@ HB_HD double safe_log(double x, double yz2, double r)
     return (r == 0.0) ? 0.0 : l;
 }
 
+// The same two rules on the library's own sequences (hb200_xmath.cuh, defined after this
+// header): used by the rule-exact path of kernel variant 2. Values agree with the libm versions
+// to ~1e-16; every branch decision (x == 0, r == 0, r == -x, signs) is identical.
+HB_HD double fast_log(double a);
+HB_HD double fast_atan2(double y, double x);
+HB_HD double fast_rcp(double x);
+template <bool XM> HB_HD double safe_atan2_t(double y, double x)
+{
+    if (!XM) return safe_atan2(y, x);
+    const double a = fast_atan2(x < 0.0 ? -y : y, fabs(x));  // atan(y / x) for x != 0
+    const double lim = (y > 0.0) ? (kPi / 2) : ((y < 0.0) ? (-kPi / 2) : 0.0);
+    return (x != 0.0) ? a : lim;
+}
+template <bool XM> HB_HD double safe_log_t(double x, double yz2, double r)
+{
+    if (!XM) return safe_log(x, yz2, r);
+    const bool neg = x < 0.0;
+    const bool axis = neg && (r == -x);
+    const double arg = neg ? (axis ? -2.0 * x : yz2 * fast_rcp(r - x)) : (x + r);
+    double l = fast_log(arg);
+    l = axis ? -l : l;
+    return (r == 0.0) ? 0.0 : l;
+}
+
 // Geometry of one (observer, prism) pair: shifted coordinates and the partial
 // sums every kernel shares. Index 0 = east/north/top, 1 = west/south/bottom
 // (the reference's vertex order).
@@ -252,7 +276,7 @@ template <int FS> HB_HD bool nan_rule(const PairPreds& p, unsigned mag_rules)
 // pairs with an exactly-zero shifted coordinate, and as the cross-check of
 // the merged path. `prm` = {G*rho} for gravity, {me, mn, mu} for magnetics.
 // Adds this pair's contribution to acc[0..nout).
-template <int FS>
+template <int FS, bool XM = false>
 HB_HD void prism_pair_direct(const PairGeom& g, const double* prm, unsigned mag_rules, double* acc,
                              unsigned& flags)
 {
@@ -270,12 +294,12 @@ HB_HD void prism_pair_direct(const PairGeom& g, const double* prm, unsigned mag_
                 const double r = sqrt(add_rn(en2, g.su2[k]));
                 const double sg = ((i + j + k) & 1) ? -1.0 : 1.0;
                 double Le = 0, Ln = 0, Lu = 0, Ae = 0, An = 0, Au = 0;
-                if (T::le) Le = safe_log(e, add_rn(g.sn2[j], g.su2[k]), r);
-                if (T::ln) Ln = safe_log(n, add_rn(g.se2[i], g.su2[k]), r);
-                if (T::lu) Lu = safe_log(u, en2, r);
-                if (T::ae) Ae = safe_atan2(n * u, e * r);
-                if (T::an) An = safe_atan2(e * u, n * r);
-                if (T::au) Au = safe_atan2(e * n, u * r);
+                if (T::le) Le = safe_log_t<XM>(e, add_rn(g.sn2[j], g.su2[k]), r);
+                if (T::ln) Ln = safe_log_t<XM>(n, add_rn(g.se2[i], g.su2[k]), r);
+                if (T::lu) Lu = safe_log_t<XM>(u, en2, r);
+                if (T::ae) Ae = safe_atan2_t<XM>(n * u, e * r);
+                if (T::an) An = safe_atan2_t<XM>(e * u, n * r);
+                if (T::au) Au = safe_atan2_t<XM>(e * n, u * r);
                 if (FS == F_POT) {
                     sum[0] += sg * (e * n * Lu + n * u * Le + e * u * Ln - 0.5 * g.se2[i] * Ae
                                     - 0.5 * g.sn2[j] * An - 0.5 * g.su2[k] * Au);
