@@ -20,7 +20,12 @@ hb._lib.load().hb200_set_variant(variant)
 rng = np.random.default_rng(0)
 
 
+ONLY = os.environ.get("SWEEP_ONLY", "")
+
+
 def timeit(name, pairs, fn):
+    if ONLY and ONLY not in name:
+        return
     fn()
     best = min(_t(fn) for _ in range(3))
     print(json.dumps({"case": name, "variant": variant, "pairs": pairs, "seconds": best,
@@ -52,6 +57,11 @@ flat[:, 4] = -np.abs(prisms[:, 4])
 on_top = (coords[0][:32768], coords[1][:32768], np.zeros(32768))
 timeit("prism_gravity g_z, all pairs on the direct path (observers in the top-face plane)",
        float(n_p) * 32768, lambda: hb.prism_gravity(on_top, flat, density, "g_z", disable_checks=True))
+# tensor component on the same geometry: every pair takes the rule-exact path (face rule)
+timeit("prism_gravity g_zz, all pairs on the exact path (observers in the top-face plane)",
+       float(n_p) * 32768, lambda: hb.prism_gravity(on_top, flat, density, "g_zz", disable_checks=True))
+timeit("prism_magnetic b, all pairs on the exact path (observers in the top-face plane)",
+       float(n_p) * 32768, lambda: hb.prism_magnetic(on_top, flat, mag, "b", disable_checks=True))
 lc, east_c, north_c, bottom, top, rho = layer_config2(n=300, seed=2)
 with warnings.catch_warnings():
     warnings.simplefilter("ignore")
