@@ -1,8 +1,9 @@
 // hb200_fast.cuh -- merged-transcendental evaluation of the 8-vertex prism sum.
 //
-// Valid for pairs whose six shifted coordinates are all non-zero (observer not
-// in the plane of any prism face); every other pair takes prism_pair_direct,
-// which carries the reference's singular-point rules verbatim.
+// Valid for the pairs needs_exact_path<FS>() lets through (roughly: observer not in
+// the plane of a prism face; potential/accelerations tolerate one such axis); every
+// other pair takes prism_pair_direct, which carries the reference's singular-point
+// rules verbatim.
 //
 // The reference (choclo kernels behind gravity.py:526-537 / magnetic.py:319)
 // evaluates per vertex 1-3 safe_log and 1-3 safe_atan2 and forms an
@@ -20,7 +21,7 @@
 //            simplifies to  atan2(c a (b0 r1 - b1 r0), a^2 r0 r1 + b0 b1 c^2).
 // Merged forms are algebraically identical to the vertex sum and round better
 // (the far-field cancellation happens inside the ratio, not between logs).
-// g_z: 16 log + 8 atan + 24 div per pair  ->  4 log + 4 atan2 + 4 div.
+// g_z: 16 log + 8 atan + 24 div per pair  ->  4 log + 2..4 atan2 + 6 div.
 #pragma once
 #include "hb200_math.cuh"
 #include "hb200_xmath.cuh"
