@@ -43,6 +43,10 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 # FP64-pipe instruction equivalents per pair of the REFERENCE algorithm
 I_PAIR = {"layer_gz": 1068, "c1_gz": 1068, "tensor": 2020, "mag_b": 2100, "eqs": 26.5}
 NOMINAL_FP64_FLOPS = 148 * 64 * 2 * 1.965e9  # 37.2 TFLOP/s
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE prism_kernel launch of the default workload
+# at full size (profiles/r1_traffic_layer_gz_full_launch.csv; 22.6 MB read + 1.5 MB written;
+# algorithmic: 6 MB observers + 16 MB packed prisms + 2 MB result). L2 serves 31.8 GB of tile loads.
+DRAM_TRAFFIC_PER_LAUNCH = {"layer_gz": 22625024 + 1515776}
 # executed thread-instructions per pair of the CURRENT kernels, from the committed ncu source
 # pages (profiles/r1_opmix_*_final.txt): (FP64 pipe, all other pipes)
 EXECUTED_PER_PAIR = {"layer_gz": (224.7, 147.4), "c1_gz": (224.7, 147.4), "tensor": (284.1, 171.6),
@@ -446,7 +450,7 @@ def run_b200(args):
                 "note": "algorithmic flops = 2 x I_pair of the REFERENCE algorithm (SURVEY 8d); "
                         "the merged-transcendental kernel executes fewer instructions per pair, "
                         "pipe utilisation is in profiles/",
-                "traffic": None,
+                "traffic": DRAM_TRAFFIC_PER_LAUNCH.get(args.workload) if not args.n_obs else None,
                 "executed": executed,
             },
             "cpu_baseline": cpu_baseline,
