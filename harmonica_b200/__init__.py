@@ -12,8 +12,12 @@ ctypes binding. There is no CPU fallback.
 from ._dipole import dipole_magnetic
 from ._eqs import (
     EquivalentSources,
+    EquivalentSourcesGB,
     EquivalentSourcesSph,
+    eqs_fit,
+    eqs_fit_gradient_boosted,
     eqs_jacobian,
+    eqs_jacobian_spherical,
     eqs_predict,
     predict_numba_parallel,
     predict_numba_serial,
@@ -29,11 +33,15 @@ __version__ = "0.1.0"
 __all__ = [
     "DatasetAccessorPrismLayer",
     "EquivalentSources",
+    "EquivalentSourcesGB",
     "EquivalentSourcesSph",
     "dipole_magnetic",
     "HarmonicaB200Error",
     "PrismLayer",
+    "eqs_fit",
+    "eqs_fit_gradient_boosted",
     "eqs_jacobian",
+    "eqs_jacobian_spherical",
     "eqs_predict",
     "init",
     "point_gravity",

@@ -29,6 +29,7 @@ MASK_TENSOR = 0x3F0
 
 _dp = ctypes.POINTER(ctypes.c_double)
 _u32p = ctypes.POINTER(ctypes.c_uint32)
+_i64p = ctypes.POINTER(ctypes.c_int64)
 _i64 = ctypes.c_int64
 _u32 = ctypes.c_uint32
 _int = ctypes.c_int
@@ -62,6 +63,13 @@ SIGNATURES = {
     "hb200_dipole_magnetic": (
         _int, [_dp, _dp, _dp, _i64, _dp, _dp, _dp, _dp, _dp, _dp, _i64, _u32, _int, _dp, _u32p]),
     "hb200_eqs_jacobian": (_int, [_dp, _dp, _dp, _i64, _dp, _dp, _dp, _i64, _dp]),
+    "hb200_eqs_jacobian_spherical": (_int, [_dp, _dp, _dp, _i64, _dp, _dp, _dp, _i64, _dp]),
+    "hb200_eqs_fit": (
+        _int, [_dp, _dp, _dp, _i64, _dp, _dp, _dp, _i64, _dp, _dp, ctypes.c_double, _int, _dp,
+               ctypes.POINTER(_int)]),
+    "hb200_eqs_fit_gb": (
+        _int, [_dp, _dp, _dp, _i64, _dp, _dp, _dp, _i64, _dp, _dp, ctypes.c_double, _int, _i64,
+               _i64p, _i64p, _i64p, _i64p, _dp, _dp]),
     "hb200_prism_ws_bytes": (_sz, [_i64, _i64, _int]),
     "hb200_point_ws_bytes": (_sz, [_i64, _i64]),
     "hb200_prism_gravity_dev": (

@@ -725,6 +725,8 @@ Scales gravity_scales_for_mask(uint32_t mask)
 
 }  // namespace
 
+#include "hb200_fit_host.cuh"
+
 // =============================================================== C ABI
 extern "C" {
 
@@ -759,6 +761,7 @@ uint64_t hb200_launch_count(void) { return g_launches.load(); }
 
 void hb200_shutdown(void)
 {
+    dense_release();
     for (Dev& d : g_devs) {
         cudaSetDevice(d.id);
         if (d.pool) cudaFree(d.pool);
@@ -1013,9 +1016,10 @@ int hb200_dipole_magnetic(const double* easting, const double* northing, const d
                         out, flags, launch, ws_dipole);
 }
 
-int hb200_eqs_jacobian(const double* easting, const double* northing, const double* upward,
-                       int64_t n_obs, const double* src_easting, const double* src_northing,
-                       const double* src_upward, int64_t n_src, double* jac)
+static int eqs_jacobian_host(int spherical, const double* easting, const double* northing,
+                             const double* upward, int64_t n_obs, const double* src_easting,
+                             const double* src_northing, const double* src_upward, int64_t n_src,
+                             double* jac)
 {
     std::lock_guard<std::mutex> lock(g_mu);
     int rc = lazy_init();
@@ -1041,15 +1045,184 @@ int hb200_eqs_jacobian(const double* easting, const double* northing, const doub
     double* d_jac = dev.take<double>((size_t)slab * n_src);
     for (int64_t i0 = 0; i0 < n_obs; i0 += slab) {
         const int64_t rows = std::min(slab, n_obs - i0);
-        dim3 grid((unsigned)((n_src + 255) / 256), (unsigned)((rows + 15) / 16));
-        eqs_jacobian_kernel<<<grid, 256, 0, dev.st>>>(d_o[0] + i0, d_o[1] + i0, d_o[2] + i0, rows,
-                                                     d_p[0], d_p[1], d_p[2], n_src, d_jac);
-        CU(cudaGetLastError());
-        g_launches += 1;
+        const double* obs[3] = {d_o[0] + i0, d_o[1] + i0, d_o[2] + i0};
+        rc = build_jacobian_dev(dev, spherical, obs, rows, d_p, n_src, d_jac);
+        if (rc) return rc;
         CU(cudaMemcpyAsync(jac + i0 * n_src, d_jac, (size_t)rows * n_src * 8, cudaMemcpyDeviceToHost,
                            dev.st));
         CU(cudaStreamSynchronize(dev.st));
     }
+    return HB200_OK;
+}
+
+int hb200_eqs_jacobian(const double* easting, const double* northing, const double* upward,
+                       int64_t n_obs, const double* src_easting, const double* src_northing,
+                       const double* src_upward, int64_t n_src, double* jac)
+{
+    return eqs_jacobian_host(0, easting, northing, upward, n_obs, src_easting, src_northing,
+                             src_upward, n_src, jac);
+}
+
+int hb200_eqs_jacobian_spherical(const double* longitude, const double* latitude,
+                                 const double* radius, int64_t n_obs, const double* src_longitude,
+                                 const double* src_latitude, const double* src_radius,
+                                 int64_t n_src, double* jac)
+{
+    return eqs_jacobian_host(1, longitude, latitude, radius, n_obs, src_longitude, src_latitude,
+                             src_radius, n_src, jac);
+}
+
+int hb200_eqs_fit(const double* easting, const double* northing, const double* upward,
+                  int64_t n_obs, const double* src_easting, const double* src_northing,
+                  const double* src_upward, int64_t n_src, const double* data,
+                  const double* weights, double damping, int spherical, double* coefs,
+                  int* solver_path)
+{
+    std::lock_guard<std::mutex> lock(g_mu);
+    int rc = lazy_init();
+    if (rc) return rc;
+    if (n_obs <= 0 || n_src <= 0) return fail(HB200_EINVAL, "the fit needs data points and sources");
+    Dev& dev = g_devs[0];
+    CU(cudaSetDevice(dev.id));
+    const size_t need = 5 * align_up(n_obs * 8) + 4 * align_up(n_src * 8)
+                      + align_up((size_t)n_obs * n_src * 8);
+    rc = dev.ensure(need + 4096);
+    if (rc) return rc;
+    double* d_o[3];
+    double* d_p[3];
+    const double* ho[3] = {easting, northing, upward};
+    const double* hp[3] = {src_easting, src_northing, src_upward};
+    for (int c = 0; c < 3; c++) {
+        d_o[c] = dev.take<double>(n_obs);
+        d_p[c] = dev.take<double>(n_src);
+        CU(cudaMemcpyAsync(d_o[c], ho[c], n_obs * 8, cudaMemcpyHostToDevice, dev.st));
+        CU(cudaMemcpyAsync(d_p[c], hp[c], n_src * 8, cudaMemcpyHostToDevice, dev.st));
+    }
+    double* d_data = dev.take<double>(n_obs);
+    double* d_w = dev.take<double>(n_obs);
+    double* d_coef = dev.take<double>(n_src);
+    double* d_jac = dev.take<double>((size_t)n_obs * n_src);
+    CU(cudaMemcpyAsync(d_data, data, n_obs * 8, cudaMemcpyHostToDevice, dev.st));
+    if (weights) CU(cudaMemcpyAsync(d_w, weights, n_obs * 8, cudaMemcpyHostToDevice, dev.st));
+    rc = build_jacobian_dev(dev, spherical, d_o, n_obs, d_p, n_src, d_jac);
+    if (rc) return rc;
+    const bool damped = !std::isnan(damping);
+    rc = dense_least_squares(dev, d_jac, n_obs, n_src, d_data, weights ? d_w : nullptr, damped,
+                             damping, d_coef, solver_path);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(coefs, d_coef, n_src * 8, cudaMemcpyDeviceToHost, dev.st));
+    CU(cudaStreamSynchronize(dev.st));
+    return HB200_OK;
+}
+
+int hb200_eqs_fit_gb(const double* easting, const double* northing, const double* upward,
+                     int64_t n_obs, const double* src_easting, const double* src_northing,
+                     const double* src_upward, int64_t n_src, const double* data,
+                     const double* weights, double damping, int spherical, int64_t n_windows,
+                     const int64_t* src_index, const int64_t* src_offset,
+                     const int64_t* data_index, const int64_t* data_offset, double* coefs,
+                     double* rmse)
+{
+    std::lock_guard<std::mutex> lock(g_mu);
+    int rc = lazy_init();
+    if (rc) return rc;
+    if (n_obs <= 0 || n_src <= 0 || n_windows < 0)
+        return fail(HB200_EINVAL, "the fit needs data points and sources");
+    int64_t max_nd = 0, max_np = 0;
+    size_t max_jac = 0;
+    for (int64_t w = 0; w < n_windows; w++) {
+        const int64_t np = src_offset[w + 1] - src_offset[w], nd = data_offset[w + 1] - data_offset[w];
+        if (np <= 0 || nd <= 0) return fail(HB200_EINVAL, "window %lld is empty", (long long)w);
+        max_np = std::max(max_np, np);
+        max_nd = std::max(max_nd, nd);
+        max_jac = std::max(max_jac, (size_t)np * (size_t)nd);
+    }
+    const int64_t n_si = src_offset[n_windows], n_di = data_offset[n_windows];
+    Dev& dev = g_devs[0];
+    CU(cudaSetDevice(dev.id));
+    const int64_t n_blocks = (n_obs + 255) / 256;
+    const size_t ws_bytes = point_ws_bytes(n_obs, std::max<int64_t>(max_np, 1), dev.sms);
+    const size_t need = 7 * align_up(n_obs * 8) + 4 * align_up(n_src * 8)
+                      + align_up(n_si * 8) + align_up(n_di * 8) + 5 * align_up(max_nd * 8)
+                      + 4 * align_up(max_np * 8) + align_up(max_jac * 8) + align_up(n_blocks * 8)
+                      + align_up((n_windows + 1) * 8) + align_up(ws_bytes);
+    rc = dev.ensure(need + 8192);
+    if (rc) return rc;
+    cudaStream_t st = dev.st;
+    double* d_o[3];
+    double* d_p[3];
+    const double* ho[3] = {easting, northing, upward};
+    const double* hp[3] = {src_easting, src_northing, src_upward};
+    for (int c = 0; c < 3; c++) {
+        d_o[c] = dev.take<double>(n_obs);
+        d_p[c] = dev.take<double>(n_src);
+        CU(cudaMemcpyAsync(d_o[c], ho[c], n_obs * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_p[c], hp[c], n_src * 8, cudaMemcpyHostToDevice, st));
+    }
+    double* d_residue = dev.take<double>(n_obs);
+    double* d_w = dev.take<double>(n_obs);
+    double* d_pred = dev.take<double>(n_obs);
+    double* d_coefs = dev.take<double>(n_src);
+    int64_t* d_si = dev.take<int64_t>(std::max<int64_t>(n_si, 1));
+    int64_t* d_di = dev.take<int64_t>(std::max<int64_t>(n_di, 1));
+    double* c_o[3] = {dev.take<double>(max_nd), dev.take<double>(max_nd), dev.take<double>(max_nd)};
+    double* c_res = dev.take<double>(max_nd);
+    double* c_w = dev.take<double>(max_nd);
+    double* c_p[3] = {dev.take<double>(max_np), dev.take<double>(max_np), dev.take<double>(max_np)};
+    double* c_coef = dev.take<double>(max_np);
+    double* d_jac = dev.take<double>(max_jac);
+    double* d_bsum = dev.take<double>(n_blocks);
+    double* d_rmse = dev.take<double>(n_windows + 1);
+    void* d_ws = dev.take<char>(ws_bytes);
+    CU(cudaMemcpyAsync(d_residue, data, n_obs * 8, cudaMemcpyHostToDevice, st));
+    if (weights) CU(cudaMemcpyAsync(d_w, weights, n_obs * 8, cudaMemcpyHostToDevice, st));
+    if (n_si) CU(cudaMemcpyAsync(d_si, src_index, n_si * 8, cudaMemcpyHostToDevice, st));
+    if (n_di) CU(cudaMemcpyAsync(d_di, data_index, n_di * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(d_coefs, 0, n_src * 8, st));
+    CU(cudaMemsetAsync(dev.d_flags, 0, sizeof(unsigned), st));
+    // errors[0] = sqrt(mean(data^2)), gradient_boosted.py:253
+    residue_update_kernel<<<(unsigned)n_blocks, 256, 0, st>>>(d_residue, nullptr, n_obs, d_bsum);
+    finish_rmse_kernel<<<1, 256, 0, st>>>(d_bsum, n_blocks, n_obs, d_rmse);
+    CU(cudaGetLastError());
+    g_launches += 2;
+    const bool damped = !std::isnan(damping);
+    for (int64_t w = 0; w < n_windows; w++) {
+        const int64_t np = src_offset[w + 1] - src_offset[w], nd = data_offset[w + 1] - data_offset[w];
+        const int64_t* si = d_si + src_offset[w];
+        const int64_t* di = d_di + data_offset[w];
+        // gradient_boosted.py:265-271: the sources, data points, residues and weights of the window
+        Gather4 gp = {{d_p[0], d_p[1], d_p[2], nullptr}, {c_p[0], c_p[1], c_p[2], nullptr}};
+        gather_kernel<<<blocks_for(np), 256, 0, st>>>(gp, si, np);
+        Gather4 go = {{d_o[0], d_o[1], d_o[2], d_residue}, {c_o[0], c_o[1], c_o[2], c_res}};
+        gather_kernel<<<blocks_for(nd), 256, 0, st>>>(go, di, nd);
+        if (weights) {
+            Gather4 gw = {{d_w, nullptr, nullptr, nullptr}, {c_w, nullptr, nullptr, nullptr}};
+            gather_kernel<<<blocks_for(nd), 256, 0, st>>>(gw, di, nd);
+            g_launches += 1;
+        }
+        CU(cudaGetLastError());
+        g_launches += 2;
+        // :273-280: Jacobian of the window and its least-squares coefficients
+        rc = build_jacobian_dev(dev, spherical, c_o, nd, c_p, np, d_jac);
+        if (rc) return rc;
+        rc = dense_least_squares(dev, d_jac, nd, np, c_res, weights ? c_w : nullptr, damped, damping,
+                                 c_coef, nullptr);
+        if (rc) return rc;
+        // :282-289: field of the window's sources on EVERY data point
+        rc = point_gravity_dev_impl(d_o[0], d_o[1], d_o[2], n_obs, c_p[0], c_p[1], c_p[2], c_coef, np,
+                                    1u << F_POT, spherical, 0, false, d_pred, dev.d_flags, d_ws,
+                                    ws_bytes, dev.sms, st);
+        if (rc) return rc;
+        // :290-294: residue, RMSE history, coefficients
+        residue_update_kernel<<<(unsigned)n_blocks, 256, 0, st>>>(d_residue, d_pred, n_obs, d_bsum);
+        finish_rmse_kernel<<<1, 256, 0, st>>>(d_bsum, n_blocks, n_obs, d_rmse + w + 1);
+        scatter_add_kernel<<<blocks_for(np), 256, 0, st>>>(d_coefs, si, c_coef, np);
+        CU(cudaGetLastError());
+        g_launches += 3;
+    }
+    CU(cudaMemcpyAsync(coefs, d_coefs, n_src * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(rmse, d_rmse, (n_windows + 1) * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     return HB200_OK;
 }
 

@@ -158,6 +158,47 @@ int hb200_eqs_jacobian(const double* easting, const double* northing, const doub
                        int64_t n_obs, const double* src_easting, const double* src_northing,
                        const double* src_upward, int64_t n_src, double* jac);
 
+/* the same matrix with greens_func_spherical (EquivalentSourcesSph.jacobian,
+ * _equivalent_sources/spherical.py:249-283, 412-424): longitude, latitude in degrees */
+int hb200_eqs_jacobian_spherical(const double* longitude, const double* latitude,
+                                 const double* radius, int64_t n_obs, const double* src_longitude,
+                                 const double* src_latitude, const double* src_radius,
+                                 int64_t n_src, double* jac);
+
+/* replaces the body of EquivalentSources.fit, _equivalent_sources/cartesian.py:277-280
+ * (EquivalentSourcesSph.fit, spherical.py:213-215): Jacobian + verde.base.least_squares,
+ * entirely on the device (device 0 of hb200_init). The Jacobian never leaves HBM; its
+ * columns are scaled by their standard deviation, rows by sqrt(weights) (weights may be
+ * NULL), then
+ *   damping given (not NaN): (X'X + damping I) c = X'y by Cholesky, like sklearn's Ridge
+ *       (dual form when n_src > n_obs; SVD ridge filter if the factorisation fails);
+ *   damping = NaN ("None"): minimum-norm least squares from the SVD with singular values
+ *       below eps * s_max dropped, like scipy.linalg.lstsq behind sklearn's LinearRegression.
+ * coefs (n_src) receives the unscaled coefficients. *solver_path (may be NULL): 0 Cholesky,
+ * 1 SVD pseudo-inverse, 2 SVD ridge filter. Dense algebra: cuBLAS / cuSOLVER, loaded on
+ * first use. */
+int hb200_eqs_fit(const double* easting, const double* northing, const double* upward,
+                  int64_t n_obs, const double* src_easting, const double* src_northing,
+                  const double* src_upward, int64_t n_src, const double* data,
+                  const double* weights, double damping, int spherical, double* coefs,
+                  int* solver_path);
+
+/* replaces EquivalentSourcesGB._gradient_boosting, _equivalent_sources/
+ * gradient_boosted.py:244-293: for every window (in the given order) fit the window's sources
+ * to the residue of the window's data points (as hb200_eqs_fit), predict their field on ALL
+ * data points, update the residue and add the coefficients. Window w owns
+ * src_index[src_offset[w] .. src_offset[w+1]) and data_index[data_offset[w] .. ), both
+ * non-empty with distinct entries. coefs (n_src) receives the summed coefficients, rmse
+ * (n_windows + 1) the reference's rmse_per_iteration_. Everything between the upload of the
+ * inputs and the download of coefs / rmse runs on the device. */
+int hb200_eqs_fit_gb(const double* easting, const double* northing, const double* upward,
+                     int64_t n_obs, const double* src_easting, const double* src_northing,
+                     const double* src_upward, int64_t n_src, const double* data,
+                     const double* weights, double damping, int spherical, int64_t n_windows,
+                     const int64_t* src_index, const int64_t* src_offset,
+                     const int64_t* data_index, const int64_t* data_offset, double* coefs,
+                     double* rmse);
+
 /* ---- device-buffer entry points (current device, async on stream) -------- */
 size_t hb200_prism_ws_bytes(int64_t n_obs, int64_t n_sources, int n_fields);
 size_t hb200_point_ws_bytes(int64_t n_obs, int64_t n_sources);
