@@ -27,6 +27,7 @@ from ._point import point_gravity
 from ._prism_gravity import prism_gravity
 from ._prism_layer import DatasetAccessorPrismLayer, PrismLayer, prism_layer, prism_layer_gravity
 from ._prism_magnetic import prism_magnetic
+from ._tesseroid import tesseroid_gravity
 
 __version__ = "0.1.0"
 
@@ -51,4 +52,5 @@ __all__ = [
     "prism_layer",
     "prism_layer_gravity",
     "prism_magnetic",
+    "tesseroid_gravity",
 ]

@@ -16,6 +16,9 @@ LIB_PATH = os.path.join(_HERE, "libharmonica_b200.so")
 HB200_OK = 0
 FLAG_SINGULAR = 1
 FLAG_ZERO_DIV = 2
+FLAG_TESS_STACK = 4
+FLAG_TESS_LEAVES = 8
+FLAG_TESS_INSIDE = 16
 SHARD_AUTO, SHARD_OBSERVERS, SHARD_SOURCES = 0, 1, 2
 MAG_DEFAULT_RULES = 3
 
@@ -70,6 +73,12 @@ SIGNATURES = {
     "hb200_eqs_fit_gb": (
         _int, [_dp, _dp, _dp, _i64, _dp, _dp, _dp, _i64, _dp, _dp, ctypes.c_double, _int, _i64,
                _i64p, _i64p, _i64p, _i64p, _dp, _dp]),
+    "hb200_tesseroid_gravity": (
+        _int, [_dp, _dp, _dp, _i64, _dp, _dp, _i64, _int, _int, _int, _dp, _u32p]),
+    "hb200_tesseroid_inside_scan": (_int, [_dp, _dp, _dp, _i64, _dp, _i64, _u32p]),
+    "hb200_tesseroid_ws_bytes": (_sz, [_i64, _i64]),
+    "hb200_tesseroid_gravity_dev": (
+        _int, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _int, _int, _vp, _vp, _vp, _sz, _vp]),
     "hb200_prism_ws_bytes": (_sz, [_i64, _i64, _int]),
     "hb200_point_ws_bytes": (_sz, [_i64, _i64]),
     "hb200_prism_gravity_dev": (

@@ -1,0 +1,207 @@
+"""
+``tesseroid_gravity``: forward model of tesseroids (spherical prisms) on the GPU.
+
+Drop-in for ``harmonica.tesseroid_gravity`` (``harmonica/_forward/tesseroid_gravity.py:36-224``)
+for constant densities: same signature, checks, error messages, units and signs. The pair loop
+(``jit_tesseroid_gravity``, :236-339: adaptive discretisation + Gauss-Legendre point masses) runs
+in ``libharmonica_b200.so`` (``hb200_tesseroid_gravity``); the O(N x P) "points outside
+tesseroids" check (``_tesseroid_utils.py:398-454``) is a device scan as well.
+
+Not provided: densities given as a numba-jitted function (``_tesseroid_variable_density.py``);
+a Python callable cannot run inside the CUDA kernel.
+"""
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._utils import broadcast_coordinates
+
+_FIELDS = {"potential": 0, "g_z": 3}
+
+
+def _check_tesseroids(tesseroids):
+    """``_tesseroid_utils.py:303-395``: boundary checks (same order, same messages)."""
+    west, east, south, north, bottom, top = tuple(tesseroids[:, i] for i in range(6))
+    err_msg = "Invalid tesseroid or tesseroids. "
+
+    def fail(invalid, text):
+        msg = err_msg + text
+        for tess in tesseroids[invalid]:
+            msg += f"\tInvalid tesseroid: {tess}\n"
+        raise ValueError(msg)
+
+    invalid = np.logical_or(
+        np.logical_or(south < -90, south > 90), np.logical_or(north < -90, north > 90)
+    )
+    if invalid.any():
+        fail(invalid, "The latitudinal boundaries must be inside the [-90, 90] degrees interval.\n")
+    invalid = south > north
+    if invalid.any():
+        fail(invalid, "The south boundary can't be greater than the north one.\n")
+    invalid = np.logical_or(bottom < 0, top < 0)
+    if invalid.any():
+        fail(invalid, "The bottom and top radii should be positive or zero.\n")
+    invalid = bottom > top
+    if invalid.any():
+        fail(invalid, "The bottom radius boundary can't be greater than the top one.\n")
+    invalid = np.logical_or(
+        np.logical_or(west < -180, west > 360), np.logical_or(east < -180, east > 360)
+    )
+    if invalid.any():
+        fail(invalid, "The longitudinal boundaries must be inside the [-180, 360] degrees interval.\n")
+    if (west > east).any():
+        tesseroids = _longitude_continuity(tesseroids)
+        west, east = tesseroids[:, 0], tesseroids[:, 1]
+    invalid = west > east
+    if invalid.any():
+        fail(invalid, "The west boundary can't be greater than the east one.\n")
+    invalid = east - west > 360
+    if invalid.any():
+        fail(
+            invalid,
+            "The difference between east and west boundaries cannot be greater than "
+            "one turn around the globe.\n",
+        )
+    return tesseroids
+
+
+def _longitude_continuity(tesseroids):
+    """``_tesseroid_utils.py:457-486``: west > east tesseroids are moved to [-180, 180)."""
+    tesseroids = tesseroids.copy()
+    west, east = tesseroids[:, 0], tesseroids[:, 1]
+    change = west > east
+    east[change] = ((east[change] + 180) % 360) - 180
+    west[change] = ((west[change] + 180) % 360) - 180
+    return tesseroids
+
+
+def _discard_null_tesseroids(tesseroids, density):
+    """``_tesseroid_utils.py:489-538``: zero volume or zero density."""
+    west, east, south, north, bottom, top = tuple(tesseroids[:, i] for i in range(6))
+    null = (west == east) | (south == north) | (bottom == top)
+    null[density == 0] = True
+    keep = np.logical_not(null)
+    return tesseroids[keep, :], density[keep]
+
+
+def _conflicting_pairs(coordinates, tesseroids, block=4096):
+    """The (point, tesseroid) index pairs of ``_check_points_outside_tesseroids`` (:431-454),
+    point-major like the reference's loop; only run once the device scan has found a conflict."""
+    longitude, latitude, radius = coordinates
+    west, east, south, north, bottom, top = (tesseroids[:, i][None, :] for i in range(6))
+    pairs = []
+    for start in range(0, longitude.size, block):
+        lon = longitude[start:start + block, None]
+        lat = latitude[start:start + block, None]
+        rad = radius[start:start + block, None]
+        lon_360 = lon % 360
+        lon_180 = ((lon + 180) % 360) - 180
+        inside = (
+            (((west < lon_180) & (lon_180 < east)) | ((west < lon_360) & (lon_360 < east)))
+            & (south < lat) & (lat < north) & (bottom < rad) & (rad < top)
+        )  # fmt: skip
+        ii, jj = np.nonzero(inside)
+        pairs.extend(zip((ii + start).tolist(), jj.tolist()))
+    return pairs
+
+
+def check_points_outside_tesseroids(coordinates, tesseroids):
+    """
+    Raise ``ValueError`` if a computation point lies inside a tesseroid
+    (``_tesseroid_utils.py:398-428``); the pair scan runs on the device.
+    """
+    coordinates = tuple(_lib.f64(np.atleast_1d(c).ravel()) for c in coordinates[:3])
+    tesseroids = _lib.f64(np.atleast_2d(tesseroids))
+    if coordinates[0].size == 0 or tesseroids.shape[0] == 0:
+        return
+    lib = _lib.ensure_init()
+    flags = ctypes.c_uint32(0)
+    _lib.check(
+        lib.hb200_tesseroid_inside_scan(
+            _lib.ptr(coordinates[0]), _lib.ptr(coordinates[1]), _lib.ptr(coordinates[2]),
+            coordinates[0].size, _lib.ptr(tesseroids), tesseroids.shape[0], ctypes.byref(flags),
+        )  # fmt: skip
+    )
+    if not flags.value & _lib.FLAG_TESS_INSIDE:
+        return
+    longitude, latitude, radius = coordinates
+    err_msg = (
+        "Found computation point(s) inside tesseroid(s). "
+        "Computation points must be outside of tesseroids.\n"
+    )
+    for i, j in _conflicting_pairs(coordinates, tesseroids):
+        west, east, south, north, bottom, top = tesseroids[j, :]
+        err_msg += (
+            f" - Computation point '({longitude[i]}, {latitude[i]}, {radius[i]})' "
+            "inside tesseroid "
+            f"'({west}, {east}, {south}, {north}, {bottom}, {top})'.\n"
+        )
+    raise ValueError(err_msg)
+
+
+def tesseroid_gravity(
+    coordinates,
+    tesseroids,
+    density,
+    field,
+    parallel=True,
+    radial_adaptive_discretization=False,
+    dtype=np.float64,
+    progressbar=False,
+    disable_checks=False,
+    *,
+    shard="auto",
+):
+    """
+    Gravitational potential (J/kg) or downward acceleration ``g_z`` (mGal) of tesseroids on
+    computation points given as (longitude, latitude, radius) in degrees and metres.
+
+    ``parallel`` and ``progressbar`` are accepted for signature compatibility (the device is
+    always parallel; one launch reports no intermediate progress). All arithmetic is float64 and
+    the result is cast to ``dtype`` at the end.
+    """
+    if field not in _FIELDS:
+        raise ValueError(f"Gravitational field {field} not recognized")
+    if callable(density):
+        raise NotImplementedError(
+            "harmonica_b200.tesseroid_gravity needs constant densities: a density function "
+            "(variable-density tesseroids) cannot run inside the CUDA kernel"
+        )
+    shape, coords = broadcast_coordinates(coordinates)
+    tesseroids = np.atleast_2d(np.asarray(tesseroids, dtype=np.float64))
+    if not disable_checks:
+        tesseroids = _check_tesseroids(tesseroids)
+        check_points_outside_tesseroids(coords, tesseroids)
+    density = np.atleast_1d(density).ravel()
+    if not disable_checks and density.size != tesseroids.shape[0]:
+        raise ValueError(
+            f"Number of elements in density ({density.size}) "
+            + f"mismatch the number of tesseroids ({tesseroids.shape[0]})"
+        )
+    tesseroids, density = _discard_null_tesseroids(tesseroids, density)
+    tesseroids, density = _lib.f64(tesseroids), _lib.f64(density)
+    lib = _lib.ensure_init()
+    out = np.empty(coords[0].size, dtype=np.float64)
+    flags = ctypes.c_uint32(0)
+    _lib.check(
+        lib.hb200_tesseroid_gravity(
+            _lib.ptr(coords[0]), _lib.ptr(coords[1]), _lib.ptr(coords[2]), coords[0].size,
+            _lib.ptr(tesseroids), _lib.ptr(density), tesseroids.shape[0], _FIELDS[field],
+            int(bool(radial_adaptive_discretization)), _lib.shard_mode(shard), _lib.ptr(out),
+            ctypes.byref(flags),
+        )  # fmt: skip
+    )
+    # the reference raises from inside the jitted loop: numba's float division raises on a zero
+    # divisor (a computation point on a corner that 3-D discretisation splits without end, or
+    # on a quadrature node); _tesseroid_utils.py:192-207 raise OverflowError
+    if flags.value & _lib.FLAG_ZERO_DIV:
+        raise ZeroDivisionError("division by zero")
+    if flags.value & _lib.FLAG_TESS_STACK:
+        raise OverflowError("Stack Overflow. Try to increase the stack size.")
+    if flags.value & _lib.FLAG_TESS_LEAVES:
+        raise OverflowError(
+            "Exceeded maximum discretizations. Please increase the MAX_DISCRETIZATIONS."
+        )
+    return out.astype(dtype, copy=False).reshape(shape)

@@ -20,6 +20,7 @@
 
 #include "../../include/harmonica_b200.h"
 #include "hb200_kernels.cuh"
+#include "hb200_tess.cuh"
 
 using namespace hb;
 
@@ -519,6 +520,63 @@ int dipole_magnetic_dev_impl(const double* oe, const double* on, const double* o
     return HB200_OK;
 }
 
+// tesseroid_gravity: one field per pass (potential or g_z); workspace = [packed][partials]
+size_t tesseroid_ws_bytes(int64_t n_obs, int64_t n_src, int sms)
+{
+    return align_up((size_t)std::max<int64_t>(n_src, 1) * kTessStride * sizeof(double))
+         + partial_bytes_for(n_obs, n_src, 1, kTessBlock, sms) + 256;
+}
+
+int tesseroid_dev_impl(const double* lon, const double* lat, const double* rad, int64_t n_obs,
+                       const double* tesseroids, const double* density, int64_t n_tess, int field,
+                       int radial, bool raw, double* out, unsigned* d_flags, void* wsp,
+                       size_t ws_bytes, int sms, cudaStream_t st)
+{
+    if (field != F_POT && field != F_U) return fail(HB200_EINVAL, "tesseroids: potential or g_z only");
+    Ws ws(wsp, ws_bytes);
+    double* packed = ws.take((size_t)std::max<int64_t>(n_tess, 1) * kTessStride * sizeof(double));
+    if (!packed) return fail(HB200_EINVAL, "workspace too small");
+    if (n_obs == 0) return HB200_OK;
+    if (n_tess == 0) {
+        CU(cudaMemsetAsync(out, 0, sizeof(double) * n_obs, st));
+        return HB200_OK;
+    }
+    pack_tesseroids_kernel<<<(unsigned)((n_tess + 255) / 256), 256, 0, st>>>(tesseroids, density,
+                                                                            n_tess, packed);
+    CU(cudaGetLastError());
+    double* partial = (double*)(ws.base + ws.used);
+    const size_t partial_bytes = ws.left();
+    int64_t chunk_len = 0;
+    int chunks = choose_chunks(n_obs, n_tess, kTessBlock, sms, &chunk_len);
+    if (chunks > 1 && (size_t)chunks * n_obs * sizeof(double) > partial_bytes) {
+        chunks = 1;
+        chunk_len = n_tess;
+    }
+    // tesseroid_gravity.py:222-225: g_z is the downward component in mGal
+    const double scale = raw ? 1.0 : (field == F_U ? -1e5 : 1.0);
+    TessArgs a;
+    a.lon = lon; a.lat = lat; a.rad = rad; a.n_obs = n_obs;
+    a.packed = packed; a.n_src = n_tess; a.chunk_len = chunk_len;
+    a.out = chunks > 1 ? partial : out;
+    a.scale = scale;
+    a.ratio = field == F_POT ? 1.0 : 2.5;  // tesseroid_gravity.py:33 DISTANCE_SIZE_RATII
+    a.radial = radial;
+    a.flags = d_flags;
+    dim3 grid((unsigned)((n_obs + kTessBlock - 1) / kTessBlock), (unsigned)chunks);
+    if (field == F_POT) tesseroid_kernel<F_POT><<<grid, kTessBlock, 0, st>>>(a);
+    else tesseroid_kernel<F_U><<<grid, kTessBlock, 0, st>>>(a);
+    CU(cudaGetLastError());
+    g_launches += chunks > 1 ? 3 : 2;
+    if (chunks > 1) {
+        Scales sc;
+        sc.s[0] = scale;
+        reduce_partials_kernel<<<(unsigned)((n_obs + 255) / 256), 256, 0, st>>>(partial, chunks, 1,
+                                                                               n_obs, sc, out);
+        CU(cudaGetLastError());
+    }
+    return HB200_OK;
+}
+
 // ------------------------------------------------------------- host sharding
 int lazy_init()
 {
@@ -711,6 +769,12 @@ size_t ws_dipole(int64_t no, int64_t ns, int nf, int sms)
 {
     (void)nf;
     return dipole_ws_bytes(no, ns, sms);
+}
+
+size_t ws_tesseroid(int64_t no, int64_t ns, int nf, int sms)
+{
+    (void)nf;
+    return tesseroid_ws_bytes(no, ns, sms);
 }
 
 Scales gravity_scales_for_mask(uint32_t mask)
@@ -1016,6 +1080,67 @@ int hb200_dipole_magnetic(const double* easting, const double* northing, const d
                         out, flags, launch, ws_dipole);
 }
 
+int hb200_tesseroid_gravity(const double* longitude, const double* latitude, const double* radius,
+                            int64_t n_obs, const double* tesseroids, const double* density,
+                            int64_t n_tesseroids, int field, int radial_adaptive_discretization,
+                            int shard_mode, double* out, uint32_t* flags)
+{
+    if (field != HB200_POTENTIAL && field != HB200_G_Z)
+        return fail(HB200_EINVAL, "tesseroid_gravity computes the potential or g_z, not field %d", field);
+    if (n_obs < 0 || n_tesseroids < 0) return fail(HB200_EINVAL, "negative size");
+    std::vector<HostArray> arrays = {{tesseroids, n_tesseroids, 6, true},
+                                     {density, n_tesseroids, 1, true}};
+    auto launch = [=](Dev& dev, const double* oe, const double* on, const double* ou, int64_t no,
+                      std::vector<double*>& arr, int64_t ns, bool raw, double* d_out, void* ws,
+                      size_t wsb) {
+        return tesseroid_dev_impl(oe, on, ou, no, arr[0], arr[1], ns, field,
+                                  radial_adaptive_discretization, raw, d_out, dev.d_flags, ws, wsb,
+                                  dev.sms, dev.st);
+    };
+    Scales sc;
+    for (int c = 0; c < 6; c++) sc.s[c] = 1.0;
+    sc.s[0] = field == HB200_G_Z ? -1e5 : 1.0;
+    return run_host_job(longitude, latitude, radius, n_obs, arrays, n_tesseroids, 1, shard_mode, true,
+                        sc, out, flags, launch, ws_tesseroid);
+}
+
+int hb200_tesseroid_inside_scan(const double* longitude, const double* latitude,
+                                const double* radius, int64_t n_obs, const double* tesseroids,
+                                int64_t n_tesseroids, uint32_t* flags)
+{
+    if (!flags) return fail(HB200_EINVAL, "flags must not be NULL");
+    *flags = 0;
+    if (n_obs <= 0 || n_tesseroids <= 0) return HB200_OK;
+    std::vector<HostArray> arrays = {{tesseroids, n_tesseroids, 6, false}};
+    auto launch = [=](Dev& dev, const double* oe, const double* on, const double* ou, int64_t no,
+                      std::vector<double*>& arr, int64_t ns, bool raw, double* d_out, void* ws,
+                      size_t wsb) {
+        (void)raw; (void)d_out; (void)ns;
+        Ws w(ws, wsb);
+        double* packed = w.take((size_t)n_tesseroids * kTessStride * sizeof(double));
+        if (!packed) return fail(HB200_EINVAL, "workspace too small");
+        // the density slot of the record is not read by the scan
+        pack_tesseroids_kernel<<<(unsigned)((n_tesseroids + 255) / 256), 256, 0, dev.st>>>(
+            arr[0], arr[0], n_tesseroids, packed);
+        int64_t chunk_len;
+        int chunks = choose_chunks(no, n_tesseroids, 128, dev.sms, &chunk_len);
+        TessArgs a;
+        a.lon = oe; a.lat = on; a.rad = ou; a.n_obs = no; a.packed = packed;
+        a.n_src = n_tesseroids; a.chunk_len = chunk_len; a.out = nullptr; a.scale = 1.0;
+        a.ratio = 0.0; a.radial = 0; a.flags = dev.d_flags;
+        dim3 grid((unsigned)((no + 127) / 128), (unsigned)chunks);
+        tesseroid_inside_scan_kernel<<<grid, 128, 0, dev.st>>>(a);
+        CU(cudaGetLastError());
+        g_launches += 2;
+        return HB200_OK;
+    };
+    Scales sc;
+    for (int c = 0; c < 6; c++) sc.s[c] = 1.0;
+    std::vector<double> dummy((size_t)n_obs);
+    return run_host_job(longitude, latitude, radius, n_obs, arrays, n_tesseroids, 1,
+                        HB200_SHARD_OBSERVERS, false, sc, dummy.data(), flags, launch, ws_tesseroid);
+}
+
 static int eqs_jacobian_host(int spherical, const double* easting, const double* northing,
                              const double* upward, int64_t n_obs, const double* src_easting,
                              const double* src_northing, const double* src_upward, int64_t n_src,
@@ -1235,6 +1360,22 @@ size_t hb200_prism_ws_bytes(int64_t n_obs, int64_t n_sources, int n_fields)
 size_t hb200_point_ws_bytes(int64_t n_obs, int64_t n_sources)
 {
     return point_ws_bytes(n_obs, n_sources, 148);
+}
+
+size_t hb200_tesseroid_ws_bytes(int64_t n_obs, int64_t n_tesseroids)
+{
+    return tesseroid_ws_bytes(n_obs, n_tesseroids, sm_count_current());
+}
+
+int hb200_tesseroid_gravity_dev(const double* longitude, const double* latitude, const double* radius,
+                                int64_t n_obs, const double* tesseroids, const double* density,
+                                int64_t n_tesseroids, int field, int radial_adaptive_discretization,
+                                double* out, uint32_t* flags_dev, void* ws, size_t ws_bytes,
+                                void* stream)
+{
+    return tesseroid_dev_impl(longitude, latitude, radius, n_obs, tesseroids, density, n_tesseroids,
+                              field, radial_adaptive_discretization, false, out, flags_dev, ws,
+                              ws_bytes, sm_count_current(), (cudaStream_t)stream);
 }
 
 int hb200_prism_gravity_dev(const double* easting, const double* northing, const double* upward,

@@ -62,6 +62,9 @@ enum hb200_field {
 
 #define HB200_FLAG_SINGULAR 1u /* an observer sits on a singular point of a prism */
 #define HB200_FLAG_ZERO_DIV 2u /* observer coincides with a point source */
+#define HB200_FLAG_TESS_STACK 4u  /* tesseroids: the reference's "Stack Overflow" OverflowError */
+#define HB200_FLAG_TESS_LEAVES 8u /* tesseroids: "Exceeded maximum discretizations" */
+#define HB200_FLAG_TESS_INSIDE 16u /* tesseroids: a computation point lies inside a tesseroid */
 
 #define HB200_SHARD_AUTO 0
 #define HB200_SHARD_OBSERVERS 1
@@ -153,6 +156,26 @@ int hb200_dipole_magnetic(const double* easting, const double* northing, const d
                           const double* moment_u, int64_t n_src, uint32_t component_mask,
                           int shard_mode, double* out, uint32_t* flags);
 
+/* replaces jit_tesseroid_gravity, _forward/tesseroid_gravity.py:236-339 (constant densities):
+ * adaptive discretisation (_tesseroid_utils.py:136-217, STACK_SIZE 100, MAX_DISCRETIZATIONS
+ * 100000, distance-size ratio 1 for the potential and 2.5 for g_z) + 2x2x2 Gauss-Legendre
+ * point masses (:19-107). longitude, latitude in degrees, radius in metres; tesseroids is
+ * (n_tesseroids, 6) row-major [w, e, s, n, bottom, top]; field is HB200_POTENTIAL (J/kg) or
+ * HB200_G_Z (downward, mGal, tesseroid_gravity.py:222-225). *flags gets HB200_FLAG_TESS_*
+ * where the reference raises OverflowError and HB200_FLAG_ZERO_DIV where its jitted loop raises
+ * ZeroDivisionError (a tesseroid dimension or a node distance of exactly zero). */
+int hb200_tesseroid_gravity(const double* longitude, const double* latitude, const double* radius,
+                            int64_t n_obs, const double* tesseroids, const double* density,
+                            int64_t n_tesseroids, int field, int radial_adaptive_discretization,
+                            int shard_mode, double* out, uint32_t* flags);
+
+/* replaces _check_points_outside_tesseroids, _forward/_tesseroid_utils.py:431-454, as one
+ * pass: *flags gets HB200_FLAG_TESS_INSIDE if any computation point lies strictly inside any
+ * tesseroid (the host then lists the pairs for the reference's error message). */
+int hb200_tesseroid_inside_scan(const double* longitude, const double* latitude,
+                                const double* radius, int64_t n_obs, const double* tesseroids,
+                                int64_t n_tesseroids, uint32_t* flags);
+
 /* replaces jacobian, _equivalent_sources/utils.py:54-74: jac[i*n_src+j] = 1/dist */
 int hb200_eqs_jacobian(const double* easting, const double* northing, const double* upward,
                        int64_t n_obs, const double* src_easting, const double* src_northing,
@@ -202,6 +225,12 @@ int hb200_eqs_fit_gb(const double* easting, const double* northing, const double
 /* ---- device-buffer entry points (current device, async on stream) -------- */
 size_t hb200_prism_ws_bytes(int64_t n_obs, int64_t n_sources, int n_fields);
 size_t hb200_point_ws_bytes(int64_t n_obs, int64_t n_sources);
+size_t hb200_tesseroid_ws_bytes(int64_t n_obs, int64_t n_tesseroids);
+int hb200_tesseroid_gravity_dev(const double* longitude, const double* latitude, const double* radius,
+                                int64_t n_obs, const double* tesseroids, const double* density,
+                                int64_t n_tesseroids, int field, int radial_adaptive_discretization,
+                                double* out, uint32_t* flags_dev, void* ws, size_t ws_bytes,
+                                void* stream);
 int hb200_prism_gravity_dev(const double* easting, const double* northing, const double* upward,
                             int64_t n_obs, const double* prisms, const double* density,
                             int64_t n_prisms, uint32_t field_mask, double* out,

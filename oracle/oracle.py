@@ -45,9 +45,8 @@ def lib():
     global _LIB
     if _LIB is None:
         path = os.path.join(_HERE, "liboracle.so")
-        if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(
-            os.path.join(_HERE, "choclo_port.c")
-        ):
+        sources = [os.path.join(_HERE, f) for f in ("choclo_port.c", "tesseroid_port.c")]
+        if not os.path.exists(path) or os.path.getmtime(path) < max(map(os.path.getmtime, sources)):
             build()
         L = ctypes.CDLL(path)
         L.hbo_safe_atan2.restype = ctypes.c_double
@@ -103,6 +102,19 @@ def lib():
         L.hbo_eqs_predict_spherical_loop.argtypes = [
             _i64, _dp, _dp, _dp, _i64, _dp, _dp, _dp, _dp, _dp, _dp, ctypes.c_int,
         ]  # fmt: skip
+        L.hbo_tesseroid_loop.restype = ctypes.c_int
+        L.hbo_tesseroid_loop.argtypes = [
+            ctypes.c_int, _i64, _dp, _dp, _dp, _i64, _dp, _dp, ctypes.c_double, ctypes.c_int, _dp,
+            ctypes.POINTER(ctypes.c_int64), ctypes.c_int,
+        ]  # fmt: skip
+        L.hbo_adaptive_discretization.restype = ctypes.c_int64
+        L.hbo_adaptive_discretization.argtypes = [
+            _dp, _dp, ctypes.c_double, _dp, ctypes.c_int, _dp, _i64, ctypes.c_int,
+        ]  # fmt: skip
+        L.hbo_tesseroid_dimensions.restype = None
+        L.hbo_tesseroid_dimensions.argtypes = [_dp, _dp, _dp, _dp]
+        L.hbo_distance_tesseroid_point.restype = ctypes.c_double
+        L.hbo_distance_tesseroid_point.argtypes = [_dp, _dp]
         _LIB = L
     return _LIB
 
@@ -320,3 +332,78 @@ def eqs_predict_spherical(coordinates, points, coefs, nthreads=0):
     if zd:
         raise ZeroDivisionError("division by zero")
     return out.reshape(cast.shape)
+
+
+# ----------------------------------------------------------------- tesseroids
+TESSEROID_RATII = {"potential": 1.0, "g_z": 2.5}  # tesseroid_gravity.py:33
+
+
+def longitude_continuity(tesseroids):
+    """_tesseroid_utils.py:457-486: move west > east tesseroids to [-180, 180)."""
+    tesseroids = np.array(tesseroids, dtype=np.float64)
+    west, east = tesseroids[:, 0], tesseroids[:, 1]
+    change = west > east
+    east[change] = ((east[change] + 180) % 360) - 180
+    west[change] = ((west[change] + 180) % 360) - 180
+    return tesseroids
+
+
+def discard_null_tesseroids(tesseroids, density):
+    """_tesseroid_utils.py:489-538."""
+    west, east, south, north, bottom, top = (tesseroids[:, i] for i in range(6))
+    null = (west == east) | (south == north) | (bottom == top)
+    null[density == 0] = True
+    return tesseroids[~null], density[~null]
+
+
+def adaptive_discretization(coordinates, tesseroid, distance_size_ratio, radial=False,
+                            stack_size=100, max_small=100000):
+    """The leaves of ``_adaptive_discretization`` (_tesseroid_utils.py:136-217) as an array;
+    raises OverflowError where the reference does."""
+    coordinates = _f64(np.asarray(coordinates, dtype=float).ravel())
+    tesseroid = _f64(np.asarray(tesseroid, dtype=float).ravel())
+    stack = np.empty((stack_size, 6))
+    small = np.empty((max_small, 6))
+    n = lib().hbo_adaptive_discretization(_p(coordinates), _p(tesseroid), distance_size_ratio,
+                                          _p(stack), stack_size, _p(small), max_small, int(radial))
+    if n == -1:
+        raise OverflowError("Stack Overflow. Try to increase the stack size.")
+    if n == -2:
+        raise OverflowError("Exceeded maximum discretizations. Please increase the MAX_DISCRETIZATIONS.")
+    if n == -4:
+        raise ZeroDivisionError("division by zero")
+    return small[:n].copy()
+
+
+def tesseroid_gravity(coordinates, tesseroids, density, field, radial_adaptive_discretization=False,
+                      nthreads=0, return_counts=False):
+    """Restatement of ``tesseroid_gravity`` (tesseroid_gravity.py:36-224) for constant densities
+    and valid models (the input checks are restated in the product and tested against the
+    reference's expectations directly)."""
+    if field not in TESSEROID_RATII:
+        raise ValueError(f"Gravitational field {field} not recognized")
+    cast, (lon, lat, rad) = _coords(coordinates)
+    tesseroids = np.atleast_2d(np.asarray(tesseroids, dtype=np.float64))
+    if (tesseroids[:, 0] > tesseroids[:, 1]).any():
+        tesseroids = longitude_continuity(tesseroids)
+    density = np.atleast_1d(np.asarray(density, dtype=np.float64)).ravel()
+    tesseroids, density = discard_null_tesseroids(tesseroids, density)
+    tesseroids, density = _f64(tesseroids), _f64(density)
+    out = np.zeros(lon.size, dtype=np.float64)
+    counts = np.zeros((lon.size, tesseroids.shape[0]), dtype=np.int64) if return_counts else None
+    status = lib().hbo_tesseroid_loop(
+        FIELD_IDS[field], lon.size, _p(lon), _p(lat), _p(rad), tesseroids.shape[0], _p(tesseroids),
+        _p(density), TESSEROID_RATII[field], int(bool(radial_adaptive_discretization)), _p(out),
+        counts.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)) if return_counts else None, nthreads,
+    )  # fmt: skip
+    if status & 1:
+        raise OverflowError("Stack Overflow. Try to increase the stack size.")
+    if status & 2:
+        raise OverflowError("Exceeded maximum discretizations. Please increase the MAX_DISCRETIZATIONS.")
+    if status & 4:
+        raise ZeroDivisionError("division by zero")  # numba's error model for float division
+    if field == "g_z":
+        out *= -1
+        out *= 1e5
+    out = out.reshape(cast.shape)
+    return (out, counts) if return_counts else out

@@ -21,6 +21,9 @@ Modules loaded (reference file):
   harmonica._forward.point            src/harmonica/_forward/point.py
   harmonica._equivalent_sources.utils src/harmonica/_equivalent_sources/utils.py
   harmonica._forward.dipole           src/harmonica/_forward/dipole.py
+  harmonica._forward._tesseroid_utils src/harmonica/_forward/_tesseroid_utils.py
+  harmonica._forward.tesseroid_gravity src/harmonica/_forward/tesseroid_gravity.py
+      (which also pulls in _tesseroid_variable_density.py)
 """
 
 import importlib
@@ -90,6 +93,8 @@ def load():
     _loaded["point"] = importlib.import_module("harmonica._forward.point")
     _loaded["eqs_utils"] = importlib.import_module("harmonica._equivalent_sources.utils")
     _loaded["dipole"] = importlib.import_module("harmonica._forward.dipole")
+    _loaded["tesseroid_utils"] = importlib.import_module("harmonica._forward._tesseroid_utils")
+    _loaded["tesseroid"] = importlib.import_module("harmonica._forward.tesseroid_gravity")
     return types.SimpleNamespace(**_loaded)
 
 

@@ -8,6 +8,7 @@
 
 #include "../../harmonica_b200/csrc/hb200_math.cuh"
 #include "../../harmonica_b200/csrc/hb200_fast.cuh"
+#include "../../harmonica_b200/csrc/hb200_tess.cuh"
 
 using namespace hb;
 
@@ -79,3 +80,47 @@ void hbt_prism_loop(int fs, int variant, int64_t n_obs, const double* oe, const 
     if (flags) *flags = f;
 }
 }
+
+extern "C" {
+
+// host build of the tesseroid pair function (hb200_tess.cuh), summed like the kernel does:
+// out[i] = sum_j pair(i, j); counts (may be null): leaves per pair, n_obs x n_tess
+void hbt_tesseroid_loop(int field, int64_t n_obs, const double* lon, const double* lat,
+                        const double* rad, int64_t n_tess, const double* tesseroids,
+                        const double* density, int radial, double* out, int64_t* counts,
+                        unsigned* flags)
+{
+    double stack[kTessStack * 6];
+    unsigned f = 0;
+    const double ratio = field == F_POT ? 1.0 : 2.5;
+    for (int64_t i = 0; i < n_obs; i++) {
+        TessObs o;
+        tess_make_obs(o, lon[i], lat[i], rad[i]);
+        double acc = 0.0;
+        for (int64_t j = 0; j < n_tess; j++) {
+            int leaves;
+            if (field == F_POT)
+                leaves = tess_pair<F_POT>(o, tesseroids + 6 * j, density[j], ratio, radial != 0, stack, acc, f);
+            else
+                leaves = tess_pair<F_U>(o, tesseroids + 6 * j, density[j], ratio, radial != 0, stack, acc, f);
+            if (counts) counts[i * n_tess + j] = leaves;
+        }
+        out[i] = acc;
+    }
+    if (flags) *flags = f;
+}
+
+// test/test_tesseroid.py:317-336: tiny stack / tiny leaf budget provoke the overflow flags
+unsigned hbt_tesseroid_overflow(int which, const double* point, const double* tesseroid, double ratio)
+{
+    double stack[kTessStack * 6];
+    TessObs o;
+    tess_make_obs(o, point[0], point[1], point[2]);
+    double acc = 0.0;
+    unsigned f = 0;
+    if (which == 0) tess_pair<F_POT, 2, kTessMaxLeaves>(o, tesseroid, 1.0, ratio, false, stack, acc, f);
+    else tess_pair<F_POT, kTessStack, 2>(o, tesseroid, 1.0, ratio, false, stack, acc, f);
+    return f;
+}
+
+}  // extern "C"

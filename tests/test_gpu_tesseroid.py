@@ -1,0 +1,118 @@
+"""
+GPU parity tests of ``tesseroid_gravity``: public API -> ctypes ->
+``hb200_tesseroid_gravity`` / ``hb200_tesseroid_inside_scan`` -> kernels, against the golden
+fixtures written by the reference's unmodified ``tesseroid_gravity`` and against the oracle.
+Tolerance: max|got - want| <= 1e-9 * max|want| (the CUDA build contracts FMAs and uses CUDA's
+sin / cos / acos; the host build of the same source is bit-identical, tests/test_tesseroid_host.py).
+"""
+
+import re
+
+import numpy as np
+import numpy.testing as npt
+import pytest
+
+import oracle as O
+from _common import TOL, max_rel
+from test_tesseroid_host import MEAN_RADIUS, MODES, _cases, _key, _shell, _shell_analytical
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("field,radial", MODES)
+@pytest.mark.parametrize("name", ["random", "doctest", "four", "wrapped"])
+def test_golden_tesseroid_gravity(hb, name, field, radial):
+    g, cases = _cases()
+    coords, tesseroids, density = cases[name]
+    want = g[_key(name, field, radial)]
+    if want.dtype.kind == "U":  # the reference's jitted loop raises (division by zero)
+        with pytest.raises(ZeroDivisionError):
+            hb.tesseroid_gravity(coords, tesseroids, density, field, radial_adaptive_discretization=radial)
+        return
+    got = hb.tesseroid_gravity(coords, tesseroids, density, field, radial_adaptive_discretization=radial)
+    assert np.shape(got) == want.shape
+    assert max_rel(got, want) <= TOL
+
+
+@pytest.mark.parametrize("field,radial", MODES)
+def test_tesseroid_gravity_vs_oracle(hb, field, radial):
+    rng = np.random.default_rng(91)
+    R = MEAN_RADIUS
+    n_tess, n_obs = 700, 900
+    w, s = rng.uniform(-170, 160, n_tess), rng.uniform(-85, 75, n_tess)
+    tesseroids = np.stack([w, w + rng.uniform(0.1, 10, n_tess), s, s + rng.uniform(0.1, 10, n_tess),
+                           R - rng.uniform(1e3, 1e5, n_tess), R - rng.uniform(0, 500, n_tess)], 1)  # fmt: skip
+    density = rng.uniform(-1000, 3000, n_tess)
+    density[::50] = 0.0  # null tesseroids are discarded on the host
+    coords = (rng.uniform(-180, 180, n_obs), rng.uniform(-90, 90, n_obs),
+              R + rng.uniform(0, 10.0 ** rng.uniform(1, 6, n_obs)))  # fmt: skip
+    want = O.tesseroid_gravity(coords, tesseroids, density, field, radial)
+    got = hb.tesseroid_gravity(coords, tesseroids, density, field, radial_adaptive_discretization=radial)
+    assert max_rel(got, want) <= TOL
+    # few observers, many tesseroids: the source list is split over grid.y and reduced
+    few = tuple(c[:7] for c in coords)
+    got = hb.tesseroid_gravity(few, tesseroids, density, field, radial_adaptive_discretization=radial)
+    assert max_rel(got, np.asarray(want)[:7]) <= TOL
+    # source-sharded combination (one device: same answer)
+    got = hb.tesseroid_gravity(few, tesseroids, density, field, radial_adaptive_discretization=radial,
+                               shard="sources")  # fmt: skip
+    assert max_rel(got, np.asarray(want)[:7]) <= TOL
+
+
+@pytest.mark.parametrize("field", ["potential", "g_z"])
+def test_spherical_shell(hb, field):
+    """test/test_tesseroid.py:683-770: the closed form of a homogeneous shell, 0.1 %"""
+    lon, lat = np.meshgrid(np.arange(0, 351, 10.0), np.arange(-90, 91, 10.0))
+    coords = (lon, lat, np.full_like(lon, MEAN_RADIUS))
+    for thickness in (10, 1e3, 1e5):
+        tesseroids = _shell((12, 6), thickness)
+        want = _shell_analytical(MEAN_RADIUS, MEAN_RADIUS - thickness, 1000, MEAN_RADIUS)[field]
+        got = hb.tesseroid_gravity(coords, tesseroids, 1000 * np.ones((12, 6)), field)
+        assert got.shape == lon.shape
+        npt.assert_allclose(got, want, rtol=1e-3)
+        radius = MEAN_RADIUS + 1e3
+        tesseroids = _shell((6, 6), thickness)
+        want = _shell_analytical(MEAN_RADIUS, MEAN_RADIUS - thickness, 1000, radius)[field]
+        got = hb.tesseroid_gravity([0, 0, radius], tesseroids, 1000 * np.ones(36), field,
+                                   radial_adaptive_discretization=True)  # fmt: skip
+        npt.assert_allclose(got, want, rtol=1e-3)
+
+
+def test_errors_shapes_and_dtypes(hb):
+    R = MEAN_RADIUS
+    tess = [-10.0, 10.0, -10.0, 10.0, R - 1e3, R]
+    # test/test_tesseroid.py:112-131: density size
+    with pytest.raises(ValueError, match=re.escape("Number of elements in density (3) mismatch")):
+        hb.tesseroid_gravity([0, 0, R + 100], [tess, tess], [1.0, 2.0, 3.0], "potential")
+    # :247-314: points inside tesseroids (device scan), phased longitudes included
+    msg = re.escape("Found computation point(s) inside tesseroid(s)")
+    for point in ([0, 0, R - 500], [360, 0, R - 500]):
+        with pytest.raises(ValueError, match=msg):
+            hb.tesseroid_gravity(point, tess, 1000.0, "g_z")
+    with pytest.raises(ValueError, match=msg) as err:
+        hb.tesseroid_gravity(([0, 80, 25], [0, 82, 25], [150, 4000, 450]),
+                             [[-10, 10, -10, 10, 100, 200], [20, 30, 20, 30, 400, 500],
+                              [-50, -40, -30, -20, 100, 500]], [1.0, 1.0, 1.0], "potential")  # fmt: skip
+    assert "'(0.0, 0.0, 150.0)' inside tesseroid '(-10.0, 10.0, -10.0, 10.0, 100.0, 200.0)'" in str(err.value)
+    assert "'(25.0, 25.0, 450.0)' inside tesseroid '(20.0, 30.0, 20.0, 30.0, 400.0, 500.0)'" in str(err.value)
+    # points on the faces are outside (:251-268)
+    on_faces = np.array([[0, 0, 250], [20, 0, 150], [0, 0, 200], [0, 0, 100], [-10, 0, 150], [0, 10, 150]], dtype=float).T
+    hb._tesseroid.check_points_outside_tesseroids(tuple(on_faces), np.atleast_2d([-10.0, 10, -10, 10, 100, 200]))
+    # :223-245: disable_checks lets an inverted tesseroid through; its potential is the opposite
+    valid = hb.tesseroid_gravity([0.0, 0.0, 10.0], [0.0, 10.0, 0.0, 10.0, 10.0, 20.0], 100.0, "potential")
+    inverted = hb.tesseroid_gravity([0.0, 0.0, 10.0], [0.0, 10.0, 0.0, 10.0, 20.0, 10.0], 100.0,
+                                    "potential", disable_checks=True)  # fmt: skip
+    npt.assert_allclose(inverted, -valid)
+    # shapes, dtype, scalars, empty model
+    lon, lat = np.meshgrid(np.linspace(-5, 5, 4), np.linspace(-3, 3, 3))
+    out = hb.tesseroid_gravity((lon, lat, np.full_like(lon, R + 1e3)), tess, 2670.0, "g_z", dtype="float32")
+    assert out.shape == (3, 4) and out.dtype == np.float32
+    want = O.tesseroid_gravity((lon, lat, np.full_like(lon, R + 1e3)), tess, 2670.0, "g_z")
+    npt.assert_allclose(out, want, rtol=1e-6)
+    assert np.shape(hb.tesseroid_gravity([0, 0, R + 10], tess, 2670.0, "potential")) == ()
+    zero = hb.tesseroid_gravity([0, 0, R + 10], [tess], [0.0], "g_z")  # all tesseroids null
+    assert float(zero) == 0.0
+    lib = hb._lib.load()
+    before = lib.hb200_launch_count()
+    hb.tesseroid_gravity([0, 0, R + 10], tess, 2670.0, "potential")
+    assert lib.hb200_launch_count() - before >= 3  # inside scan (pack + scan), pack + kernel

@@ -1,0 +1,320 @@
+"""
+Tesseroid forward model, CPU side (no GPU):
+
+* the oracle (oracle/tesseroid_port.c) against the golden fixtures written by the reference's
+  UNMODIFIED ``tesseroid_gravity`` (real numba, oracle/make_golden_tesseroid.py): bit-identical;
+* oracle pins from the reference's own tests: spherical-shell closed form
+  (test/test_tesseroid.py:664-770), discretisation monotonicity (:585-661), overflow errors
+  (:317-336), distance / dimension closed forms (:377-423);
+* the HOST BUILD of the product's pair function (csrc/hb200_tess.cuh, the statements the CUDA
+  kernel executes) against the oracle: bit-identical values and leaf counts;
+* the product's host-side checks (``harmonica_b200/_tesseroid.py``) against the reference's
+  expectations (test/test_tesseroid.py:101-220, 339-462).
+"""
+
+import ctypes
+import re
+
+import numpy as np
+import numpy.testing as npt
+import pytest
+
+import oracle as O
+from _common import golden, harness
+
+MEAN_RADIUS = 6371008.771415059  # boule.WGS84.mean_radius
+G = 6.6743e-11
+MODES = [("potential", False), ("potential", True), ("g_z", False), ("g_z", True)]
+
+
+def _key(name, field, radial):
+    return f"{name}_{field}_{'3d' if radial else '2d'}"
+
+
+def _cases():
+    g = golden("tesseroid")
+    R = MEAN_RADIUS
+    return g, {
+        "random": (tuple(g["random_coords"]), g["random_tesseroids"], g["random_density"]),
+        "doctest": ([0, 0, R], [-1.0, 1.0, -1.0, 1.0, R - 1000, R], 2670.0),
+        "four": ([[-5.0, 0.0, 1.0], [-5.0, 0.0, 5.0], [R + 100] * 3],
+                 [[-10.0, 0, -10.0, 0, R - 1e3, R], [-10.0, 0, 0, 10.0, R - 1e3, R],
+                  [0, 10.0, -10.0, 0, R - 1e3, R], [0, 10.0, 0, 10.0, R - 1e3, R]],
+                 1000.0 * np.ones(4)),
+        "wrapped": ([0, 0, R + 1e3], [350, 10, -10, 10, R - 1e4, R], 1e3),
+    }  # fmt: skip
+
+
+def harness_tesseroid(coordinates, tesseroids, density, field, radial):
+    """Host build of hb200_tess.cuh summed like the kernel (SI, before sign / unit)."""
+    H = harness()
+    dp = ctypes.POINTER(ctypes.c_double)
+    lon, lat, rad = (np.ascontiguousarray(np.atleast_1d(c), dtype=np.float64).ravel() for c in coordinates)
+    tesseroids = np.ascontiguousarray(np.atleast_2d(tesseroids), dtype=np.float64)
+    density = np.ascontiguousarray(np.atleast_1d(density), dtype=np.float64)
+    out = np.zeros(lon.size)
+    counts = np.zeros((lon.size, tesseroids.shape[0]), dtype=np.int64)
+    flags = ctypes.c_uint(0)
+    H.hbt_tesseroid_loop(
+        {"potential": 0, "g_z": 3}[field], ctypes.c_int64(lon.size), lon.ctypes.data_as(dp),
+        lat.ctypes.data_as(dp), rad.ctypes.data_as(dp), ctypes.c_int64(tesseroids.shape[0]),
+        tesseroids.ctypes.data_as(dp), density.ctypes.data_as(dp), int(radial),
+        out.ctypes.data_as(dp), counts.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+        ctypes.byref(flags),
+    )  # fmt: skip
+    return out, counts, flags.value
+
+
+# ------------------------------------------------------------------ oracle vs the reference
+@pytest.mark.parametrize("field,radial", MODES)
+@pytest.mark.parametrize("name", ["random", "doctest", "four", "wrapped"])
+def test_oracle_is_bit_identical_to_the_reference(name, field, radial):
+    g, cases = _cases()
+    coords, tesseroids, density = cases[name]
+    want = g[_key(name, field, radial)]
+    if want.dtype.kind == "U":  # the reference raised (numba's division by zero)
+        assert str(want) == "ZeroDivisionError"
+        with pytest.raises(ZeroDivisionError):
+            O.tesseroid_gravity(coords, tesseroids, density, field, radial)
+        return
+    got = O.tesseroid_gravity(coords, tesseroids, density, field, radial)
+    assert np.array_equal(np.asarray(got).reshape(want.shape), want)
+
+
+def test_oracle_leaves_match_the_reference():
+    g = golden("tesseroid")
+    tess = [-10.0, 10.0, -10.0, 10.0, 1.0, 10.0]
+    for tag, radial in (("leaves_2d", False), ("leaves_3d", True)):
+        setup = g[tag + "_setup"]
+        got = O.adaptive_discretization(setup[:3], tess, setup[3], radial)
+        assert np.array_equal(got, g[tag])
+    # test/test_tesseroid.py:642-661: 2-D discretisation never splits the radial direction
+    assert np.all(g["leaves_2d"][:, 4] == 1.0) and np.all(g["leaves_2d"][:, 5] == 10.0)
+
+
+def test_doctest_value():
+    """tesseroid_gravity.py:170-183: the value the reference's doctest computes."""
+    g = golden("tesseroid")
+    R = MEAN_RADIUS
+    got = O.tesseroid_gravity([0, 0, R], [-1.0, 1.0, -1.0, 1.0, R - 1000, R], 2670.0, "g_z")
+    assert float(got) == float(g["doctest_g_z_2d"])
+    npt.assert_allclose(got, 112.567, atol=1e-3)  # within 0.6 % of the Bouguer slab 2 pi G rho h
+
+
+# ------------------------------------------------------------------ oracle pins
+def _shell(shape, thickness):
+    longitude = np.linspace(0, 360, shape[0] + 1)
+    latitude = np.linspace(-90, 90, shape[1] + 1)
+    top = MEAN_RADIUS
+    return np.array([[w, e, s, n, top - thickness, top]
+                     for w, e in zip(longitude[:-1], longitude[1:])
+                     for s, n in zip(latitude[:-1], latitude[1:])])  # fmt: skip
+
+
+def _shell_analytical(top, bottom, density, radius):
+    potential = 4 / 3 * np.pi * G * density * (top**3 - bottom**3) / radius
+    return {"potential": potential, "g_z": 1e5 * potential / radius}
+
+
+@pytest.mark.parametrize("field", ["potential", "g_z"])
+@pytest.mark.parametrize("thickness", [10, 1e3, 1e5])
+def test_spherical_shell_three_dim_adaptive_discret(field, thickness):
+    """test/test_tesseroid.py:729-770"""
+    radius = MEAN_RADIUS + 1e3
+    tesseroids = _shell((6, 6), thickness)
+    want = _shell_analytical(MEAN_RADIUS, MEAN_RADIUS - thickness, 1000, radius)[field]
+    got = O.tesseroid_gravity([0, 0, radius], tesseroids, 1000 * np.ones(36), field, True)
+    npt.assert_allclose(got, want, rtol=1e-3)
+
+
+@pytest.mark.parametrize("field", ["potential", "g_z"])
+def test_spherical_shell_two_dim_adaptive_discret(field):
+    """test/test_tesseroid.py:683-726 on a thinned grid of points ON the shell"""
+    lon, lat = np.meshgrid(np.arange(0, 351, 70.0), np.arange(-90, 91, 45.0))
+    coords = (lon.ravel(), lat.ravel(), np.full(lon.size, MEAN_RADIUS))
+    for thickness in (10, 1e3, 1e5):
+        tesseroids = _shell((12, 6), thickness)
+        want = _shell_analytical(MEAN_RADIUS, MEAN_RADIUS - thickness, 1000, MEAN_RADIUS)[field]
+        got = O.tesseroid_gravity(coords, tesseroids, 1000 * np.ones(72), field)
+        npt.assert_allclose(got, want, rtol=1e-3)
+
+
+@pytest.mark.parametrize("radial", [True, False])
+def test_adaptive_discretization_monotonic(radial):
+    """test/test_tesseroid.py:585-639"""
+    tess = [-10.0, 10.0, -10.0, 10.0, 1.0, 10.0]
+    radii = [10.1 if radial else 10.0, 10.5, 12.0, 13.0, 15.0, 20.0, 30.0]
+    counts = [O.adaptive_discretization([0.0, 0.0, r], tess, 10, radial).shape[0] for r in radii]
+    assert all(a >= b for a, b in zip(counts, counts[1:]))
+    counts = [O.adaptive_discretization([0.0, 0.0, 10.2], tess, ratio, radial).shape[0]
+              for ratio in np.linspace(1, 10, 10)]  # fmt: skip
+    assert all(a <= b for a, b in zip(counts, counts[1:]))
+
+
+def test_overflow_errors():
+    """test/test_tesseroid.py:317-336"""
+    tess, point = [-10.0, 10.0, -10.0, 10.0, 0.5, 1.0], [0.0, 0.0, 1.0]
+    with pytest.raises(OverflowError, match="Stack Overflow"):
+        O.adaptive_discretization(point, tess, 10, stack_size=2)
+    with pytest.raises(OverflowError, match="Exceeded maximum discretizations"):
+        O.adaptive_discretization(point, tess, 10, max_small=2)
+
+
+def test_distance_and_dimensions_closed_forms():
+    """test/test_tesseroid.py:377-423"""
+    L = O.lib()
+    dp = ctypes.POINTER(ctypes.c_double)
+
+    def distance(point, tess):
+        p, t = np.array(point, dtype=float), np.array(tess, dtype=float)
+        return L.hbo_distance_tesseroid_point(p.ctypes.data_as(dp), t.ctypes.data_as(dp))
+
+    R = MEAN_RADIUS
+    tess = [-1.0, 1.0, -1.0, 1.0, R - 0.65, R + 0.65]
+    npt.assert_allclose(distance([0.0, 0.0, R], tess), 0.0)
+    npt.assert_allclose(distance([0.0, 0.0, R + 1.0], tess), 1.0)
+    npt.assert_allclose(distance([3.0, 0.0, R], tess), 2 * R * np.sin(0.5 * np.radians(3.0)))
+    npt.assert_allclose(distance([0.0, 3.0, R], tess), 2 * R * np.sin(0.5 * np.radians(3.0)))
+    t = np.array([-1.0, 1.0, -1.0, 1.0, 0.5, 1.5])
+    dims = [ctypes.c_double() for _ in range(3)]
+    L.hbo_tesseroid_dimensions(t.ctypes.data_as(dp), *[ctypes.byref(d) for d in dims])
+    npt.assert_allclose([d.value for d in dims], [1.5 * np.radians(2.0), 1.5 * np.radians(2.0), 1.0])
+
+
+# ------------------------------------------------------------------ product math (host build)
+@pytest.mark.parametrize("field,radial", MODES)
+def test_product_pair_function_is_bit_identical_to_the_oracle(field, radial):
+    g, cases = _cases()
+    for name in ("random", "four", "wrapped"):
+        coords, tesseroids, density = cases[name]
+        tesseroids = np.atleast_2d(np.asarray(tesseroids, dtype=float))
+        if (tesseroids[:, 0] > tesseroids[:, 1]).any():
+            tesseroids = O.longitude_continuity(tesseroids)
+        density = np.atleast_1d(np.asarray(density, dtype=float))
+        want, want_counts = O.tesseroid_gravity(coords, tesseroids, density, field, radial, return_counts=True)
+        got, counts, flags = harness_tesseroid(coords, tesseroids, density, field, radial)
+        if field == "g_z":
+            got *= -1
+            got *= 1e5
+        assert flags == 0
+        assert np.array_equal(counts, want_counts)
+        assert np.array_equal(got, np.asarray(want).ravel())
+
+
+def test_product_pair_function_random_models():
+    rng = np.random.default_rng(77)
+    R = MEAN_RADIUS
+    for trial in range(4):
+        n_tess, n_obs = 30, 40
+        w, s = rng.uniform(-170, 160, n_tess), rng.uniform(-85, 75, n_tess)
+        tesseroids = np.stack([w, w + rng.uniform(0.1, 10, n_tess), s, s + rng.uniform(0.1, 10, n_tess),
+                               R - rng.uniform(1e3, 1e5, n_tess), R - rng.uniform(0, 500, n_tess)], 1)  # fmt: skip
+        density = rng.uniform(-1000, 3000, n_tess)
+        coords = (rng.uniform(-180, 180, n_obs), rng.uniform(-90, 90, n_obs),
+                  R + rng.uniform(0, 10.0 ** rng.uniform(1, 6), n_obs))  # fmt: skip
+        for field, radial in MODES:
+            want, want_counts = O.tesseroid_gravity(coords, tesseroids, density, field, radial, return_counts=True)
+            got, counts, flags = harness_tesseroid(coords, tesseroids, density, field, radial)
+            if field == "g_z":
+                got *= -1
+                got *= 1e5
+            assert flags == 0 and np.array_equal(counts, want_counts) and np.array_equal(got, want)
+
+
+def test_product_pair_function_flags():
+    """where the reference raises, the pair function reports a flag (and terminates)"""
+    R = MEAN_RADIUS
+    # a point on the top-face centre with 3-D discretisation: numba's ZeroDivisionError
+    _, _, flags = harness_tesseroid([0, 0, R], [-1.0, 1.0, -1.0, 1.0, R - 1000, R], 2670.0, "g_z", True)
+    assert flags & 2
+    with pytest.raises(ZeroDivisionError):
+        O.tesseroid_gravity([0, 0, R], [-1.0, 1.0, -1.0, 1.0, R - 1000, R], 2670.0, "g_z", True)
+    # test/test_tesseroid.py:317-336: a stack of 2 / a leaf budget of 2 overflow
+    H = harness()
+    dp = ctypes.POINTER(ctypes.c_double)
+    H.hbt_tesseroid_overflow.restype = ctypes.c_uint
+    H.hbt_tesseroid_overflow.argtypes = [ctypes.c_int, dp, dp, ctypes.c_double]
+    tess, point = np.array([-10.0, 10.0, -10.0, 10.0, 0.5, 1.0]), np.array([0.0, 0.0, 1.0])
+    assert H.hbt_tesseroid_overflow(0, point.ctypes.data_as(dp), tess.ctypes.data_as(dp), 10.0) == 4
+    assert H.hbt_tesseroid_overflow(1, point.ctypes.data_as(dp), tess.ctypes.data_as(dp), 10.0) == 8
+
+
+# ------------------------------------------------------------------ product host checks
+def test_check_tesseroids_valid_and_invalid():
+    """test/test_tesseroid.py:134-220"""
+    from harmonica_b200._tesseroid import _check_tesseroids
+
+    w, e, s, n, bottom, top = -10, 10, -10, 10, 100, 200
+    for tess in ([w, e, s, n, bottom, top], [w, w, s, n, bottom, top], [w, e, s, s, bottom, top],
+                 [w, e, s, n, bottom, bottom], [350, 10, s, n, bottom, top], [-70, -60, s, n, bottom, top],
+                 [-150, 150, s, n, bottom, top], [0, 360, s, n, bottom, top], [-180, 180, s, n, bottom, top]):  # fmt: skip
+        _check_tesseroids(np.atleast_2d(np.array(tess, dtype=float)))
+    bad = [
+        ("The south boundary can't be greater than the north one", [w, e, n, s, bottom, top]),
+        ("The latitudinal boundaries must be inside the [-90, 90] degrees interval", [w, e, s, -100, bottom, top]),
+        ("The latitudinal boundaries must be inside the [-90, 90] degrees interval", [w, e, 100, n, bottom, top]),
+        ("The bottom radius boundary can't be greater than the top one", [w, e, s, n, top, bottom]),
+        ("The bottom and top radii should be positive or zero", [w, e, s, n, bottom, -1]),
+        ("The bottom and top radii should be positive or zero", [w, e, s, n, -1, top]),
+        ("The longitudinal boundaries must be inside the [-180, 360] degrees interval", [-200, e, s, n, bottom, top]),
+        ("The longitudinal boundaries must be inside the [-180, 360] degrees interval", [w, 400, s, n, bottom, top]),
+        ("The west boundary can't be greater than the east one", [30, 0, s, n, bottom, top]),
+        ("The west boundary can't be greater than the east one", [-60, -70, s, n, bottom, top]),
+        ("The west boundary can't be greater than the east one", [300, -150, s, n, bottom, top]),
+        ("The west boundary can't be greater than the east one", [350, 340, s, n, bottom, top]),
+        ("The difference between east and west boundaries cannot be greater than one turn around the globe",
+         [-150, 300, s, n, bottom, top]),
+    ]  # fmt: skip
+    for msg, tess in bad:
+        with pytest.raises(ValueError, match=re.escape(msg)):
+            _check_tesseroids(np.atleast_2d(np.array(tess, dtype=float)))
+
+
+def test_longitude_continuity_and_null_tesseroids():
+    """test/test_tesseroid.py:339-441"""
+    from harmonica_b200._tesseroid import _discard_null_tesseroids, _longitude_continuity
+
+    for tess, want in (([-10, 10], (-10, 10)), ([-70, -60], (-70, -60)), ([350, 10], (-10, 10))):
+        out = _longitude_continuity(np.atleast_2d(np.array(tess + [-10, 10, 1, 2], dtype=float)))
+        assert (out[0, 0], out[0, 1]) == want
+    top, bottom = MEAN_RADIUS, MEAN_RADIUS - 1e3
+    tesseroids = np.array([
+        [-10, -5, -10, -5, bottom, top], [-10, -5, -5, 0, bottom, top], [-10, -10, 0, 5, bottom, top],
+        [-10, -5, 5, 5, bottom, top], [-5, 0, -10, -5, top, top], [-5, 0, -5, 0, bottom, top],
+        [-5, -5, 5, 5, top, top], [-5, 0, 5, 10, bottom, top]])  # fmt: skip
+    densities = np.array([2400, 0, 2500, 2600, 2700, 2800, 2900, 3000])
+    tesseroids, densities = _discard_null_tesseroids(tesseroids, densities)
+    npt.assert_allclose(tesseroids, [[-10, -5, -10, -5, bottom, top], [-5, 0, -5, 0, bottom, top],
+                                     [-5, 0, 5, 10, bottom, top]])  # fmt: skip
+    npt.assert_allclose(densities, [2400, 2800, 3000])
+
+
+def test_points_inside_tesseroids_predicate():
+    """test/test_tesseroid.py:247-314 through the pair predicate the device scan evaluates
+    (host build) and the host-side pair listing"""
+    from harmonica_b200._tesseroid import _conflicting_pairs
+
+    tesseroid = np.atleast_2d(np.array([-10, 10, -10, 10, 100, 200], dtype=float))
+    outside = np.array([[0, 0, 250], [20, 0, 150], [0, 20, 150], [0, 0, 200], [0, 0, 100], [-10, 0, 150],
+                        [10, 0, 150], [0, -10, 150], [0, 10, 150]], dtype=float).T  # fmt: skip
+    assert _conflicting_pairs(tuple(outside), tesseroid) == []
+    for point in ([0, 0, 150], [360, 0, 150]):
+        assert _conflicting_pairs(tuple(np.atleast_2d(np.array(point, dtype=float)).T), tesseroid) == [(0, 0)]
+    phased = np.atleast_2d(np.array([260, 280, -10, 10, 100, 200], dtype=float))
+    assert _conflicting_pairs(tuple(np.atleast_2d(np.array([-90.0, 0, 150])).T), phased) == [(0, 0)]
+    tesseroids = np.array([[-10, 10, -10, 10, 100, 200], [20, 30, 20, 30, 400, 500],
+                           [-50, -40, -30, -20, 100, 500]], dtype=float)  # fmt: skip
+    points = np.array([[0, 0, 150], [80, 82, 4000], [10, 10, 450]], dtype=float).T
+    assert _conflicting_pairs(tuple(points), tesseroids) == [(0, 0)]
+
+
+def test_argument_errors_need_no_device():
+    """test/test_tesseroid.py:101-131"""
+    import harmonica_b200 as hb
+
+    with pytest.raises(ValueError, match="Gravitational field this-field-does-not-exist not recognized"):
+        hb.tesseroid_gravity([0, 0, 0], [-10, 10, -10, 10, 100, 200], 1000, "this-field-does-not-exist")
+    with pytest.raises(NotImplementedError, match="constant densities"):
+        hb.tesseroid_gravity([0, 0, 300], [-10, 10, -10, 10, 100, 200], lambda r: 1000.0, "g_z")
+    with pytest.raises(ValueError, match="The bottom radius boundary can't be greater than the top one"):
+        hb.tesseroid_gravity([0.0, 0.0, 10.0], [0.0, 10.0, 0.0, 10.0, 20.0, 10.0], 100.0, "potential")
