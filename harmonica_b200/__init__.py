@@ -28,6 +28,7 @@ from ._prism_gravity import prism_gravity
 from ._prism_layer import DatasetAccessorPrismLayer, PrismLayer, prism_layer, prism_layer_gravity
 from ._prism_magnetic import prism_magnetic
 from ._tesseroid import tesseroid_gravity
+from ._tesseroid_layer import DatasetAccessorTesseroidLayer, TesseroidLayer, tesseroid_layer
 
 __version__ = "0.1.0"
 
@@ -53,4 +54,7 @@ __all__ = [
     "prism_layer_gravity",
     "prism_magnetic",
     "tesseroid_gravity",
+    "tesseroid_layer",
+    "TesseroidLayer",
+    "DatasetAccessorTesseroidLayer",
 ]

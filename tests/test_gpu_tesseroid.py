@@ -116,3 +116,43 @@ def test_errors_shapes_and_dtypes(hb):
     before = lib.hb200_launch_count()
     hb.tesseroid_gravity([0, 0, R + 10], tess, 2670.0, "potential")
     assert lib.hb200_launch_count() - before >= 3  # inside scan (pack + scan), pack + kernel
+
+
+@pytest.mark.parametrize("field", ["potential", "g_z"])
+def test_tesseroid_layer_gravity(hb, field):
+    """test/test_tesseroid_layer.py:384-532: the layer's gravity equals tesseroid_gravity of its
+    tesseroids; NaN surfaces / densities and thin tesseroids are skipped"""
+    R = MEAN_RADIUS
+    latitude, longitude = np.linspace(-10, 10, 6), np.linspace(-10, 10, 5)
+    surface = R * np.ones((6, 5)) + 1e3
+    density = 2670.0 * np.ones((6, 5))
+    lon, lat = np.meshgrid(np.arange(-10, 11, 7.0), np.arange(-10, 11, 7.0))
+    grid_coords = (lon, lat, np.full_like(lon, R + 11e3))
+    layer = hb.tesseroid_layer((longitude, latitude), surface, R, properties={"density": density})
+    tesseroids = layer.tesseroid_layer._to_tesseroids()
+    want = O.tesseroid_gravity(grid_coords, tesseroids, density.ravel(), field)
+    got = layer.tesseroid_layer.gravity(grid_coords, field=field)
+    assert got.shape == lon.shape and max_rel(got, want) <= TOL
+    # holes in the surface and in the density (with a warning)
+    holes = surface.copy()
+    holes[3, 3] = holes[2, 1] = np.nan
+    keep = np.ones(30, dtype=bool)
+    keep[[3 * 5 + 3, 2 * 5 + 1]] = False
+    layer = hb.tesseroid_layer((longitude, latitude), holes, R, properties={"density": density})
+    want = O.tesseroid_gravity(grid_coords, tesseroids[keep], density.ravel()[keep], field)
+    assert max_rel(layer.tesseroid_layer.gravity(grid_coords, field=field), want) <= TOL
+    rho = density.copy()
+    rho[3, 3] = rho[2, 1] = np.nan
+    layer = hb.tesseroid_layer((longitude, latitude), surface, R, properties={"density": rho})
+    with pytest.warns(UserWarning, match="Found missing values in 'density' property"):
+        got = layer.tesseroid_layer.gravity(grid_coords, field=field)
+    assert max_rel(got, want) <= TOL
+    # thin tesseroids are discarded
+    thin = surface.copy()
+    thin[0, :] = R + 10.0
+    layer = hb.tesseroid_layer((longitude, latitude), thin, R, properties={"density": density})
+    all_t = layer.tesseroid_layer._to_tesseroids()
+    sel = (all_t[:, 5] - all_t[:, 4]) >= 100.0
+    want = O.tesseroid_gravity(grid_coords, all_t[sel], density.ravel()[sel], field)
+    got = layer.tesseroid_layer.gravity(grid_coords, field=field, thickness_threshold=100.0)
+    assert max_rel(got, want) <= TOL

@@ -318,3 +318,64 @@ def test_argument_errors_need_no_device():
         hb.tesseroid_gravity([0, 0, 300], [-10, 10, -10, 10, 100, 200], lambda r: 1000.0, "g_z")
     with pytest.raises(ValueError, match="The bottom radius boundary can't be greater than the top one"):
         hb.tesseroid_gravity([0.0, 0.0, 10.0], [0.0, 10.0, 0.0, 10.0, 20.0, 10.0], 100.0, "potential")
+
+
+# ------------------------------------------------------------------ tesseroid layer (host logic)
+def test_tesseroid_layer_host_logic():
+    """test/test_tesseroid_layer.py:85-133, 165-293, 535-560"""
+    import harmonica_b200 as hb
+    from harmonica_b200._tesseroid_layer import _discard_thin_tesseroids
+
+    R = MEAN_RADIUS
+    latitude = np.linspace(-10, 10, 6)
+    for west, east in [(0, 480), (0, 360), (-180, 180), (0, 360 - 18 / 2)]:
+        longitude = np.linspace(west, east, 21)
+        with pytest.raises(ValueError, match="overlapping tesseroids around the globe"):
+            hb.tesseroid_layer((longitude, latitude), R * np.ones((6, 21)) + 1e3, R * np.ones((6, 21)))
+    for west, east in [(0, 360 - 18), (-180, 180 - 18)]:
+        hb.tesseroid_layer((np.linspace(west, east, 21), latitude), R * np.ones((6, 21)) + 1e3, R)
+    longitude = np.linspace(-10, 10, 5)
+    surface = R * np.ones((6, 5))
+    layer = hb.tesseroid_layer((longitude, latitude), surface, surface - 1e3)
+    acc = layer.tesseroid_layer
+    assert acc.dims == ("latitude", "longitude") and acc.spacing == (4, 5)
+    assert acc.boundaries == (longitude[0] - 2.5, longitude[-1] + 2.5, latitude[0] - 2, latitude[-1] + 2)
+    assert acc.size == 30 and acc.shape == (6, 5)
+    npt.assert_allclose(acc.top, R)
+    npt.assert_allclose(acc.bottom, R - 1e3)
+    # surface below the reference: top and bottom swap
+    acc.update_top_bottom(surface - 2e3, R - 1e3)
+    npt.assert_allclose(acc.top, R - 1e3)
+    npt.assert_allclose(acc.bottom, R - 2e3)
+    with pytest.raises(ValueError, match="Invalid surface array with shape"):
+        hb.tesseroid_layer((longitude, latitude), np.ones((7, 5)), R)
+    with pytest.raises(ValueError, match="Invalid reference array with shape"):
+        hb.tesseroid_layer((longitude, latitude), surface, np.ones((6, 4)))
+    with pytest.raises(ValueError, match="Passed longitude coordinates are not evenly spaced"):
+        hb.tesseroid_layer((np.array([-10.0, -5, 0, 7, 10]), latitude), surface, R)
+    with pytest.raises(ValueError, match="Passed latitude coordinates are not evenly spaced"):
+        hb.tesseroid_layer((longitude, np.array([-10.0, -5, 0, 7, 10, 20])), surface, R)
+    small = hb.tesseroid_layer((np.linspace(-2, 2, 2), np.linspace(-1, 1, 2)), R * np.ones((2, 2)),
+                               (R - 1e3) * np.ones((2, 2)))  # fmt: skip
+    expected = [[-4.0, 0.0, -2.0, 0.0, R - 1e3, R], [0.0, 4.0, -2.0, 0.0, R - 1e3, R],
+                [-4.0, 0.0, 0.0, 2.0, R - 1e3, R], [0.0, 4.0, 0.0, 2.0, R - 1e3, R]]  # fmt: skip
+    npt.assert_allclose(expected, small.tesseroid_layer._to_tesseroids())
+    for i in range(2):
+        for j in range(2):
+            npt.assert_allclose(small.tesseroid_layer.get_tesseroid((i, j)), expected[2 * i + j])
+    boundaries = np.array([[-10.0, 10.0, -10.0, 10.0, 0.0, 55.1], [10.0, 30.0, -10.0, 10.0, 0.0, 55.01],
+                           [-10.0, 10.0, 10.0, 30.0, 0.0, 35.0], [10.0, 30.0, 10.0, 30.0, 0.0, 84.0]])  # fmt: skip
+    thick, rho = _discard_thin_tesseroids(boundaries, np.array([2306, 2122, 2190, 2069]), 55.05)
+    npt.assert_allclose(thick, boundaries[[0, 3]])
+    npt.assert_allclose(rho, [2306, 2069])
+    # NaN masks (:296-383)
+    holes = R * np.ones((6, 5)) + 1e3
+    holes[3, 3] = holes[2, 1] = np.nan
+    density = 2670.0 * np.ones((6, 5))
+    density[0, 0] = np.nan
+    layer = hb.tesseroid_layer((longitude, latitude), holes, R, properties={"density": density})
+    mask = layer.tesseroid_layer._get_nonans_mask()
+    assert mask.sum() == 28 and not mask[3, 3] and not mask[2, 1]
+    with pytest.warns(UserWarning, match="Found missing values in 'density' property"):
+        mask = layer.tesseroid_layer._get_nonans_mask(property_name="density")
+    assert mask.sum() == 27 and not mask[0, 0]
