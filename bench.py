@@ -41,7 +41,12 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 # FP64-pipe instruction equivalents per pair of the REFERENCE algorithm
-I_PAIR = {"layer_gz": 1068, "c1_gz": 1068, "tensor": 2020, "mag_b": 2100, "eqs": 26.5}
+I_PAIR = {"layer_gz": 1068, "c1_gz": 1068, "tensor": 2020, "mag_b": 2100, "eqs": 26.5,
+          # tesseroids: one stack pop (7 sin/cos, 2 acos, the distance to the
+          # centre, 3 divisions) ~ 390 and one 2x2x2 quadrature leaf ~ 456 FP64 instructions of the
+          # reference algorithm; an unsplit pair is one pop + one leaf, near pairs cost more (the
+          # measured leaves per pair of the CPU sample are reported next to the rate)
+          "tess_gz": 390 + 456}
 NOMINAL_FP64_FLOPS = 148 * 64 * 2 * 1.965e9  # 37.2 TFLOP/s
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE prism_kernel launch of the default workload
 # at full size (profiles/r1_traffic_layer_gz_full_launch.csv; 22.6 MB read + 1.5 MB written;
@@ -101,6 +106,23 @@ def make_workload(name, n_obs, n_src, rank):
         return dict(kind="eqs", coords=coords, points=(pe, pn, pu), coefs=coefs, n_src=n_src,
                     mask=1, nf=1,
                     desc=f"EquivalentSources.predict (sum coef/r), {n_src} sources x {n_obs} observers")
+    if name == "tess_gz":
+        # a 2 x 2 degree global layer of tesseroids (topography-like tops) seen from 10 km above
+        # the reference sphere: most pairs are far (one leaf), the ones below each observer split
+        n_obs = n_obs or 65_536
+        rng = np.random.default_rng(6 + 100 * rank)
+        R = 6371008.771415059
+        lon_c, lat_c = np.meshgrid(np.arange(-179.0, 180.0, 2.0), np.arange(-89.0, 90.0, 2.0))
+        top = R + 2e3 * np.sin(np.radians(3 * lon_c)) * np.cos(np.radians(2 * lat_c)) - 3e3
+        tess = np.stack([lon_c.ravel() - 1, lon_c.ravel() + 1, lat_c.ravel() - 1, lat_c.ravel() + 1,
+                         np.full(lon_c.size, R - 30e3), top.ravel()], axis=1)  # fmt: skip
+        density = rng.uniform(2500, 3300, lon_c.size)
+        coords = (rng.uniform(-180, 180, n_obs), np.degrees(np.arcsin(rng.uniform(-1, 1, n_obs))),
+                  np.full(n_obs, R + 10e3))  # fmt: skip
+        return dict(kind="tess", coords=coords, tesseroids=np.ascontiguousarray(tess),
+                    density=density, n_src=tess.shape[0], mask=1 << 3, nf=1,
+                    desc=f"tesseroid_gravity g_z, {tess.shape[0]} tesseroids (2x2 degree global layer) "
+                    f"x {n_obs} observers at 10 km")  # fmt: skip
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -173,6 +195,8 @@ def cpu_rate(wl, n_obs_sample, nthreads):
             O.prism_gravity(sub, wl["prisms"], wl["density"], f, nthreads=nthreads)
     elif wl["kind"] == "mag":
         O.prism_magnetic(sub, wl["prisms"], wl["mag"], "b", nthreads=nthreads)
+    elif wl["kind"] == "tess":
+        O.tesseroid_gravity(sub, wl["tesseroids"], wl["density"], "g_z", nthreads=nthreads)
     else:
         O.eqs_predict(sub, wl["points"], wl["coefs"], nthreads=nthreads)
     dt = time.perf_counter() - t0
@@ -267,6 +291,8 @@ def run_b200(args):
         pairs_per_step_rank = float(n_obs) * float(n_src)
     if wl["kind"] == "eqs":
         ws_bytes = lib.hb200_point_ws_bytes(n_obs, n_src)
+    elif wl["kind"] == "tess":
+        ws_bytes = lib.hb200_tesseroid_ws_bytes(n_obs, n_src)
     else:
         ws_bytes = lib.hb200_prism_ws_bytes(n_obs, n_src, nf)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
@@ -302,6 +328,18 @@ def run_b200(args):
             return hb.prism_gravity(coords, wl["prisms"], wl["density"], fields, disable_checks=True)
         h2d = 8 * (3 * n_obs + 7 * n_src)
         launches_per_step = 2  # pack_prisms_kernel + prism_kernel (+1 reduce when sources are chunked)
+    elif wl["kind"] == "tess":
+        ts, rho = t(wl["tesseroids"]), t(wl["density"])
+
+        def step_dev():
+            return lib.hb200_tesseroid_gravity_dev(P(oe), P(on), P(ou), n_obs, P(ts), P(rho), n_src,
+                                                   3, 0, P(out), P(flags), P(ws), ws_bytes, stream)
+
+        def step_host():
+            return hb.tesseroid_gravity(coords, wl["tesseroids"], wl["density"], "g_z",
+                                        disable_checks=True)
+        h2d = 8 * (3 * n_obs + 7 * n_src)
+        launches_per_step = 2  # pack_tesseroids_kernel + tesseroid_kernel
     elif wl["kind"] == "mag":
         pr = t(wl["prisms"])
         m = [t(x) for x in wl["mag"]]
