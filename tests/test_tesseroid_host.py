@@ -65,6 +65,34 @@ def harness_tesseroid(coordinates, tesseroids, density, field, radial):
     return out, counts, flags.value
 
 
+def reference_conditioning(coordinates, tesseroids, density, field, radial, trials=4):
+    """
+    How far the REFERENCE's own result moves (relative to max|field|) when its input coordinates
+    change by one unit in the last place: its spherical distance goes through 1 - cos(psi), which
+    loses (radius / distance)^2 * 1e-16 digits for nearby quadrature nodes, so two correct
+    float64 evaluations with differently rounded sin / cos (glibc here, CUDA on the device) can
+    only agree to this level. Used as the parity bar where it exceeds 1e-9.
+    """
+    coords = [np.atleast_1d(np.asarray(c, dtype=np.float64)) for c in coordinates]
+    base = np.atleast_1d(O.tesseroid_gravity(coords, tesseroids, density, field, radial))
+    worst = 0.0
+    for k in range(trials):
+        rng = np.random.default_rng(k)
+        moved = [c * (1 + 2.2e-16 * rng.integers(-1, 2, c.shape)) for c in coords]
+        out = np.atleast_1d(O.tesseroid_gravity(moved, tesseroids, density, field, radial))
+        worst = max(worst, float(np.max(np.abs(out - base)) / np.max(np.abs(base))))
+    return worst
+
+
+def test_reference_conditioning_near_the_surface():
+    """the 'four' case (points 100 m above 10-degree tesseroids): g_z moves by ~2e-9 of its
+    maximum under a 1-ulp change of the inputs, the potential by ~1e-13"""
+    _, cases = _cases()
+    coords, tesseroids, density = cases["four"]
+    assert reference_conditioning(coords, tesseroids, density, "g_z", False) > 2e-10
+    assert reference_conditioning(coords, tesseroids, density, "potential", False) < 1e-11
+
+
 # ------------------------------------------------------------------ oracle vs the reference
 @pytest.mark.parametrize("field,radial", MODES)
 @pytest.mark.parametrize("name", ["random", "doctest", "four", "wrapped"])
