@@ -49,6 +49,8 @@ SIGNATURES = {
     "hb200_last_error": (ctypes.c_char_p, []),
     "hb200_set_variant": (_int, [_int]),
     "hb200_get_variant": (_int, []),
+    "hb200_set_tesseroid_variant": (_int, [_int]),
+    "hb200_get_tesseroid_variant": (_int, []),
     "hb200_launch_count": (ctypes.c_uint64, []),
     "hb200_prism_gravity": (
         _int, [_dp, _dp, _dp, _i64, _dp, _dp, _i64, _u32, _int, _dp, _u32p]),

@@ -521,9 +521,11 @@ int dipole_magnetic_dev_impl(const double* oe, const double* on, const double* o
 }
 
 // tesseroid_gravity: one field per pass (potential or g_z); workspace = [packed][partials]
+int g_tess_variant = 1;  // 1: root records + deferred walks (default); 0: first build
+
 size_t tesseroid_ws_bytes(int64_t n_obs, int64_t n_src, int sms)
 {
-    return align_up((size_t)std::max<int64_t>(n_src, 1) * kTessStride * sizeof(double))
+    return align_up((size_t)std::max<int64_t>(n_src, 1) * kTessRec * sizeof(double))
          + partial_bytes_for(n_obs, n_src, 1, kTessBlock, sms) + 256;
 }
 
@@ -534,15 +536,20 @@ int tesseroid_dev_impl(const double* lon, const double* lat, const double* rad, 
 {
     if (field != F_POT && field != F_U) return fail(HB200_EINVAL, "tesseroids: potential or g_z only");
     Ws ws(wsp, ws_bytes);
-    double* packed = ws.take((size_t)std::max<int64_t>(n_tess, 1) * kTessStride * sizeof(double));
+    const int variant = g_tess_variant;
+    double* packed = ws.take((size_t)std::max<int64_t>(n_tess, 1) * kTessRec * sizeof(double));
     if (!packed) return fail(HB200_EINVAL, "workspace too small");
     if (n_obs == 0) return HB200_OK;
     if (n_tess == 0) {
         CU(cudaMemsetAsync(out, 0, sizeof(double) * n_obs, st));
         return HB200_OK;
     }
-    pack_tesseroids_kernel<<<(unsigned)((n_tess + 255) / 256), 256, 0, st>>>(tesseroids, density,
-                                                                            n_tess, packed);
+    if (variant == 0)
+        pack_tesseroids_kernel<<<(unsigned)((n_tess + 255) / 256), 256, 0, st>>>(tesseroids, density,
+                                                                                n_tess, packed);
+    else
+        pack_tesseroid_records_kernel<<<(unsigned)((n_tess + 127) / 128), 128, 0, st>>>(
+            tesseroids, density, n_tess, packed);
     CU(cudaGetLastError());
     double* partial = (double*)(ws.base + ws.used);
     const size_t partial_bytes = ws.left();
@@ -563,8 +570,13 @@ int tesseroid_dev_impl(const double* lon, const double* lat, const double* rad, 
     a.radial = radial;
     a.flags = d_flags;
     dim3 grid((unsigned)((n_obs + kTessBlock - 1) / kTessBlock), (unsigned)chunks);
-    if (field == F_POT) tesseroid_kernel<F_POT><<<grid, kTessBlock, 0, st>>>(a);
-    else tesseroid_kernel<F_U><<<grid, kTessBlock, 0, st>>>(a);
+    if (variant == 0) {
+        if (field == F_POT) tesseroid_kernel<F_POT><<<grid, kTessBlock, 0, st>>>(a);
+        else tesseroid_kernel<F_U><<<grid, kTessBlock, 0, st>>>(a);
+    } else {
+        if (field == F_POT) tesseroid_deferred_kernel<F_POT><<<grid, kTessBlock, 0, st>>>(a);
+        else tesseroid_deferred_kernel<F_U><<<grid, kTessBlock, 0, st>>>(a);
+    }
     CU(cudaGetLastError());
     g_launches += chunks > 1 ? 3 : 2;
     if (chunks > 1) {
@@ -821,6 +833,13 @@ int hb200_set_variant(int variant)
     return HB200_OK;
 }
 int hb200_get_variant(void) { return g_variant; }
+int hb200_set_tesseroid_variant(int variant)
+{
+    if (variant < 0 || variant > 1) return fail(HB200_EINVAL, "tesseroid variant must be 0 or 1");
+    g_tess_variant = variant;
+    return HB200_OK;
+}
+int hb200_get_tesseroid_variant(void) { return g_tess_variant; }
 uint64_t hb200_launch_count(void) { return g_launches.load(); }
 
 void hb200_shutdown(void)

@@ -14,10 +14,19 @@
 // The SPLIT DECISIONS (distance / size < ratio) are evaluated with the reference's expressions in
 // the reference's order, so that the set of leaves is the reference's (a decision can only flip
 // when distance / size equals the ratio to within the rounding of sin / cos / acos). What is
-// restructured is decision-neutral and value-identical: the leaves are integrated as they are
-// popped instead of being collected first (same order of additions), the observer's radians /
-// cos / sin are hoisted out of the pair loop, and the two distinct cos(longitude_p - longitude) of
-// a leaf are computed once instead of for all eight nodes.
+// restructured is decision-neutral and value-identical:
+//   * the leaves are integrated as they are popped instead of being collected first;
+//   * the observer's radians / cos / sin are hoisted out of the pair loop, the two distinct
+//     cos(longitude_p - longitude) of a leaf are computed once instead of for all eight nodes;
+//   * everything about a ROOT tesseroid that does not depend on the observer (its dimensions, the
+//     trig of its centre, its eight quadrature nodes and their masses) is computed once per
+//     tesseroid by the pack kernel with the same statements (tess_pack_record) instead of once
+//     per pair: 98 % of the pairs of a typical model never split, for them the pair loop is left
+//     with three cosines, nine square roots and the divisions;
+//   * (kernel variant 1) pairs that do split are deferred and walked later by all lanes of the warp
+//     concurrently, each lane through its own list, instead of one lane at a time while the
+//     others wait (the first build ran with 19.8 of 32 lanes active, profiles/).
+// Only the ORDER in which a thread adds its pairs changes with the last item.
 #pragma once
 #include "hb200_math.cuh"
 
@@ -25,7 +34,8 @@ namespace hb {
 
 constexpr int kTessStack = 100;          // tesseroid_gravity.py:30  STACK_SIZE
 constexpr int kTessMaxLeaves = 100000;   // tesseroid_gravity.py:31  MAX_DISCRETIZATIONS
-constexpr int kTessStride = 8;           // w e s n bottom top density -
+constexpr int kTessStride = 8;           // plain record: w e s n bottom top density -
+constexpr int kTessRec = 32;             // root record with the observer-independent parts
 constexpr unsigned FLAG_TESS_STACK = 4u;    // "Stack Overflow. Try to increase the stack size."
 constexpr unsigned FLAG_TESS_LEAVES = 8u;   // "Exceeded maximum discretizations."
 constexpr unsigned FLAG_TESS_INSIDE = 16u;  // a computation point lies inside a tesseroid
@@ -68,33 +78,104 @@ HB_HD void tess_make_obs(TessObs& o, double lon, double lat, double rad)
     o.sphi = sin(phi);
 }
 
-// _tesseroid_utils.py:19-107 with point.py:324-354. FIELD: F_POT or F_U (radial component).
-template <int FIELD>
-HB_HD double tess_glq(const TessObs& o, double w, double e, double s, double n, double bottom,
-                      double top, double density, unsigned& flags)
+// ---- the observer-independent parts of one tesseroid -----------------------------------------
+struct TessDims {
+    double l_lon, l_lat, l_rad;  // _tesseroid_dimensions
+};
+struct TessCentre {
+    double lam, cphi, sphi, rad;  // radians(longitude), cos / sin of radians(latitude), radius
+};
+struct TessNodes {
+    double lam[2];              // GLQ longitude nodes, radians
+    double cphi[2], sphi[2];    // GLQ latitude nodes
+    double rad[2];              // GLQ radial nodes
+    double mass[2][2];          // [lat node][radial node]: density * a_factor * kappa (weights 1)
+};
+
+// _tesseroid_utils.py:261-279
+HB_HD void tess_dims(TessDims& d, double w, double e, double s, double n, double bottom, double top)
+{
+    const double wr = w * kDeg2Rad, er = e * kDeg2Rad, sr = s * kDeg2Rad, nr = n * kDeg2Rad;
+    const double latitude_center = (nr + sr) / 2;
+    d.l_lat = top * acos(sin(nr) * sin(sr) + cos(nr) * cos(sr));
+    const double sc = sin(latitude_center), cc = cos(latitude_center);
+    d.l_lon = top * acos(sc * sc + cc * cc * cos(er - wr));
+    d.l_rad = top - bottom;
+}
+
+// the point _distance_tesseroid_point (:282-300) measures to, as distance_spherical sees it
+HB_HD void tess_centre(TessCentre& c, double w, double e, double s, double n, double bottom,
+                       double top)
+{
+    c.lam = ((w + e) / 2) * kDeg2Rad;
+    const double latitude_p = ((s + n) / 2) * kDeg2Rad;
+    c.rad = (bottom + top) / 2;
+    c.cphi = cos(latitude_p);
+    c.sphi = sin(latitude_p);
+}
+
+// utils.py:164-201 between the observer and the centre
+HB_HD double tess_distance(const TessObs& o, const TessCentre& c)
+{
+    const double coslambda = cos(c.lam - o.lam);
+    const double cospsi = c.sphi * o.sphi + c.cphi * o.cphi * coslambda;
+    const double dr = o.rad - c.rad;
+    return sqrt(dr * dr + 2 * o.rad * c.rad * (1 - cospsi));
+}
+
+// _tesseroid_utils.py:186-191. Returns false where numba's float division raises
+// ZeroDivisionError (all three quotients are evaluated; a child so small that acos(...) == 0).
+HB_HD bool tess_split_counts(double distance, const TessDims& d, double ratio, bool radial,
+                             int& n_lon, int& n_lat, int& n_rad)
+{
+    n_lon = n_lat = n_rad = 1;
+    if (d.l_lon == 0.0 || d.l_lat == 0.0 || d.l_rad == 0.0) return false;
+    n_lon = (distance / d.l_lon < ratio) ? 2 : 1;
+    n_lat = (distance / d.l_lat < ratio) ? 2 : 1;
+    n_rad = (distance / d.l_rad < ratio && radial) ? 2 : 1;
+    return true;
+}
+
+// the node coordinates and masses of gauss_legendre_quadrature (:19-107)
+HB_HD void tess_nodes(TessNodes& q, double w, double e, double s, double n, double bottom,
+                      double top, double density)
 {
     const double a_factor = 1.0 / 8 * ((e - w) * kDeg2Rad) * ((n - s) * kDeg2Rad) * (top - bottom);
-    double coslambda[2];
 #pragma unroll
     for (int i = 0; i < 2; i++) {
         const double node = i ? kGlqNode : -kGlqNode;
-        const double longitude_p = (0.5 * (e - w) * node + 0.5 * (e + w)) * kDeg2Rad;
-        coslambda[i] = cos(longitude_p - o.lam);
+        q.lam[i] = (0.5 * (e - w) * node + 0.5 * (e + w)) * kDeg2Rad;
+        const double latitude_p = (0.5 * (n - s) * node + 0.5 * (n + s)) * kDeg2Rad;
+        q.cphi[i] = cos(latitude_p);
+        q.sphi[i] = sin(latitude_p);
+        q.rad[i] = 0.5 * (top - bottom) * node + 0.5 * (top + bottom);
     }
-    double result = 0.0;
 #pragma unroll
-    for (int j = 0; j < 2; j++) {
-        const double latitude_p = (0.5 * (n - s) * (j ? kGlqNode : -kGlqNode) + 0.5 * (n + s)) * kDeg2Rad;
-        const double cosphi_p = cos(latitude_p), sinphi_p = sin(latitude_p);
+    for (int j = 0; j < 2; j++)
 #pragma unroll
         for (int k = 0; k < 2; k++) {
-            const double radius_p = 0.5 * (top - bottom) * (k ? kGlqNode : -kGlqNode) + 0.5 * (top + bottom);
-            const double kappa = radius_p * radius_p * cosphi_p;
-            const double mass = density * a_factor * kappa;  // the three GLQ weights are 1
+            const double kappa = q.rad[k] * q.rad[k] * q.cphi[j];
+            q.mass[j][k] = density * a_factor * kappa;  // the three GLQ weights are 1
+        }
+}
+
+// sum over the eight nodes in the reference's order (latitude, radius, longitude) with the
+// kernels of point.py:324-354. FIELD: F_POT or F_U (radial component).
+template <int FIELD> HB_HD double tess_glq_nodes(const TessObs& o, const TessNodes& q, unsigned& flags)
+{
+    double coslambda[2];
+#pragma unroll
+    for (int i = 0; i < 2; i++) coslambda[i] = cos(q.lam[i] - o.lam);
+    double result = 0.0;
+#pragma unroll
+    for (int j = 0; j < 2; j++)
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const double radius_p = q.rad[k];
             const double dr = o.rad - radius_p;
 #pragma unroll
             for (int i = 0; i < 2; i++) {
-                const double cospsi = sinphi_p * o.sphi + cosphi_p * o.cphi * coslambda[i];
+                const double cospsi = q.sphi[j] * o.sphi + q.cphi[j] * o.cphi * coslambda[i];
                 const double dist = sqrt(dr * dr + 2 * o.rad * radius_p * (1 - cospsi));
                 double kern;
                 if (dist == 0.0) flags |= FLAG_ZERO_DIV;  // observer on a quadrature node
@@ -104,88 +185,154 @@ HB_HD double tess_glq(const TessObs& o, double w, double e, double s, double n, 
                     const double delta_z = o.rad - radius_p * cospsi;
                     kern = -kG * delta_z / (dist * dist * dist);
                 }
-                result += mass * kern;
+                result += q.mass[j][k] * kern;
             }
         }
-    }
     return result;
 }
 
+// ---- the walk over the adaptive discretisation of one pair --------------------------------------
+struct TessWalk {
+    int stack_top;   // < 0: no pair in progress
+    int n_leaves;
+    double density;
+};
+
+HB_HD void tess_walk_begin(TessWalk& w, const double* tess, double density, double* stack)
+{
+#pragma unroll
+    for (int c = 0; c < 6; c++) stack[c] = tess[c];
+    w.stack_top = 0;
+    w.n_leaves = 0;
+    w.density = density;
+}
+
+// One pop of _adaptive_discretization (:178-216): either pushes the children (_split_tesseroid)
+// or integrates the leaf into `acc`. Where the reference raises, a flag is set and the walk of
+// this pair ends. `stack` holds STACK x 6 doubles and is private to the caller. (STACK /
+// MAX_LEAVES are template parameters only so that the tests can provoke the overflow errors like
+// the reference's do.)
+template <int FIELD, int STACK = kTessStack, int MAX_LEAVES = kTessMaxLeaves>
+HB_HD void tess_walk_step(const TessObs& o, double ratio, bool radial, double* stack, TessWalk& wk,
+                          double& acc, unsigned& flags)
+{
+    const double* q = stack + 6 * wk.stack_top;
+    const double w = q[0], e = q[1], s = q[2], n = q[3], bottom = q[4], top = q[5];
+    wk.stack_top -= 1;
+    TessDims dims;
+    tess_dims(dims, w, e, s, n, bottom, top);
+    TessCentre centre;
+    tess_centre(centre, w, e, s, n, bottom, top);
+    const double distance = tess_distance(o, centre);
+    int n_lon, n_lat, n_rad;
+    if (!tess_split_counts(distance, dims, ratio, radial, n_lon, n_lat, n_rad)) {
+        flags |= FLAG_ZERO_DIV;
+        wk.stack_top = -1;
+        return;
+    }
+    if (n_lon * n_lat * n_rad > 1) {
+        if ((wk.stack_top + 1) + n_lon * n_lat * n_rad > STACK) {
+            flags |= FLAG_TESS_STACK;
+            wk.stack_top = -1;
+            return;
+        }
+        // _split_tesseroid
+        const double d_lon = (e - w) / n_lon, d_lat = (n - s) / n_lat, d_rad = (top - bottom) / n_rad;
+        for (int i = 0; i < n_lon; i++)
+            for (int j = 0; j < n_lat; j++)
+                for (int k = 0; k < n_rad; k++) {
+                    wk.stack_top += 1;
+                    double* c = stack + 6 * wk.stack_top;
+                    c[0] = w + d_lon * i;
+                    c[1] = w + d_lon * (i + 1);
+                    c[2] = s + d_lat * j;
+                    c[3] = s + d_lat * (j + 1);
+                    c[4] = bottom + d_rad * k;
+                    c[5] = bottom + d_rad * (k + 1);
+                }
+    } else {
+        if (wk.n_leaves + 1 > MAX_LEAVES) {
+            flags |= FLAG_TESS_LEAVES;
+            wk.stack_top = -1;
+            return;
+        }
+        TessNodes nodes;
+        tess_nodes(nodes, w, e, s, n, bottom, top, wk.density);
+        acc += tess_glq_nodes<FIELD>(o, nodes, flags);
+        wk.n_leaves += 1;
+    }
+}
+
 // One (observer, tesseroid) pair: adds the quadrature of every leaf of the adaptive
-// discretisation to `acc` in the reference's order. `stack` holds STACK x 6 doubles and is
-// private to the caller. Returns the number of leaves. (STACK / MAX_LEAVES are template
-// parameters only so that the tests can provoke the overflow errors like the reference's do.)
+// discretisation to `acc` in the reference's order. Returns the number of leaves.
 template <int FIELD, int STACK = kTessStack, int MAX_LEAVES = kTessMaxLeaves>
 HB_HD int tess_pair(const TessObs& o, const double* tess, double density, double ratio, bool radial,
                     double* stack, double& acc, unsigned& flags)
 {
+    TessWalk wk;
+    tess_walk_begin(wk, tess, density, stack);
+    while (wk.stack_top >= 0)
+        tess_walk_step<FIELD, STACK, MAX_LEAVES>(o, ratio, radial, stack, wk, acc, flags);
+    return wk.n_leaves;
+}
+
+// ---- root record -----------------------------------------------------------------------------------
+// [0..5] w e s n bottom top  [6] density  [7..9] l_lon l_lat l_rad
+// [10..13] centre: lam cphi sphi rad   [14,15] node lam   [16,17] node cphi   [18,19] node sphi
+// [20,21] node rad   [22..25] mass[j][k]   [26..31] unused
+HB_HD void tess_pack_record(double* rec, const double* tess, double density)
+{
 #pragma unroll
-    for (int c = 0; c < 6; c++) stack[c] = tess[c];
-    int stack_top = 0;
-    int n_leaves = 0;
-    while (stack_top >= 0) {
-        const double* q = stack + 6 * stack_top;
-        const double w = q[0], e = q[1], s = q[2], n = q[3], bottom = q[4], top = q[5];
-        stack_top -= 1;
-        // _tesseroid_dimensions
-        const double wr = w * kDeg2Rad, er = e * kDeg2Rad, sr = s * kDeg2Rad, nr = n * kDeg2Rad;
-        const double latitude_center = (nr + sr) / 2;
-        const double l_lat = top * acos(sin(nr) * sin(sr) + cos(nr) * cos(sr));
-        const double sc = sin(latitude_center), cc = cos(latitude_center);
-        const double l_lon = top * acos(sc * sc + cc * cc * cos(er - wr));
-        const double l_rad = top - bottom;
-        // _distance_tesseroid_point -> distance_spherical (degrees in, centre of the tesseroid)
-        const double longitude_p = ((w + e) / 2) * kDeg2Rad;
-        const double latitude_p = ((s + n) / 2) * kDeg2Rad;
-        const double radius_p = (bottom + top) / 2;
-        const double cosphi_p = cos(latitude_p), sinphi_p = sin(latitude_p);
-        const double coslambda = cos(longitude_p - o.lam);
-        const double cospsi = sinphi_p * o.sphi + cosphi_p * o.cphi * coslambda;
-        const double dr = o.rad - radius_p;
-        const double distance = sqrt(dr * dr + 2 * o.rad * radius_p * (1 - cospsi));
-        // numba evaluates all three quotients and raises ZeroDivisionError on a zero divisor
-        // (a child so small that acos(...) == 0: the observer sits on a corner that every level
-        // of the 3-D discretisation keeps splitting)
-        if (l_lon == 0.0 || l_lat == 0.0 || l_rad == 0.0) {
-            flags |= FLAG_ZERO_DIV;
-            return n_leaves;
-        }
-        const int n_lon = (distance / l_lon < ratio) ? 2 : 1;
-        const int n_lat = (distance / l_lat < ratio) ? 2 : 1;
-        const int n_rad = (distance / l_rad < ratio && radial) ? 2 : 1;
-        if (n_lon * n_lat * n_rad > 1) {
-            if ((stack_top + 1) + n_lon * n_lat * n_rad > STACK) {
-                flags |= FLAG_TESS_STACK;
-                return n_leaves;
-            }
-            // _split_tesseroid
-            const double d_lon = (e - w) / n_lon, d_lat = (n - s) / n_lat, d_rad = (top - bottom) / n_rad;
-            for (int i = 0; i < n_lon; i++)
-                for (int j = 0; j < n_lat; j++)
-                    for (int k = 0; k < n_rad; k++) {
-                        stack_top += 1;
-                        double* c = stack + 6 * stack_top;
-                        c[0] = w + d_lon * i;
-                        c[1] = w + d_lon * (i + 1);
-                        c[2] = s + d_lat * j;
-                        c[3] = s + d_lat * (j + 1);
-                        c[4] = bottom + d_rad * k;
-                        c[5] = bottom + d_rad * (k + 1);
-                    }
-        } else {
-            if (n_leaves + 1 > MAX_LEAVES) {
-                flags |= FLAG_TESS_LEAVES;
-                return n_leaves;
-            }
-            acc += tess_glq<FIELD>(o, w, e, s, n, bottom, top, density, flags);
-            n_leaves += 1;
-        }
+    for (int c = 0; c < 6; c++) rec[c] = tess[c];
+    rec[6] = density;
+    TessDims d;
+    tess_dims(d, tess[0], tess[1], tess[2], tess[3], tess[4], tess[5]);
+    rec[7] = d.l_lon; rec[8] = d.l_lat; rec[9] = d.l_rad;
+    TessCentre c;
+    tess_centre(c, tess[0], tess[1], tess[2], tess[3], tess[4], tess[5]);
+    rec[10] = c.lam; rec[11] = c.cphi; rec[12] = c.sphi; rec[13] = c.rad;
+    TessNodes q;
+    tess_nodes(q, tess[0], tess[1], tess[2], tess[3], tess[4], tess[5], density);
+    rec[14] = q.lam[0]; rec[15] = q.lam[1];
+    rec[16] = q.cphi[0]; rec[17] = q.cphi[1];
+    rec[18] = q.sphi[0]; rec[19] = q.sphi[1];
+    rec[20] = q.rad[0]; rec[21] = q.rad[1];
+    rec[22] = q.mass[0][0]; rec[23] = q.mass[0][1]; rec[24] = q.mass[1][0]; rec[25] = q.mass[1][1];
+#pragma unroll
+    for (int c2 = 26; c2 < kTessRec; c2++) rec[c2] = 0.0;
+}
+
+// The root pop of a pair from its record. Returns 1 when the root is a leaf (integrated into
+// `acc`), 0 when it splits (the caller walks it with tess_pair / tess_walk_step, which repeat the
+// root decision with the same values) and -1 where the reference raises (flag set).
+template <int FIELD>
+HB_HD int tess_root(const TessObs& o, const double* rec, double ratio, bool radial, double& acc,
+                    unsigned& flags)
+{
+    TessDims dims;
+    dims.l_lon = rec[7]; dims.l_lat = rec[8]; dims.l_rad = rec[9];
+    TessCentre centre;
+    centre.lam = rec[10]; centre.cphi = rec[11]; centre.sphi = rec[12]; centre.rad = rec[13];
+    const double distance = tess_distance(o, centre);
+    int n_lon, n_lat, n_rad;
+    if (!tess_split_counts(distance, dims, ratio, radial, n_lon, n_lat, n_rad)) {
+        flags |= FLAG_ZERO_DIV;
+        return -1;
     }
-    return n_leaves;
+    if (n_lon * n_lat * n_rad > 1) return 0;
+    TessNodes q;
+    q.lam[0] = rec[14]; q.lam[1] = rec[15];
+    q.cphi[0] = rec[16]; q.cphi[1] = rec[17];
+    q.sphi[0] = rec[18]; q.sphi[1] = rec[19];
+    q.rad[0] = rec[20]; q.rad[1] = rec[21];
+    q.mass[0][0] = rec[22]; q.mass[0][1] = rec[23]; q.mass[1][0] = rec[24]; q.mass[1][1] = rec[25];
+    acc += tess_glq_nodes<FIELD>(o, q, flags);
+    return 1;
 }
 
 #if defined(__CUDACC__)
 // ------------------------------------------------------------------ kernels
+// plain records (the inside scan and kernel variant 0)
 __global__ void pack_tesseroids_kernel(const double* __restrict__ tesseroids,
                                        const double* __restrict__ density, int64_t n,
                                        double* __restrict__ packed)
@@ -197,6 +344,19 @@ __global__ void pack_tesseroids_kernel(const double* __restrict__ tesseroids,
     for (int c = 0; c < 6; c++) q[c] = tesseroids[j * 6 + c];
     q[6] = density[j];
     q[7] = 0.0;
+}
+
+// root records: everything about a tesseroid that does not depend on the observer
+__global__ void pack_tesseroid_records_kernel(const double* __restrict__ tesseroids,
+                                              const double* __restrict__ density, int64_t n,
+                                              double* __restrict__ packed)
+{
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    double t[6];
+#pragma unroll
+    for (int c = 0; c < 6; c++) t[c] = tesseroids[j * 6 + c];
+    tess_pack_record(packed + j * kTessRec, t, density[j]);
 }
 
 struct TessArgs {
@@ -215,10 +375,12 @@ struct TessArgs {
 };
 
 constexpr int kTessBlock = 64;  // observers per CTA: the per-thread stack lives in local memory
+constexpr int kTessTile = 32;   // root records per shared-memory tile (8 KB)
+constexpr int kTessDefer = 16;  // split pairs a thread collects before the warp walks them
 
+// Variant 0 (first build, kept selectable): plain records, every pair walked where it is met.
 // One thread owns one observer, keeps its accumulator in a register and its discretisation
 // stack (4.8 KB) in local memory; the CTA walks the tesseroid records in shared-memory tiles.
-// Lanes diverge only inside tess_pair (near pairs split, far pairs do not).
 template <int FIELD>
 __global__ void __launch_bounds__(kTessBlock) tesseroid_kernel(const TessArgs a)
 {
@@ -250,6 +412,72 @@ __global__ void __launch_bounds__(kTessBlock) tesseroid_kernel(const TessArgs a)
     }
     if (flags && a.flags) atomicOr(a.flags, flags);
 }
+
+// Walk the pairs a thread has deferred: every lane goes through ITS list with ITS stack, one pop
+// per trip of a single loop, so the lanes of a warp work concurrently whatever the shapes of
+// their discretisation trees.
+template <int FIELD>
+__device__ __forceinline__ void tess_walk_deferred(const TessObs& o, const TessArgs& a,
+                                                   const int64_t* defer, int& n_defer,
+                                                   double* stack, double& acc, unsigned& flags)
+{
+    TessWalk wk;
+    wk.stack_top = -1;
+    wk.n_leaves = 0;
+    wk.density = 0.0;
+    int k = 0;
+    while (true) {
+        if (wk.stack_top < 0) {
+            if (k >= n_defer) break;
+            const double* rec = a.packed + defer[k++] * kTessRec;
+            tess_walk_begin(wk, rec, rec[6], stack);
+        }
+        tess_walk_step<FIELD>(o, a.ratio, a.radial != 0, stack, wk, acc, flags);
+    }
+    n_defer = 0;
+}
+
+// Variant 1 (default): root records + deferred walks. The loop over a tile is uniform (root
+// decision from the record, unsplit pairs integrated at once, three cosines per pair); a pair
+// that splits is only noted. When any lane of the warp has kTessDefer pairs noted, and at the
+// end, all lanes walk their lists together.
+template <int FIELD>
+__global__ void __launch_bounds__(kTessBlock) tesseroid_deferred_kernel(const TessArgs a)
+{
+    __shared__ double tile[kTessTile * kTessRec];
+    double stack[kTessStack * 6];
+    int64_t defer[kTessDefer];
+    int n_defer = 0;
+    const int64_t i = (int64_t)blockIdx.x * kTessBlock + threadIdx.x;
+    const bool live = i < a.n_obs;
+    const int64_t ic = live ? i : a.n_obs - 1;
+    TessObs o;
+    tess_make_obs(o, a.lon[ic], a.lat[ic], a.rad[ic]);
+    double acc = 0.0;
+    unsigned flags = 0;
+    const int64_t begin = (int64_t)blockIdx.y * a.chunk_len;
+    const int64_t end = begin + a.chunk_len < a.n_src ? begin + a.chunk_len : a.n_src;
+    for (int64_t t0 = begin; t0 < end; t0 += kTessTile) {
+        const int cnt = (int)((end - t0) < kTessTile ? (end - t0) : kTessTile);
+        __syncthreads();
+        for (int x = threadIdx.x; x < cnt * kTessRec; x += kTessBlock)
+            tile[x] = a.packed[t0 * kTessRec + x];
+        __syncthreads();
+        for (int s = 0; s < cnt; s++) {
+            if (live && tess_root<FIELD>(o, tile + s * kTessRec, a.ratio, a.radial != 0, acc, flags) == 0)
+                defer[n_defer++] = t0 + s;
+            if (__any_sync(0xffffffffu, n_defer == kTessDefer))
+                tess_walk_deferred<FIELD>(o, a, defer, n_defer, stack, acc, flags);
+        }
+    }
+    tess_walk_deferred<FIELD>(o, a, defer, n_defer, stack, acc, flags);
+    if (live) {
+        if (gridDim.y == 1) a.out[i] = acc * a.scale;
+        else a.out[(int64_t)blockIdx.y * a.n_obs + i] = acc;
+    }
+    if (flags && a.flags) atomicOr(a.flags, flags);
+}
+
 // check_points_outside_tesseroids as one pass: sets FLAG_TESS_INSIDE if any pair conflicts
 __global__ void __launch_bounds__(128) tesseroid_inside_scan_kernel(const TessArgs a)
 {

@@ -30,6 +30,13 @@ def emit(**kw):
 
 
 def tesseroids():
+    for variant in (1, 0):
+        lib.hb200_set_tesseroid_variant(variant)
+        _tesseroids(variant)
+    lib.hb200_set_tesseroid_variant(1)
+
+
+def _tesseroids(variant):
     import bench
 
     for n_obs in (4096, 32768):
@@ -39,7 +46,7 @@ def tesseroids():
                 dt, _ = timed(lambda: hb.tesseroid_gravity(wl["coords"], wl["tesseroids"], wl["density"], field,
                                                            radial_adaptive_discretization=radial,
                                                            disable_checks=True), repeat=1)  # fmt: skip
-                emit(row="tesseroid_gravity", field=field, radial=radial, n_obs=n_obs, n_tess=wl["n_src"],
+                emit(row="tesseroid_gravity", kernel_variant=variant, field=field, radial=radial, n_obs=n_obs, n_tess=wl["n_src"],
                      seconds=dt, pairs_per_s=n_obs * wl["n_src"] / dt, api="numpy host API, e2e")  # fmt: skip
     # observers ON the surface of a regional model: deep splitting
     rng = np.random.default_rng(1)
@@ -50,7 +57,7 @@ def tesseroids():
     coords = (rng.uniform(-10, 10, 8192), rng.uniform(-10, 10, 8192), np.full(8192, R + 10.0))
     dt, _ = timed(lambda: hb.tesseroid_gravity(coords, tess, np.full(lon_c.size, 2670.0), "g_z",
                                                disable_checks=True), repeat=1)  # fmt: skip
-    emit(row="tesseroid_gravity", case="observers 10 m above a 0.5 degree regional layer", n_obs=8192,
+    emit(row="tesseroid_gravity", kernel_variant=variant, case="observers 10 m above a 0.5 degree regional layer", n_obs=8192,
          n_tess=int(lon_c.size), seconds=dt, pairs_per_s=8192 * lon_c.size / dt)  # fmt: skip
 
 

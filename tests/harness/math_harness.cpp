@@ -110,6 +110,51 @@ void hbt_tesseroid_loop(int field, int64_t n_obs, const double* lon, const doubl
     if (flags) *flags = f;
 }
 
+// The per-thread algorithm of tesseroid_deferred_kernel on the host: root records, root decision
+// from the record, unsplit pairs integrated at once, split pairs noted and walked when `defer_cap`
+// of them are pending and at the end (one lane, so no warp vote). leaves: leaves per pair.
+void hbt_tesseroid_loop_deferred(int field, int64_t n_obs, const double* lon, const double* lat,
+                                 const double* rad, int64_t n_tess, const double* tesseroids,
+                                 const double* density, int radial, int defer_cap, double* out,
+                                 int64_t* counts, unsigned* flags)
+{
+    double stack[kTessStack * 6];
+    double* records = new double[(size_t)(n_tess > 0 ? n_tess : 1) * kTessRec];
+    for (int64_t j = 0; j < n_tess; j++) tess_pack_record(records + j * kTessRec, tesseroids + 6 * j, density[j]);
+    int64_t* defer = new int64_t[defer_cap > 0 ? defer_cap : 1];
+    unsigned f = 0;
+    const double ratio = field == F_POT ? 1.0 : 2.5;
+    for (int64_t i = 0; i < n_obs; i++) {
+        TessObs o;
+        tess_make_obs(o, lon[i], lat[i], rad[i]);
+        double acc = 0.0;
+        int n_defer = 0;
+        auto walk = [&]() {
+            for (int k = 0; k < n_defer; k++) {
+                const double* rec = records + defer[k] * kTessRec;
+                int leaves;
+                if (field == F_POT) leaves = tess_pair<F_POT>(o, rec, rec[6], ratio, radial != 0, stack, acc, f);
+                else leaves = tess_pair<F_U>(o, rec, rec[6], ratio, radial != 0, stack, acc, f);
+                if (counts) counts[i * n_tess + defer[k]] = leaves;
+            }
+            n_defer = 0;
+        };
+        for (int64_t j = 0; j < n_tess; j++) {
+            const double* rec = records + j * kTessRec;
+            const int r = field == F_POT ? tess_root<F_POT>(o, rec, ratio, radial != 0, acc, f)
+                                         : tess_root<F_U>(o, rec, ratio, radial != 0, acc, f);
+            if (counts) counts[i * n_tess + j] = r == 1 ? 1 : 0;
+            if (r == 0) defer[n_defer++] = j;
+            if (n_defer == defer_cap) walk();
+        }
+        walk();
+        out[i] = acc;
+    }
+    delete[] records;
+    delete[] defer;
+    if (flags) *flags = f;
+}
+
 // test/test_tesseroid.py:317-336: tiny stack / tiny leaf budget provoke the overflow flags
 unsigned hbt_tesseroid_overflow(int which, const double* point, const double* tesseroid, double ratio)
 {

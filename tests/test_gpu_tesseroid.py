@@ -24,9 +24,18 @@ from test_tesseroid_host import (MEAN_RADIUS, MODES, _cases, _key, _shell, _shel
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=[1, 0], ids=["deferred", "plain"])
+def tess_variant(request, hb):
+    """both tesseroid kernels: 1 = root records + deferred walks (default), 0 = first build"""
+    lib = hb._lib.load()
+    assert lib.hb200_set_tesseroid_variant(request.param) == 0
+    yield request.param
+    lib.hb200_set_tesseroid_variant(1)
+
+
 @pytest.mark.parametrize("field,radial", MODES)
 @pytest.mark.parametrize("name", ["random", "doctest", "four", "wrapped"])
-def test_golden_tesseroid_gravity(hb, name, field, radial):
+def test_golden_tesseroid_gravity(hb, tess_variant, name, field, radial):
     g, cases = _cases()
     coords, tesseroids, density = cases[name]
     want = g[_key(name, field, radial)]
@@ -42,7 +51,7 @@ def test_golden_tesseroid_gravity(hb, name, field, radial):
 
 
 @pytest.mark.parametrize("field,radial", MODES)
-def test_tesseroid_gravity_vs_oracle(hb, field, radial):
+def test_tesseroid_gravity_vs_oracle(hb, tess_variant, field, radial):
     rng = np.random.default_rng(91)
     R = MEAN_RADIUS
     n_tess, n_obs = 700, 900
@@ -69,7 +78,7 @@ def test_tesseroid_gravity_vs_oracle(hb, field, radial):
 
 
 @pytest.mark.parametrize("field", ["potential", "g_z"])
-def test_spherical_shell(hb, field):
+def test_spherical_shell(hb, tess_variant, field):
     """test/test_tesseroid.py:683-770: the closed form of a homogeneous shell, 0.1 %"""
     lon, lat = np.meshgrid(np.arange(0, 351, 10.0), np.arange(-90, 91, 10.0))
     coords = (lon, lat, np.full_like(lon, MEAN_RADIUS))
@@ -125,6 +134,8 @@ def test_errors_shapes_and_dtypes(hb):
     before = lib.hb200_launch_count()
     hb.tesseroid_gravity([0, 0, R + 10], tess, 2670.0, "potential")
     assert lib.hb200_launch_count() - before >= 3  # inside scan (pack + scan), pack + kernel
+    assert lib.hb200_get_tesseroid_variant() == 1
+    assert lib.hb200_set_tesseroid_variant(7) != 0
 
 
 @pytest.mark.parametrize("field", ["potential", "g_z"])
