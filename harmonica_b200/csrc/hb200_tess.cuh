@@ -376,7 +376,10 @@ struct TessArgs {
 
 constexpr int kTessBlock = 64;  // observers per CTA: the per-thread stack lives in local memory
 constexpr int kTessTile = 32;   // root records per shared-memory tile (8 KB)
-constexpr int kTessDefer = 16;  // split pairs a thread collects before the warp walks them
+// Split pairs a thread collects before the warp walks them. It has to exceed the number of
+// tesseroids that split for ONE observer in typical models: with 16 every lane filled its list
+// inside its own neighbourhood, alone, and the walks ran with 1-3 of 32 lanes (ncu, profiles/).
+constexpr int kTessDefer = 64;
 
 // Variant 0 (first build, kept selectable): plain records, every pair walked where it is met.
 // One thread owns one observer, keeps its accumulator in a register and its discretisation
@@ -418,7 +421,7 @@ __global__ void __launch_bounds__(kTessBlock) tesseroid_kernel(const TessArgs a)
 // their discretisation trees.
 template <int FIELD>
 __device__ __forceinline__ void tess_walk_deferred(const TessObs& o, const TessArgs& a,
-                                                   const int64_t* defer, int& n_defer,
+                                                   const int* defer, int& n_defer, int64_t begin,
                                                    double* stack, double& acc, unsigned& flags)
 {
     TessWalk wk;
@@ -429,7 +432,7 @@ __device__ __forceinline__ void tess_walk_deferred(const TessObs& o, const TessA
     while (true) {
         if (wk.stack_top < 0) {
             if (k >= n_defer) break;
-            const double* rec = a.packed + defer[k++] * kTessRec;
+            const double* rec = a.packed + (begin + defer[k++]) * kTessRec;
             tess_walk_begin(wk, rec, rec[6], stack);
         }
         tess_walk_step<FIELD>(o, a.ratio, a.radial != 0, stack, wk, acc, flags);
@@ -446,7 +449,7 @@ __global__ void __launch_bounds__(kTessBlock) tesseroid_deferred_kernel(const Te
 {
     __shared__ double tile[kTessTile * kTessRec];
     double stack[kTessStack * 6];
-    int64_t defer[kTessDefer];
+    int defer[kTessDefer];  // offsets from `begin`
     int n_defer = 0;
     const int64_t i = (int64_t)blockIdx.x * kTessBlock + threadIdx.x;
     const bool live = i < a.n_obs;
@@ -465,12 +468,12 @@ __global__ void __launch_bounds__(kTessBlock) tesseroid_deferred_kernel(const Te
         __syncthreads();
         for (int s = 0; s < cnt; s++) {
             if (live && tess_root<FIELD>(o, tile + s * kTessRec, a.ratio, a.radial != 0, acc, flags) == 0)
-                defer[n_defer++] = t0 + s;
+                defer[n_defer++] = (int)(t0 - begin) + s;
             if (__any_sync(0xffffffffu, n_defer == kTessDefer))
-                tess_walk_deferred<FIELD>(o, a, defer, n_defer, stack, acc, flags);
+                tess_walk_deferred<FIELD>(o, a, defer, n_defer, begin, stack, acc, flags);
         }
     }
-    tess_walk_deferred<FIELD>(o, a, defer, n_defer, stack, acc, flags);
+    tess_walk_deferred<FIELD>(o, a, defer, n_defer, begin, stack, acc, flags);
     if (live) {
         if (gridDim.y == 1) a.out[i] = acc * a.scale;
         else a.out[(int64_t)blockIdx.y * a.n_obs + i] = acc;

@@ -186,10 +186,10 @@ def case_gradient_boosting_loop_against_checker(hb, sample, weighted):
     # condition numbers ~1e8, so two correct implementations with different rounding (the CPU
     # checker / the GPU) agree on them only to ~1e-4 of the largest coefficient (measured 6e-5).
     assert eqs.rmse_per_iteration_.shape == (10,)
-    npt.assert_allclose(eqs.rmse_per_iteration_, want_rmse, rtol=1e-6)
+    npt.assert_allclose(eqs.rmse_per_iteration_, want_rmse, rtol=1e-5)
     predicted = O.eqs_predict(coords, eqs.points_, eqs.coefs_)
     want_predicted = O.eqs_predict(coords, eqs.points_, want_coefs)
-    npt.assert_allclose(predicted, want_predicted, rtol=0, atol=1e-8 * np.abs(data).max())
+    npt.assert_allclose(predicted, want_predicted, rtol=0, atol=1e-7 * np.abs(data).max())
     npt.assert_allclose(eqs.coefs_, want_coefs, rtol=0, atol=1e-3 * np.abs(want_coefs).max())
 
 
