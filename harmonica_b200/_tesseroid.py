@@ -141,6 +141,30 @@ def check_points_outside_tesseroids(coordinates, tesseroids):
     raise ValueError(err_msg)
 
 
+def _locality_order(longitude, latitude):
+    """
+    Permutation that puts computation points that are close on the sphere next to each other
+    (Morton order of longitude / latitude quantised to 16 bits). The 32 observers of a warp then
+    split the same tesseroids, so their discretisation walks run in lockstep; the results do not
+    depend on the order of the observers.
+    """
+    def spread(v):  # interleave 16 bits with zeros
+        v = v.astype(np.uint64)
+        v = (v | (v << np.uint64(8))) & np.uint64(0x00FF00FF)
+        v = (v | (v << np.uint64(4))) & np.uint64(0x0F0F0F0F)
+        v = (v | (v << np.uint64(2))) & np.uint64(0x33333333)
+        v = (v | (v << np.uint64(1))) & np.uint64(0x55555555)
+        return v
+
+    lon = np.mod(longitude, 360.0)
+    lat = np.clip(latitude, -90.0, 90.0) + 90.0
+    with np.errstate(invalid="ignore"):
+        qx = np.nan_to_num(lon * (65535.0 / 360.0)).astype(np.int64)
+        qy = np.nan_to_num(lat * (65535.0 / 180.0)).astype(np.int64)
+    key = spread(np.clip(qx, 0, 65535)) | (spread(np.clip(qy, 0, 65535)) << np.uint64(1))
+    return np.argsort(key, kind="stable")
+
+
 def tesseroid_gravity(
     coordinates,
     tesseroids,
@@ -153,10 +177,14 @@ def tesseroid_gravity(
     disable_checks=False,
     *,
     shard="auto",
+    sort_observers=True,
 ):
     """
     Gravitational potential (J/kg) or downward acceleration ``g_z`` (mGal) of tesseroids on
     computation points given as (longitude, latitude, radius) in degrees and metres.
+
+    ``sort_observers`` (extension): hand the computation points to the device in a locality
+    preserving order (and return the result in the caller's order); it only affects speed.
 
     ``parallel`` and ``progressbar`` are accepted for signature compatibility (the device is
     always parallel; one launch reports no intermediate progress). All arithmetic is float64 and
@@ -183,6 +211,10 @@ def tesseroid_gravity(
     tesseroids, density = _discard_null_tesseroids(tesseroids, density)
     tesseroids, density = _lib.f64(tesseroids), _lib.f64(density)
     lib = _lib.ensure_init()
+    order = None
+    if sort_observers and coords[0].size >= 2048:
+        order = _locality_order(coords[0], coords[1])
+        coords = tuple(np.ascontiguousarray(c[order]) for c in coords)
     out = np.empty(coords[0].size, dtype=np.float64)
     flags = ctypes.c_uint32(0)
     _lib.check(
@@ -204,4 +236,8 @@ def tesseroid_gravity(
         raise OverflowError(
             "Exceeded maximum discretizations. Please increase the MAX_DISCRETIZATIONS."
         )
+    if order is not None:
+        unsorted = np.empty_like(out)
+        unsorted[order] = out
+        out = unsorted
     return out.astype(dtype, copy=False).reshape(shape)

@@ -458,3 +458,69 @@ def test_deferred_algorithm_flags():
     R = MEAN_RADIUS
     _, _, flags = harness_tesseroid_deferred([0, 0, R], [-1.0, 1.0, -1.0, 1.0, R - 1000, R], 2670.0, "g_z", True)
     assert flags & 2  # numba's ZeroDivisionError, found while walking the deferred pair
+
+
+# ------------------------------------------------------------------ wrapper logic without a device
+class _StandInLibrary:
+    """The two tesseroid entry points of libharmonica_b200.so answered by the host build of the
+    same pair function: lets the CPU suite run the wrapper's own logic (checks, null discard,
+    observer ordering, flags -> exceptions, dtype / shape handling)."""
+
+    def hb200_num_devices(self):
+        return 1
+
+    @staticmethod
+    def _array(pointer, count):
+        return np.ctypeslib.as_array(pointer, shape=(count,)).copy() if count else np.zeros(0)
+
+    def hb200_tesseroid_gravity(self, lon, lat, rad, n, tess, rho, n_tess, field, radial, shard, out, flags):
+        result = np.ctypeslib.as_array(out, shape=(n,))
+        if n_tess == 0:
+            result[:] = 0.0
+            return 0
+        tesseroids = self._array(tess, n_tess * 6).reshape(n_tess, 6)
+        got, _, flag_bits = harness_tesseroid_deferred(
+            (self._array(lon, n), self._array(lat, n), self._array(rad, n)), tesseroids,
+            self._array(rho, n_tess), {0: "potential", 3: "g_z"}[field], radial)  # fmt: skip
+        result[:] = got * (-1e5 if field == 3 else 1.0)
+        flags._obj.value = flag_bits
+        return 0
+
+    def hb200_tesseroid_inside_scan(self, lon, lat, rad, n, tess, n_tess, flags):
+        from harmonica_b200._tesseroid import _conflicting_pairs
+
+        tesseroids = self._array(tess, n_tess * 6).reshape(n_tess, 6)
+        pairs = _conflicting_pairs((self._array(lon, n), self._array(lat, n), self._array(rad, n)), tesseroids)
+        flags._obj.value = 16 if pairs else 0
+        return 0
+
+
+def test_wrapper_logic_with_a_stand_in_library(monkeypatch):
+    import harmonica_b200 as hb
+    from harmonica_b200 import _lib
+
+    monkeypatch.setattr(_lib, "ensure_init", lambda: _StandInLibrary())
+    rng = np.random.default_rng(5)
+    R = MEAN_RADIUS
+    w, s = rng.uniform(-60, 50, 12), rng.uniform(-60, 50, 12)
+    tesseroids = np.stack([w, w + 8, s, s + 8, np.full(12, R - 2e4), np.full(12, R - 100.0)], axis=1)
+    tesseroids[3, 1] = tesseroids[3, 0]  # a null tesseroid
+    density = rng.uniform(2000, 3000, 12)
+    density[5] = 0.0
+    n = 3000  # above the threshold of the locality ordering
+    coords = (rng.uniform(-70, 70, n), rng.uniform(-70, 70, n), R + rng.uniform(0, 5e4, n))
+    want = O.tesseroid_gravity(coords, tesseroids, density, "g_z")
+    ordered = hb.tesseroid_gravity(coords, tesseroids, density, "g_z")
+    plain = hb.tesseroid_gravity(coords, tesseroids, density, "g_z", sort_observers=False)
+    assert np.array_equal(ordered, plain)  # the order of the observers never changes a value
+    assert np.max(np.abs(ordered - want)) <= 1e-13 * np.max(np.abs(want))
+    grid = tuple(c.reshape(50, 60) for c in coords)
+    out = hb.tesseroid_gravity(grid, tesseroids, density, "potential", dtype="float32")
+    assert out.shape == (50, 60) and out.dtype == np.float32
+    with pytest.raises(ValueError, match=re.escape("Found computation point(s) inside tesseroid(s)")):
+        hb.tesseroid_gravity([w[0] + 4, s[0] + 4, R - 1e4], tesseroids, density, "g_z")
+    with pytest.raises(ZeroDivisionError):
+        hb.tesseroid_gravity([0, 0, R], [-1.0, 1.0, -1.0, 1.0, R - 1000, R], 2670.0, "g_z",
+                             radial_adaptive_discretization=True)  # fmt: skip
+    with pytest.raises(ValueError, match=re.escape("Number of elements in density (2) mismatch")):
+        hb.tesseroid_gravity([0, 0, R + 10], tesseroids, [1.0, 2.0], "g_z")
