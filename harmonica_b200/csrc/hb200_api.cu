@@ -1282,6 +1282,13 @@ int hb200_eqs_fit_gb(const double* easting, const double* northing, const double
         max_jac = std::max(max_jac, (size_t)np * (size_t)nd);
     }
     const int64_t n_si = src_offset[n_windows], n_di = data_offset[n_windows];
+    // the gather / scatter kernels trust the index lists: check them here, on the host
+    for (int64_t k = 0; k < n_si; k++)
+        if (src_index[k] < 0 || src_index[k] >= n_src)
+            return fail(HB200_EINVAL, "source index %lld out of range", (long long)src_index[k]);
+    for (int64_t k = 0; k < n_di; k++)
+        if (data_index[k] < 0 || data_index[k] >= n_obs)
+            return fail(HB200_EINVAL, "data index %lld out of range", (long long)data_index[k]);
     Dev& dev = g_devs[0];
     CU(cudaSetDevice(dev.id));
     const int64_t n_blocks = (n_obs + 255) / 256;
