@@ -521,7 +521,7 @@ int dipole_magnetic_dev_impl(const double* oe, const double* on, const double* o
 }
 
 // tesseroid_gravity: one field per pass (potential or g_z); workspace = [packed][partials]
-int g_tess_variant = 1;  // 1: root records + deferred walks (default); 0: first build
+int g_tess_variant = 2;  // 0: first build; 1: root records + deferred walks; 2: 1 + fast far field
 
 size_t tesseroid_ws_bytes(int64_t n_obs, int64_t n_src, int sms)
 {
@@ -547,9 +547,12 @@ int tesseroid_dev_impl(const double* lon, const double* lat, const double* rad, 
     if (variant == 0)
         pack_tesseroids_kernel<<<(unsigned)((n_tess + 255) / 256), 256, 0, st>>>(tesseroids, density,
                                                                                 n_tess, packed);
-    else
+    else if (variant == 1)
         pack_tesseroid_records_kernel<<<(unsigned)((n_tess + 127) / 128), 128, 0, st>>>(
             tesseroids, density, n_tess, packed);
+    else
+        pack_tesseroid_fast_records_kernel<<<(unsigned)((n_tess + 127) / 128), 128, 0, st>>>(
+            tesseroids, density, n_tess, field == F_POT ? 1.0 : 2.5, radial, packed);
     CU(cudaGetLastError());
     double* partial = (double*)(ws.base + ws.used);
     const size_t partial_bytes = ws.left();
@@ -573,9 +576,12 @@ int tesseroid_dev_impl(const double* lon, const double* lat, const double* rad, 
     if (variant == 0) {
         if (field == F_POT) tesseroid_kernel<F_POT><<<grid, kTessBlock, 0, st>>>(a);
         else tesseroid_kernel<F_U><<<grid, kTessBlock, 0, st>>>(a);
+    } else if (variant == 1) {
+        if (field == F_POT) tesseroid_deferred_kernel<F_POT, false><<<grid, kTessBlock, 0, st>>>(a);
+        else tesseroid_deferred_kernel<F_U, false><<<grid, kTessBlock, 0, st>>>(a);
     } else {
-        if (field == F_POT) tesseroid_deferred_kernel<F_POT><<<grid, kTessBlock, 0, st>>>(a);
-        else tesseroid_deferred_kernel<F_U><<<grid, kTessBlock, 0, st>>>(a);
+        if (field == F_POT) tesseroid_deferred_kernel<F_POT, true><<<grid, kTessBlock, 0, st>>>(a);
+        else tesseroid_deferred_kernel<F_U, true><<<grid, kTessBlock, 0, st>>>(a);
     }
     CU(cudaGetLastError());
     g_launches += chunks > 1 ? 3 : 2;
@@ -835,7 +841,7 @@ int hb200_set_variant(int variant)
 int hb200_get_variant(void) { return g_variant; }
 int hb200_set_tesseroid_variant(int variant)
 {
-    if (variant < 0 || variant > 1) return fail(HB200_EINVAL, "tesseroid variant must be 0 or 1");
+    if (variant < 0 || variant > 2) return fail(HB200_EINVAL, "tesseroid variant must be 0, 1 or 2");
     g_tess_variant = variant;
     return HB200_OK;
 }

@@ -23,12 +23,13 @@
 //     tesseroid by the pack kernel with the same statements (tess_pack_record) instead of once
 //     per pair: 98 % of the pairs of a typical model never split, for them the pair loop is left
 //     with three cosines, nine square roots and the divisions;
-//   * (kernel variant 1) pairs that do split are deferred and walked later by all lanes of the warp
+//   * (kernel variants 1, 2) pairs that do split are deferred and walked later by all lanes of the warp
 //     concurrently, each lane through its own list, instead of one lane at a time while the
 //     others wait (the first build ran with 19.8 of 32 lanes active, profiles/).
 // Only the ORDER in which a thread adds its pairs changes with the last item.
 #pragma once
 #include "hb200_math.cuh"
+#include "hb200_xmath.cuh"
 
 namespace hb {
 
@@ -65,6 +66,7 @@ constexpr double kDeg2Rad = kPi / 180.0;  // np.radians multiplies by pi / 180
 struct TessObs {
     double lon, lat, rad;      // degrees, degrees, metres (as given)
     double lam, cphi, sphi;    // radians(lon), cos / sin of radians(lat)
+    double clam, slam;         // cos / sin of lam (fast root path only)
 };
 
 HB_HD void tess_make_obs(TessObs& o, double lon, double lat, double rad)
@@ -76,6 +78,8 @@ HB_HD void tess_make_obs(TessObs& o, double lon, double lat, double rad)
     const double phi = lat * kDeg2Rad;
     o.cphi = cos(phi);
     o.sphi = sin(phi);
+    o.clam = cos(o.lam);
+    o.slam = sin(o.lam);
 }
 
 // ---- the observer-independent parts of one tesseroid -----------------------------------------
@@ -330,6 +334,96 @@ HB_HD int tess_root(const TessObs& o, const double* rec, double ratio, bool radi
     return 1;
 }
 
+// ---- fast root record (kernel variant 2) ------------------------------------------------------------
+// For the pairs whose ROOT does not split (the far field: almost all pairs) nothing but arithmetic
+// is left: cos(lam_p - lam) = cos lam_p cos lam + sin lam_p sin lam with both factors precomputed
+// (per tesseroid here, per observer in TessObs), the split test compares the squared distance with
+// precomputed (ratio * size)^2, 1 / distance is the library's reciprocal square root (hb200_xmath),
+// and G (and the sign) is folded into the node masses. These change roundings in the last place
+// (the cosine of the difference carries ~1.5e-16 absolute error instead of cos()'s 0.6e-16, the
+// same class as the reference's own cos(psi)), not the algorithm; pairs that split are walked with
+// the exact statements as before. Record:
+// [0..5] w e s n bottom top  [6] density  [7..9] (ratio l_lon)^2 (ratio l_lat)^2 (ratio l_rad)^2
+// (negative where that direction never splits)  [10,11] centre cos / sin lam  [12,13] centre
+// cphi sphi  [14] centre rad  [15,16] node cos lam  [17,18] node sin lam  [19,20] node cphi
+// [21,22] node sphi  [23,24] node rad  [25..28] G * mass[j][k]  [29] 1 if a dimension is zero
+HB_HD void tess_pack_record_fast(double* rec, const double* tess, double density, double ratio,
+                                 bool radial)
+{
+#pragma unroll
+    for (int c = 0; c < 6; c++) rec[c] = tess[c];
+    rec[6] = density;
+    TessDims d;
+    tess_dims(d, tess[0], tess[1], tess[2], tess[3], tess[4], tess[5]);
+    const double t_lon = ratio * d.l_lon, t_lat = ratio * d.l_lat, t_rad = ratio * d.l_rad;
+    rec[7] = t_lon * t_lon;  // NaN sizes give NaN thresholds: "distance < NaN" is false, no split
+    rec[8] = t_lat * t_lat;
+    rec[9] = radial ? t_rad * t_rad : -1.0;
+    rec[29] = (d.l_lon == 0.0 || d.l_lat == 0.0 || d.l_rad == 0.0) ? 1.0 : 0.0;
+    TessCentre c;
+    tess_centre(c, tess[0], tess[1], tess[2], tess[3], tess[4], tess[5]);
+    rec[10] = cos(c.lam); rec[11] = sin(c.lam);
+    rec[12] = c.cphi; rec[13] = c.sphi; rec[14] = c.rad;
+    TessNodes q;
+    tess_nodes(q, tess[0], tess[1], tess[2], tess[3], tess[4], tess[5], density);
+    rec[15] = cos(q.lam[0]); rec[16] = cos(q.lam[1]);
+    rec[17] = sin(q.lam[0]); rec[18] = sin(q.lam[1]);
+    rec[19] = q.cphi[0]; rec[20] = q.cphi[1];
+    rec[21] = q.sphi[0]; rec[22] = q.sphi[1];
+    rec[23] = q.rad[0]; rec[24] = q.rad[1];
+    rec[25] = kG * q.mass[0][0]; rec[26] = kG * q.mass[0][1];
+    rec[27] = kG * q.mass[1][0]; rec[28] = kG * q.mass[1][1];
+    rec[30] = 0.0; rec[31] = 0.0;
+}
+
+// Same contract as tess_root, on a fast record.
+template <int FIELD>
+HB_HD int tess_root_fast(const TessObs& o, const double* rec, double& acc, unsigned& flags)
+{
+    if (rec[29] != 0.0) {
+        flags |= FLAG_ZERO_DIV;
+        return -1;
+    }
+    const double two_r = 2 * o.rad;
+    {
+        const double coslambda = fma(rec[10], o.clam, rec[11] * o.slam);
+        const double cospsi = fma(rec[12] * o.cphi, coslambda, rec[13] * o.sphi);
+        const double dr = o.rad - rec[14];
+        const double d2 = fma(two_r * rec[14], 1 - cospsi, dr * dr);
+        if (d2 < rec[7] || d2 < rec[8] || d2 < rec[9]) return 0;
+    }
+    double coslambda[2];
+#pragma unroll
+    for (int i = 0; i < 2; i++) coslambda[i] = fma(rec[15 + i], o.clam, rec[17 + i] * o.slam);
+    double result = 0.0;
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        const double a = rec[21 + j] * o.sphi, b = rec[19 + j] * o.cphi;
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const double radius_p = rec[23 + k];
+            const double dr = o.rad - radius_p;
+            const double dr2 = dr * dr, rr = two_r * radius_p;
+            const double mass = rec[25 + 2 * j + k];
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                const double cospsi = fma(b, coslambda[i], a);
+                const double d2 = fma(rr, 1 - cospsi, dr2);
+                if (d2 == 0.0) flags |= FLAG_ZERO_DIV;  // observer on a quadrature node
+                const double inv = fast_rsqrt(d2);
+                if (FIELD == F_POT) {
+                    result = fma(mass, inv, result);
+                } else {
+                    const double delta_z = fma(-radius_p, cospsi, o.rad);
+                    result = fma(-mass * delta_z, inv * inv * inv, result);
+                }
+            }
+        }
+    }
+    acc += result;
+    return 1;
+}
+
 #if defined(__CUDACC__)
 // ------------------------------------------------------------------ kernels
 // plain records (the inside scan and kernel variant 0)
@@ -357,6 +451,19 @@ __global__ void pack_tesseroid_records_kernel(const double* __restrict__ tessero
 #pragma unroll
     for (int c = 0; c < 6; c++) t[c] = tesseroids[j * 6 + c];
     tess_pack_record(packed + j * kTessRec, t, density[j]);
+}
+
+__global__ void pack_tesseroid_fast_records_kernel(const double* __restrict__ tesseroids,
+                                                   const double* __restrict__ density, int64_t n,
+                                                   double ratio, int radial,
+                                                   double* __restrict__ packed)
+{
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    double t[6];
+#pragma unroll
+    for (int c = 0; c < 6; c++) t[c] = tesseroids[j * 6 + c];
+    tess_pack_record_fast(packed + j * kTessRec, t, density[j], ratio, radial != 0);
 }
 
 struct TessArgs {
@@ -440,11 +547,11 @@ __device__ __forceinline__ void tess_walk_deferred(const TessObs& o, const TessA
     n_defer = 0;
 }
 
-// Variant 1 (default): root records + deferred walks. The loop over a tile is uniform (root
+// Variants 1 and 2 (FAST): root records + deferred walks. The loop over a tile is uniform (root
 // decision from the record, unsplit pairs integrated at once, three cosines per pair); a pair
 // that splits is only noted. When any lane of the warp has kTessDefer pairs noted, and at the
 // end, all lanes walk their lists together.
-template <int FIELD>
+template <int FIELD, bool FAST>
 __global__ void __launch_bounds__(kTessBlock) tesseroid_deferred_kernel(const TessArgs a)
 {
     __shared__ double tile[kTessTile * kTessRec];
@@ -467,8 +574,11 @@ __global__ void __launch_bounds__(kTessBlock) tesseroid_deferred_kernel(const Te
             tile[x] = a.packed[t0 * kTessRec + x];
         __syncthreads();
         for (int s = 0; s < cnt; s++) {
-            if (live && tess_root<FIELD>(o, tile + s * kTessRec, a.ratio, a.radial != 0, acc, flags) == 0)
-                defer[n_defer++] = (int)(t0 - begin) + s;
+            int root = 1;
+            if (live)
+                root = FAST ? tess_root_fast<FIELD>(o, tile + s * kTessRec, acc, flags)
+                            : tess_root<FIELD>(o, tile + s * kTessRec, a.ratio, a.radial != 0, acc, flags);
+            if (root == 0) defer[n_defer++] = (int)(t0 - begin) + s;
             if (__any_sync(0xffffffffu, n_defer == kTessDefer))
                 tess_walk_deferred<FIELD>(o, a, defer, n_defer, begin, stack, acc, flags);
         }

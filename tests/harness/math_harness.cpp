@@ -115,12 +115,18 @@ void hbt_tesseroid_loop(int field, int64_t n_obs, const double* lon, const doubl
 // of them are pending and at the end (one lane, so no warp vote). leaves: leaves per pair.
 void hbt_tesseroid_loop_deferred(int field, int64_t n_obs, const double* lon, const double* lat,
                                  const double* rad, int64_t n_tess, const double* tesseroids,
-                                 const double* density, int radial, int defer_cap, double* out,
-                                 int64_t* counts, unsigned* flags)
+                                 const double* density, int radial, int defer_cap, int fast,
+                                 double* out, int64_t* counts, unsigned* flags)
 {
     double stack[kTessStack * 6];
     double* records = new double[(size_t)(n_tess > 0 ? n_tess : 1) * kTessRec];
-    for (int64_t j = 0; j < n_tess; j++) tess_pack_record(records + j * kTessRec, tesseroids + 6 * j, density[j]);
+    for (int64_t j = 0; j < n_tess; j++) {
+        if (fast)
+            tess_pack_record_fast(records + j * kTessRec, tesseroids + 6 * j, density[j],
+                                  field == F_POT ? 1.0 : 2.5, radial != 0);
+        else
+            tess_pack_record(records + j * kTessRec, tesseroids + 6 * j, density[j]);
+    }
     int64_t* defer = new int64_t[defer_cap > 0 ? defer_cap : 1];
     unsigned f = 0;
     const double ratio = field == F_POT ? 1.0 : 2.5;
@@ -141,8 +147,10 @@ void hbt_tesseroid_loop_deferred(int field, int64_t n_obs, const double* lon, co
         };
         for (int64_t j = 0; j < n_tess; j++) {
             const double* rec = records + j * kTessRec;
-            const int r = field == F_POT ? tess_root<F_POT>(o, rec, ratio, radial != 0, acc, f)
-                                         : tess_root<F_U>(o, rec, ratio, radial != 0, acc, f);
+            int r;
+            if (fast) r = field == F_POT ? tess_root_fast<F_POT>(o, rec, acc, f) : tess_root_fast<F_U>(o, rec, acc, f);
+            else r = field == F_POT ? tess_root<F_POT>(o, rec, ratio, radial != 0, acc, f)
+                                    : tess_root<F_U>(o, rec, ratio, radial != 0, acc, f);
             if (counts) counts[i * n_tess + j] = r == 1 ? 1 : 0;
             if (r == 0) defer[n_defer++] = j;
             if (n_defer == defer_cap) walk();

@@ -24,13 +24,17 @@ from test_tesseroid_host import (MEAN_RADIUS, MODES, _cases, _key, _shell, _shel
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=[1, 0], ids=["deferred", "plain"])
+DEFAULT_VARIANT = 2
+
+
+@pytest.fixture(params=[2, 1, 0], ids=["fast", "deferred", "plain"])
 def tess_variant(request, hb):
-    """both tesseroid kernels: 1 = root records + deferred walks (default), 0 = first build"""
+    """the tesseroid kernels: 2 = root records + deferred walks + arithmetic-only far field
+    (default), 1 = without the fast far field, 0 = first build"""
     lib = hb._lib.load()
     assert lib.hb200_set_tesseroid_variant(request.param) == 0
     yield request.param
-    lib.hb200_set_tesseroid_variant(1)
+    lib.hb200_set_tesseroid_variant(DEFAULT_VARIANT)
 
 
 @pytest.mark.parametrize("field,radial", MODES)
@@ -134,7 +138,7 @@ def test_errors_shapes_and_dtypes(hb):
     before = lib.hb200_launch_count()
     hb.tesseroid_gravity([0, 0, R + 10], tess, 2670.0, "potential")
     assert lib.hb200_launch_count() - before >= 3  # inside scan (pack + scan), pack + kernel
-    assert lib.hb200_get_tesseroid_variant() == 1
+    assert lib.hb200_get_tesseroid_variant() == DEFAULT_VARIANT
     assert lib.hb200_set_tesseroid_variant(7) != 0
 
 

@@ -410,7 +410,7 @@ def test_tesseroid_layer_host_logic():
 
 
 # ------------------------------------------------------------------ deferred kernel algorithm
-def harness_tesseroid_deferred(coordinates, tesseroids, density, field, radial, defer_cap=16):
+def harness_tesseroid_deferred(coordinates, tesseroids, density, field, radial, defer_cap=16, fast=False):
     """Host emulation of one thread of tesseroid_deferred_kernel (root records + deferred walks)."""
     H = harness()
     dp = ctypes.POINTER(ctypes.c_double)
@@ -424,7 +424,7 @@ def harness_tesseroid_deferred(coordinates, tesseroids, density, field, radial, 
         {"potential": 0, "g_z": 3}[field], ctypes.c_int64(lon.size), lon.ctypes.data_as(dp),
         lat.ctypes.data_as(dp), rad.ctypes.data_as(dp), ctypes.c_int64(tesseroids.shape[0]),
         tesseroids.ctypes.data_as(dp), density.ctypes.data_as(dp), int(radial), int(defer_cap),
-        out.ctypes.data_as(dp), counts.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+        int(fast), out.ctypes.data_as(dp), counts.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
         ctypes.byref(flags),
     )  # fmt: skip
     return out, counts, flags.value
@@ -524,3 +524,58 @@ def test_wrapper_logic_with_a_stand_in_library(monkeypatch):
                              radial_adaptive_discretization=True)  # fmt: skip
     with pytest.raises(ValueError, match=re.escape("Number of elements in density (2) mismatch")):
         hb.tesseroid_gravity([0, 0, R + 10], tesseroids, [1.0, 2.0], "g_z")
+
+
+# ------------------------------------------------------------------ fast far field (variant 2)
+@pytest.mark.parametrize("field,radial", MODES)
+def test_fast_far_field_matches_the_oracle(field, radial):
+    """kernel variant 2: arithmetic-only root path (product form of cos(lam_p - lam), reciprocal
+    square root, squared thresholds). Same leaves for every pair; values within the parity bar"""
+    g, cases = _cases()
+    for name in ("random", "four", "wrapped"):
+        coords, tesseroids, density = cases[name]
+        tesseroids = np.atleast_2d(np.asarray(tesseroids, dtype=float))
+        if (tesseroids[:, 0] > tesseroids[:, 1]).any():
+            tesseroids = O.longitude_continuity(tesseroids)
+        density = np.atleast_1d(np.asarray(density, dtype=float))
+        want, want_counts = O.tesseroid_gravity(coords, tesseroids, density, field, radial, return_counts=True)
+        got, counts, flags = harness_tesseroid_deferred(coords, tesseroids, density, field, radial, 64, fast=True)
+        if field == "g_z":
+            got *= -1e5
+        assert flags == 0
+        assert np.array_equal(counts, want_counts)
+        want = np.asarray(want).ravel()
+        bar = max(1e-9, 4 * reference_conditioning(coords, tesseroids, density, field, radial, trials=2))
+        assert np.max(np.abs(got - want)) <= bar * np.max(np.abs(want))
+
+
+def test_fast_far_field_accuracy_on_far_and_regional_models():
+    """far pairs are well conditioned: the fast path agrees with the oracle to ~1e-13 there; a
+    regional model of small tesseroids seen from nearby stays within the conditioning bar"""
+    rng = np.random.default_rng(12)
+    R = MEAN_RADIUS
+    w, s = rng.uniform(-170, 160, 60), rng.uniform(-80, 70, 60)
+    tesseroids = np.stack([w, w + rng.uniform(1, 10, 60), s, s + rng.uniform(1, 10, 60),
+                           R - rng.uniform(1e3, 1e5, 60), R - rng.uniform(0, 500, 60)], 1)  # fmt: skip
+    density = rng.uniform(-1000, 3000, 60)
+    coords = (rng.uniform(-180, 180, 80), rng.uniform(-90, 90, 80), R + rng.uniform(2e5, 2e6, 80))
+    for field, radial in MODES:
+        want, want_counts = O.tesseroid_gravity(coords, tesseroids, density, field, radial, return_counts=True)
+        got, counts, flags = harness_tesseroid_deferred(coords, tesseroids, density, field, radial, 64, fast=True)
+        if field == "g_z":
+            got *= -1e5
+        assert flags == 0 and np.array_equal(counts, want_counts)
+        assert np.max(np.abs(got - want)) <= 2e-13 * np.max(np.abs(want))
+    lon_c, lat_c = np.meshgrid(np.arange(-0.95, 1, 0.1), np.arange(-0.95, 1, 0.1))
+    small = np.stack([lon_c.ravel() - 0.05, lon_c.ravel() + 0.05, lat_c.ravel() - 0.05, lat_c.ravel() + 0.05,
+                      np.full(lon_c.size, R - 2e3), np.full(lon_c.size, R)], 1)  # fmt: skip
+    rho = np.full(lon_c.size, 2670.0)
+    near = (rng.uniform(-1, 1, 60), rng.uniform(-1, 1, 60), R + rng.uniform(50, 5e3, 60))
+    for field in ("potential", "g_z"):
+        want, want_counts = O.tesseroid_gravity(near, small, rho, field, return_counts=True)
+        got, counts, flags = harness_tesseroid_deferred(near, small, rho, field, False, 64, fast=True)
+        if field == "g_z":
+            got *= -1e5
+        bar = max(1e-9, 4 * reference_conditioning(near, small, rho, field, False, trials=2))
+        assert flags == 0 and np.array_equal(counts, want_counts)
+        assert np.max(np.abs(got - want)) <= bar * np.max(np.abs(want)), (field, bar)
