@@ -86,11 +86,11 @@ const char* hb200_last_error(void);
  * division / sqrt / log / atan2 sequences (hb200_xmath.cuh) */
 int hb200_set_variant(int variant);
 int hb200_get_variant(void);
-/* tesseroid kernels: 1 (default) = observer-independent parts of every tesseroid precomputed
- * into root records, pairs that split deferred and walked by all lanes of a warp together;
- * 2 = as 1 with an arithmetic-only far field (cosine of the longitude difference from
- * precomputed factors, the library's reciprocal square root, squared split thresholds);
- * 0 = first build (every pair walked where it is met) */
+/* tesseroid kernels: 1 = observer-independent parts of every tesseroid precomputed into root
+ * records, pairs that split deferred and walked by all lanes of a warp together; 2 (default) =
+ * as 1 with an arithmetic-only far field (cosine of the longitude difference from precomputed
+ * factors, the library's reciprocal square root, squared split thresholds); 0 = first build
+ * (every pair walked where it is met) */
 int hb200_set_tesseroid_variant(int variant);
 int hb200_get_tesseroid_variant(void);
 /* number of CUDA kernels this library has launched so far (all entry points) */
