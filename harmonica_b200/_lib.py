@@ -77,6 +77,8 @@ SIGNATURES = {
                _i64p, _i64p, _i64p, _i64p, _dp, _dp]),
     "hb200_tesseroid_gravity": (
         _int, [_dp, _dp, _dp, _i64, _dp, _dp, _i64, _int, _int, _int, _dp, _u32p]),
+    "hb200_tesseroid_gravity_variable_density": (
+        _int, [_dp, _dp, _dp, _i64, _dp, _dp, _dp, _i64, _int, _int, _dp, _u32p]),
     "hb200_tesseroid_inside_scan": (_int, [_dp, _dp, _dp, _i64, _dp, _i64, _u32p]),
     "hb200_tesseroid_ws_bytes": (_sz, [_i64, _i64]),
     "hb200_tesseroid_gravity_dev": (

@@ -7,8 +7,10 @@ for constant densities: same signature, checks, error messages, units and signs.
 in ``libharmonica_b200.so`` (``hb200_tesseroid_gravity``); the O(N x P) "points outside
 tesseroids" check (``_tesseroid_utils.py:398-454``) is a device scan as well.
 
-Not provided: densities given as a numba-jitted function (``_tesseroid_variable_density.py``);
-a Python callable cannot run inside the CUDA kernel.
+``density`` may also be a function of the radius (variable-density tesseroids, [Soler2019]_):
+see ``_tesseroid_density.py``. Not provided: a density function together with
+``radial_adaptive_discretization=True`` (the leaves then have their own radial nodes, at which a
+Python callable cannot be evaluated from inside the CUDA kernel).
 """
 
 import ctypes
@@ -16,6 +18,7 @@ import ctypes
 import numpy as np
 
 from . import _lib
+from ._tesseroid_density import density_at_radial_nodes, density_based_discretization
 from ._utils import broadcast_coordinates
 
 _FIELDS = {"potential": 0, "g_z": 3}
@@ -206,23 +209,31 @@ def tesseroid_gravity(
     """
     if field not in _FIELDS:
         raise ValueError(f"Gravitational field {field} not recognized")
-    if callable(density):
+    if callable(density) and radial_adaptive_discretization:
         raise NotImplementedError(
-            "harmonica_b200.tesseroid_gravity needs constant densities: a density function "
-            "(variable-density tesseroids) cannot run inside the CUDA kernel"
+            "harmonica_b200.tesseroid_gravity evaluates a density function on the host, at the "
+            "radial quadrature nodes of every tesseroid; with radial_adaptive_discretization=True "
+            "the leaves have their own radial nodes, which only the CUDA kernel knows"
         )
     shape, coords = broadcast_coordinates(coordinates)
     tesseroids = np.atleast_2d(np.asarray(tesseroids, dtype=np.float64))
     if not disable_checks:
         tesseroids = _check_tesseroids(tesseroids)
         check_points_outside_tesseroids(coords, tesseroids)
-    density = np.atleast_1d(density).ravel()
-    if not disable_checks and density.size != tesseroids.shape[0]:
-        raise ValueError(
-            f"Number of elements in density ({density.size}) "
-            + f"mismatch the number of tesseroids ({tesseroids.shape[0]})"
-        )
-    tesseroids, density = _discard_null_tesseroids(tesseroids, density)
+    if callable(density):
+        # tesseroid_gravity.py:182-183: radial pieces in which the density is close to linear,
+        # then density(radius_p) at the two radial quadrature nodes of every piece
+        tesseroids = density_based_discretization(tesseroids, density)
+        density, density_upper = density_at_radial_nodes(tesseroids, density)
+    else:
+        density = np.atleast_1d(density).ravel()
+        if not disable_checks and density.size != tesseroids.shape[0]:
+            raise ValueError(
+                f"Number of elements in density ({density.size}) "
+                + f"mismatch the number of tesseroids ({tesseroids.shape[0]})"
+            )
+        tesseroids, density = _discard_null_tesseroids(tesseroids, density)
+        density_upper = None
     tesseroids, density = _lib.f64(tesseroids), _lib.f64(density)
     lib = _lib.ensure_init()
     order = None
@@ -231,14 +242,21 @@ def tesseroid_gravity(
         coords = tuple(np.ascontiguousarray(c[order]) for c in coords)
     out = np.empty(coords[0].size, dtype=np.float64)
     flags = ctypes.c_uint32(0)
-    _lib.check(
-        lib.hb200_tesseroid_gravity(
+    if density_upper is None:
+        rc = lib.hb200_tesseroid_gravity(
             _lib.ptr(coords[0]), _lib.ptr(coords[1]), _lib.ptr(coords[2]), coords[0].size,
             _lib.ptr(tesseroids), _lib.ptr(density), tesseroids.shape[0], _FIELDS[field],
             int(bool(radial_adaptive_discretization)), _lib.shard_mode(shard), _lib.ptr(out),
             ctypes.byref(flags),
         )  # fmt: skip
-    )
+    else:
+        density_upper = _lib.f64(density_upper)
+        rc = lib.hb200_tesseroid_gravity_variable_density(
+            _lib.ptr(coords[0]), _lib.ptr(coords[1]), _lib.ptr(coords[2]), coords[0].size,
+            _lib.ptr(tesseroids), _lib.ptr(density), _lib.ptr(density_upper), tesseroids.shape[0],
+            _FIELDS[field], _lib.shard_mode(shard), _lib.ptr(out), ctypes.byref(flags),
+        )  # fmt: skip
+    _lib.check(rc)
     # the reference raises from inside the jitted loop: numba's float division raises on a zero
     # divisor (a computation point on a corner that 3-D discretisation splits without end, or
     # on a quadrature node); _tesseroid_utils.py:192-207 raise OverflowError

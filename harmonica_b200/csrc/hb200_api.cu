@@ -529,10 +529,12 @@ size_t tesseroid_ws_bytes(int64_t n_obs, int64_t n_src, int sms)
          + partial_bytes_for(n_obs, n_src, 1, kTessBlock, sms) + 256;
 }
 
+// density0 / density1: density at the lower / upper radial quadrature node of every tesseroid
+// (the same array twice for homogeneous tesseroids)
 int tesseroid_dev_impl(const double* lon, const double* lat, const double* rad, int64_t n_obs,
-                       const double* tesseroids, const double* density, int64_t n_tess, int field,
-                       int radial, bool raw, double* out, unsigned* d_flags, void* wsp,
-                       size_t ws_bytes, int sms, cudaStream_t st)
+                       const double* tesseroids, const double* density0, const double* density1,
+                       int64_t n_tess, int field, int radial, bool raw, double* out,
+                       unsigned* d_flags, void* wsp, size_t ws_bytes, int sms, cudaStream_t st)
 {
     if (field != F_POT && field != F_U) return fail(HB200_EINVAL, "tesseroids: potential or g_z only");
     Ws ws(wsp, ws_bytes);
@@ -545,14 +547,14 @@ int tesseroid_dev_impl(const double* lon, const double* lat, const double* rad, 
         return HB200_OK;
     }
     if (variant == 0)
-        pack_tesseroids_kernel<<<(unsigned)((n_tess + 255) / 256), 256, 0, st>>>(tesseroids, density,
-                                                                                n_tess, packed);
+        pack_tesseroids_kernel<<<(unsigned)((n_tess + 255) / 256), 256, 0, st>>>(
+            tesseroids, density0, density1, n_tess, packed);
     else if (variant == 1)
         pack_tesseroid_records_kernel<<<(unsigned)((n_tess + 127) / 128), 128, 0, st>>>(
-            tesseroids, density, n_tess, packed);
+            tesseroids, density0, density1, n_tess, packed);
     else
         pack_tesseroid_fast_records_kernel<<<(unsigned)((n_tess + 127) / 128), 128, 0, st>>>(
-            tesseroids, density, n_tess, field == F_POT ? 1.0 : 2.5, radial, packed);
+            tesseroids, density0, density1, n_tess, field == F_POT ? 1.0 : 2.5, radial, packed);
     CU(cudaGetLastError());
     double* partial = (double*)(ws.base + ws.used);
     const size_t partial_bytes = ws.left();
@@ -1105,28 +1107,50 @@ int hb200_dipole_magnetic(const double* easting, const double* northing, const d
                         out, flags, launch, ws_dipole);
 }
 
-int hb200_tesseroid_gravity(const double* longitude, const double* latitude, const double* radius,
-                            int64_t n_obs, const double* tesseroids, const double* density,
-                            int64_t n_tesseroids, int field, int radial_adaptive_discretization,
-                            int shard_mode, double* out, uint32_t* flags)
+static int tesseroid_gravity_host(const double* longitude, const double* latitude,
+                                  const double* radius, int64_t n_obs, const double* tesseroids,
+                                  const double* density0, const double* density1,
+                                  int64_t n_tesseroids, int field, int radial, int shard_mode,
+                                  double* out, uint32_t* flags)
 {
     if (field != HB200_POTENTIAL && field != HB200_G_Z)
         return fail(HB200_EINVAL, "tesseroid_gravity computes the potential or g_z, not field %d", field);
     if (n_obs < 0 || n_tesseroids < 0) return fail(HB200_EINVAL, "negative size");
     std::vector<HostArray> arrays = {{tesseroids, n_tesseroids, 6, true},
-                                     {density, n_tesseroids, 1, true}};
+                                     {density0, n_tesseroids, 1, true},
+                                     {density1, n_tesseroids, 1, true}};
     auto launch = [=](Dev& dev, const double* oe, const double* on, const double* ou, int64_t no,
                       std::vector<double*>& arr, int64_t ns, bool raw, double* d_out, void* ws,
                       size_t wsb) {
-        return tesseroid_dev_impl(oe, on, ou, no, arr[0], arr[1], ns, field,
-                                  radial_adaptive_discretization, raw, d_out, dev.d_flags, ws, wsb,
-                                  dev.sms, dev.st);
+        return tesseroid_dev_impl(oe, on, ou, no, arr[0], arr[1], arr[2], ns, field, radial, raw,
+                                  d_out, dev.d_flags, ws, wsb, dev.sms, dev.st);
     };
     Scales sc;
     for (int c = 0; c < 6; c++) sc.s[c] = 1.0;
     sc.s[0] = field == HB200_G_Z ? -1e5 : 1.0;
     return run_host_job(longitude, latitude, radius, n_obs, arrays, n_tesseroids, 1, shard_mode, true,
                         sc, out, flags, launch, ws_tesseroid);
+}
+
+int hb200_tesseroid_gravity(const double* longitude, const double* latitude, const double* radius,
+                            int64_t n_obs, const double* tesseroids, const double* density,
+                            int64_t n_tesseroids, int field, int radial_adaptive_discretization,
+                            int shard_mode, double* out, uint32_t* flags)
+{
+    return tesseroid_gravity_host(longitude, latitude, radius, n_obs, tesseroids, density, density,
+                                  n_tesseroids, field, radial_adaptive_discretization, shard_mode,
+                                  out, flags);
+}
+
+int hb200_tesseroid_gravity_variable_density(const double* longitude, const double* latitude,
+                                             const double* radius, int64_t n_obs,
+                                             const double* tesseroids, const double* density_lower,
+                                             const double* density_upper, int64_t n_tesseroids,
+                                             int field, int shard_mode, double* out,
+                                             uint32_t* flags)
+{
+    return tesseroid_gravity_host(longitude, latitude, radius, n_obs, tesseroids, density_lower,
+                                  density_upper, n_tesseroids, field, 0, shard_mode, out, flags);
 }
 
 int hb200_tesseroid_inside_scan(const double* longitude, const double* latitude,
@@ -1146,7 +1170,7 @@ int hb200_tesseroid_inside_scan(const double* longitude, const double* latitude,
         if (!packed) return fail(HB200_EINVAL, "workspace too small");
         // the density slot of the record is not read by the scan
         pack_tesseroids_kernel<<<(unsigned)((n_tesseroids + 255) / 256), 256, 0, dev.st>>>(
-            arr[0], arr[0], n_tesseroids, packed);
+            arr[0], arr[0], arr[0], n_tesseroids, packed);
         int64_t chunk_len;
         int chunks = choose_chunks(no, n_tesseroids, 128, dev.sms, &chunk_len);
         TessArgs a;
@@ -1405,9 +1429,9 @@ int hb200_tesseroid_gravity_dev(const double* longitude, const double* latitude,
                                 double* out, uint32_t* flags_dev, void* ws, size_t ws_bytes,
                                 void* stream)
 {
-    return tesseroid_dev_impl(longitude, latitude, radius, n_obs, tesseroids, density, n_tesseroids,
-                              field, radial_adaptive_discretization, false, out, flags_dev, ws,
-                              ws_bytes, sm_count_current(), (cudaStream_t)stream);
+    return tesseroid_dev_impl(longitude, latitude, radius, n_obs, tesseroids, density, density,
+                              n_tesseroids, field, radial_adaptive_discretization, false, out,
+                              flags_dev, ws, ws_bytes, sm_count_current(), (cudaStream_t)stream);
 }
 
 int hb200_prism_gravity_dev(const double* easting, const double* northing, const double* upward,

@@ -140,9 +140,11 @@ HB_HD bool tess_split_counts(double distance, const TessDims& d, double ratio, b
     return true;
 }
 
-// the node coordinates and masses of gauss_legendre_quadrature (:19-107)
+// the node coordinates and masses of gauss_legendre_quadrature (:19-107). density[k] belongs to
+// the radial node k: equal for a homogeneous tesseroid; density(radius_p) of the variable-density
+// quadrature (_tesseroid_variable_density.py:20-106) otherwise.
 HB_HD void tess_nodes(TessNodes& q, double w, double e, double s, double n, double bottom,
-                      double top, double density)
+                      double top, const double* density)
 {
     const double a_factor = 1.0 / 8 * ((e - w) * kDeg2Rad) * ((n - s) * kDeg2Rad) * (top - bottom);
 #pragma unroll
@@ -159,7 +161,7 @@ HB_HD void tess_nodes(TessNodes& q, double w, double e, double s, double n, doub
 #pragma unroll
         for (int k = 0; k < 2; k++) {
             const double kappa = q.rad[k] * q.rad[k] * q.cphi[j];
-            q.mass[j][k] = density * a_factor * kappa;  // the three GLQ weights are 1
+            q.mass[j][k] = density[k] * a_factor * kappa;  // the three GLQ weights are 1
         }
 }
 
@@ -199,16 +201,18 @@ template <int FIELD> HB_HD double tess_glq_nodes(const TessObs& o, const TessNod
 struct TessWalk {
     int stack_top;   // < 0: no pair in progress
     int n_leaves;
-    double density;
+    double density[2];  // per radial quadrature node
 };
 
-HB_HD void tess_walk_begin(TessWalk& w, const double* tess, double density, double* stack)
+HB_HD void tess_walk_begin(TessWalk& w, const double* tess, double density0, double density1,
+                           double* stack)
 {
 #pragma unroll
     for (int c = 0; c < 6; c++) stack[c] = tess[c];
     w.stack_top = 0;
     w.n_leaves = 0;
-    w.density = density;
+    w.density[0] = density0;
+    w.density[1] = density1;
 }
 
 // One pop of _adaptive_discretization (:178-216): either pushes the children (_split_tesseroid)
@@ -270,11 +274,11 @@ HB_HD void tess_walk_step(const TessObs& o, double ratio, bool radial, double* s
 // One (observer, tesseroid) pair: adds the quadrature of every leaf of the adaptive
 // discretisation to `acc` in the reference's order. Returns the number of leaves.
 template <int FIELD, int STACK = kTessStack, int MAX_LEAVES = kTessMaxLeaves>
-HB_HD int tess_pair(const TessObs& o, const double* tess, double density, double ratio, bool radial,
-                    double* stack, double& acc, unsigned& flags)
+HB_HD int tess_pair(const TessObs& o, const double* tess, double density0, double density1,
+                    double ratio, bool radial, double* stack, double& acc, unsigned& flags)
 {
     TessWalk wk;
-    tess_walk_begin(wk, tess, density, stack);
+    tess_walk_begin(wk, tess, density0, density1, stack);
     while (wk.stack_top >= 0)
         tess_walk_step<FIELD, STACK, MAX_LEAVES>(o, ratio, radial, stack, wk, acc, flags);
     return wk.n_leaves;
@@ -283,12 +287,15 @@ HB_HD int tess_pair(const TessObs& o, const double* tess, double density, double
 // ---- root record -----------------------------------------------------------------------------------
 // [0..5] w e s n bottom top  [6] density  [7..9] l_lon l_lat l_rad
 // [10..13] centre: lam cphi sphi rad   [14,15] node lam   [16,17] node cphi   [18,19] node sphi
-// [20,21] node rad   [22..25] mass[j][k]   [26..31] unused
-HB_HD void tess_pack_record(double* rec, const double* tess, double density)
+// [20,21] node rad   [22..25] mass[j][k]   [26] density of the upper radial node ([6]: lower)
+constexpr int kTessRho1 = 26;      // slot of the second density in a root record
+constexpr int kTessRho1Fast = 30;  // ... in a fast root record
+HB_HD void tess_pack_record(double* rec, const double* tess, double density0, double density1)
 {
 #pragma unroll
     for (int c = 0; c < 6; c++) rec[c] = tess[c];
-    rec[6] = density;
+    rec[6] = density0;
+    const double density[2] = {density0, density1};
     TessDims d;
     tess_dims(d, tess[0], tess[1], tess[2], tess[3], tess[4], tess[5]);
     rec[7] = d.l_lon; rec[8] = d.l_lat; rec[9] = d.l_rad;
@@ -302,8 +309,9 @@ HB_HD void tess_pack_record(double* rec, const double* tess, double density)
     rec[18] = q.sphi[0]; rec[19] = q.sphi[1];
     rec[20] = q.rad[0]; rec[21] = q.rad[1];
     rec[22] = q.mass[0][0]; rec[23] = q.mass[0][1]; rec[24] = q.mass[1][0]; rec[25] = q.mass[1][1];
+    rec[kTessRho1] = density1;
 #pragma unroll
-    for (int c2 = 26; c2 < kTessRec; c2++) rec[c2] = 0.0;
+    for (int c2 = 27; c2 < kTessRec; c2++) rec[c2] = 0.0;
 }
 
 // The root pop of a pair from its record. Returns 1 when the root is a leaf (integrated into
@@ -347,12 +355,14 @@ HB_HD int tess_root(const TessObs& o, const double* rec, double ratio, bool radi
 // (negative where that direction never splits)  [10,11] centre cos / sin lam  [12,13] centre
 // cphi sphi  [14] centre rad  [15,16] node cos lam  [17,18] node sin lam  [19,20] node cphi
 // [21,22] node sphi  [23,24] node rad  [25..28] G * mass[j][k]  [29] 1 if a dimension is zero
-HB_HD void tess_pack_record_fast(double* rec, const double* tess, double density, double ratio,
-                                 bool radial)
+// [30] density of the upper radial node
+HB_HD void tess_pack_record_fast(double* rec, const double* tess, double density0, double density1,
+                                 double ratio, bool radial)
 {
 #pragma unroll
     for (int c = 0; c < 6; c++) rec[c] = tess[c];
-    rec[6] = density;
+    rec[6] = density0;
+    const double density[2] = {density0, density1};
     TessDims d;
     tess_dims(d, tess[0], tess[1], tess[2], tess[3], tess[4], tess[5]);
     const double t_lon = ratio * d.l_lon, t_lat = ratio * d.l_lat, t_rad = ratio * d.l_rad;
@@ -373,7 +383,8 @@ HB_HD void tess_pack_record_fast(double* rec, const double* tess, double density
     rec[23] = q.rad[0]; rec[24] = q.rad[1];
     rec[25] = kG * q.mass[0][0]; rec[26] = kG * q.mass[0][1];
     rec[27] = kG * q.mass[1][0]; rec[28] = kG * q.mass[1][1];
-    rec[30] = 0.0; rec[31] = 0.0;
+    rec[kTessRho1Fast] = density1;
+    rec[31] = 0.0;
 }
 
 // Same contract as tess_root, on a fast record.
@@ -427,8 +438,9 @@ HB_HD int tess_root_fast(const TessObs& o, const double* rec, double& acc, unsig
 #if defined(__CUDACC__)
 // ------------------------------------------------------------------ kernels
 // plain records (the inside scan and kernel variant 0)
+// density0 / density1: per radial quadrature node (the same array twice for homogeneous bodies)
 __global__ void pack_tesseroids_kernel(const double* __restrict__ tesseroids,
-                                       const double* __restrict__ density, int64_t n,
+                                       const double* density0, const double* density1, int64_t n,
                                        double* __restrict__ packed)
 {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -436,26 +448,26 @@ __global__ void pack_tesseroids_kernel(const double* __restrict__ tesseroids,
     double* q = packed + j * kTessStride;
 #pragma unroll
     for (int c = 0; c < 6; c++) q[c] = tesseroids[j * 6 + c];
-    q[6] = density[j];
-    q[7] = 0.0;
+    q[6] = density0[j];
+    q[7] = density1[j];
 }
 
 // root records: everything about a tesseroid that does not depend on the observer
 __global__ void pack_tesseroid_records_kernel(const double* __restrict__ tesseroids,
-                                              const double* __restrict__ density, int64_t n,
-                                              double* __restrict__ packed)
+                                              const double* density0, const double* density1,
+                                              int64_t n, double* __restrict__ packed)
 {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     double t[6];
 #pragma unroll
     for (int c = 0; c < 6; c++) t[c] = tesseroids[j * 6 + c];
-    tess_pack_record(packed + j * kTessRec, t, density[j]);
+    tess_pack_record(packed + j * kTessRec, t, density0[j], density1[j]);
 }
 
 __global__ void pack_tesseroid_fast_records_kernel(const double* __restrict__ tesseroids,
-                                                   const double* __restrict__ density, int64_t n,
-                                                   double ratio, int radial,
+                                                   const double* density0, const double* density1,
+                                                   int64_t n, double ratio, int radial,
                                                    double* __restrict__ packed)
 {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -463,7 +475,7 @@ __global__ void pack_tesseroid_fast_records_kernel(const double* __restrict__ te
     double t[6];
 #pragma unroll
     for (int c = 0; c < 6; c++) t[c] = tesseroids[j * 6 + c];
-    tess_pack_record_fast(packed + j * kTessRec, t, density[j], ratio, radial != 0);
+    tess_pack_record_fast(packed + j * kTessRec, t, density0[j], density1[j], ratio, radial != 0);
 }
 
 struct TessArgs {
@@ -513,7 +525,7 @@ __global__ void __launch_bounds__(kTessBlock) tesseroid_kernel(const TessArgs a)
         if (i < a.n_obs)
             for (int s = 0; s < cnt; s++) {
                 const double* rec = tile + s * kTessStride;
-                tess_pair<FIELD>(o, rec, rec[6], a.ratio, a.radial != 0, stack, acc, flags);
+                tess_pair<FIELD>(o, rec, rec[6], rec[7], a.ratio, a.radial != 0, stack, acc, flags);
             }
     }
     if (i < a.n_obs) {
@@ -526,7 +538,7 @@ __global__ void __launch_bounds__(kTessBlock) tesseroid_kernel(const TessArgs a)
 // Walk the pairs a thread has deferred: every lane goes through ITS list with ITS stack, one pop
 // per trip of a single loop, so the lanes of a warp work concurrently whatever the shapes of
 // their discretisation trees.
-template <int FIELD>
+template <int FIELD, bool FAST>
 __device__ __forceinline__ void tess_walk_deferred(const TessObs& o, const TessArgs& a,
                                                    const int* defer, int& n_defer, int64_t begin,
                                                    double* stack, double& acc, unsigned& flags)
@@ -534,13 +546,13 @@ __device__ __forceinline__ void tess_walk_deferred(const TessObs& o, const TessA
     TessWalk wk;
     wk.stack_top = -1;
     wk.n_leaves = 0;
-    wk.density = 0.0;
+    wk.density[0] = wk.density[1] = 0.0;
     int k = 0;
     while (true) {
         if (wk.stack_top < 0) {
             if (k >= n_defer) break;
             const double* rec = a.packed + (begin + defer[k++]) * kTessRec;
-            tess_walk_begin(wk, rec, rec[6], stack);
+            tess_walk_begin(wk, rec, rec[6], rec[FAST ? kTessRho1Fast : kTessRho1], stack);
         }
         tess_walk_step<FIELD>(o, a.ratio, a.radial != 0, stack, wk, acc, flags);
     }
@@ -580,10 +592,10 @@ __global__ void __launch_bounds__(kTessBlock) tesseroid_deferred_kernel(const Te
                             : tess_root<FIELD>(o, tile + s * kTessRec, a.ratio, a.radial != 0, acc, flags);
             if (root == 0) defer[n_defer++] = (int)(t0 - begin) + s;
             if (__any_sync(0xffffffffu, n_defer == kTessDefer))
-                tess_walk_deferred<FIELD>(o, a, defer, n_defer, begin, stack, acc, flags);
+                tess_walk_deferred<FIELD, FAST>(o, a, defer, n_defer, begin, stack, acc, flags);
         }
     }
-    tess_walk_deferred<FIELD>(o, a, defer, n_defer, begin, stack, acc, flags);
+    tess_walk_deferred<FIELD, FAST>(o, a, defer, n_defer, begin, stack, acc, flags);
     if (live) {
         if (gridDim.y == 1) a.out[i] = acc * a.scale;
         else a.out[(int64_t)blockIdx.y * a.n_obs + i] = acc;

@@ -176,6 +176,19 @@ int hb200_tesseroid_gravity(const double* longitude, const double* latitude, con
                             int64_t n_tesseroids, int field, int radial_adaptive_discretization,
                             int shard_mode, double* out, uint32_t* flags);
 
+/* replaces jit_tesseroid_gravity_variable_density, _forward/tesseroid_gravity.py:342-445, for the
+ * horizontal (default) adaptive discretisation: the leaves of a tesseroid then keep its radial
+ * bounds, so the density function is only ever evaluated at the tesseroid's two radial
+ * Gauss-Legendre nodes (_tesseroid_variable_density.py:55-58). The host evaluates it there
+ * (after density_based_discretization, :108-157) and passes density_lower / density_upper
+ * (n_tesseroids each). Everything else as hb200_tesseroid_gravity. */
+int hb200_tesseroid_gravity_variable_density(const double* longitude, const double* latitude,
+                                             const double* radius, int64_t n_obs,
+                                             const double* tesseroids, const double* density_lower,
+                                             const double* density_upper, int64_t n_tesseroids,
+                                             int field, int shard_mode, double* out,
+                                             uint32_t* flags);
+
 /* replaces _check_points_outside_tesseroids, _forward/_tesseroid_utils.py:431-454, as one
  * pass: *flags gets HB200_FLAG_TESS_INSIDE if any computation point lies strictly inside any
  * tesseroid (the host then lists the pairs for the reference's error message). */

@@ -38,6 +38,70 @@ def random_model(seed=21, n_tess=40, n_obs=60):
     return coords, tesseroids, density
 
 
+VD_TOP, VD_BOTTOM = 6371e3, 6371e3 - 3e4
+VD_LINEAR = (2500.0, 3300.0)                      # density at the top / at the bottom
+VD_EXPONENTIAL = (2670.0, 3300.0, 5.0)            # density outer, inner, b factor
+VD_QUADRATIC = (1e-3, 3e3, 1900.0, 2e3, 5e3)      # test/test_tesseroid_variable_density.py:45-62
+
+
+def vd_density_functions():
+    """The density families of the reference's tests (test_tesseroid_variable_density.py:
+    linear :443-462, exponential :485-510, quadratic :45-100), numba-jitted like there."""
+    from numba import jit
+
+    top, bottom = VD_TOP, VD_BOTTOM
+    slope = (VD_LINEAR[0] - VD_LINEAR[1]) / (top - bottom)
+    constant_term = VD_LINEAR[0] - slope * top
+
+    @jit(nopython=True)
+    def linear(radius):
+        return slope * radius + constant_term
+
+    outer, inner, b_factor = VD_EXPONENTIAL
+    a_factor = (inner - outer) / (1 - np.exp(-b_factor))
+    exp_constant = inner - a_factor
+    thickness = top - bottom
+
+    @jit(nopython=True)
+    def exponential(radius):
+        return a_factor * np.exp(-b_factor * (radius - bottom) / thickness) + exp_constant
+
+    factor, vertex_radius, vertex_density = VD_QUADRATIC[:3]
+
+    @jit(nopython=True)
+    def quadratic(radius):
+        return factor * (radius - vertex_radius) ** 2 + vertex_density
+
+    return {"linear": linear, "exponential": exponential, "quadratic": quadratic}
+
+
+def variable_density_cases(ref):
+    """Outputs of the reference's unmodified variable-density path (real numba-jitted density
+    functions): density-based discretisation and tesseroid_gravity, horizontal discretisation."""
+    tg = ref.tesseroid.tesseroid_gravity
+    vd = ref.tesseroid_variable_density
+    fns = vd_density_functions()
+    top, bottom = VD_TOP, VD_BOTTOM
+    tesseroids = np.array([[-10, 0, -10, 0, bottom, top], [0, 10, -5, 5, bottom, top - 1e3],
+                           [20, 28, 10, 18, bottom + 5e3, top], [350, 5, 20, 30, bottom, top]], dtype=float)  # fmt: skip
+    rng = np.random.default_rng(33)
+    coords = [rng.uniform(-15, 30, 40), rng.uniform(-15, 32, 40), top + rng.uniform(0, 2e5, 40)]
+    coords[2][:10] = top  # on the outer surface
+    out = {"vd_tesseroids": tesseroids, "vd_coords": np.stack(coords)}
+    for name in ("linear", "exponential"):
+        out[f"vd_{name}_discretization"] = vd.density_based_discretization(
+            ref.tesseroid_utils._longitude_continuity(tesseroids), fns[name])
+        for field in ("potential", "g_z"):
+            out[f"vd_{name}_{field}"] = np.asarray(tg(coords, tesseroids, fns[name], field, parallel=False))
+    # test_tesseroid_variable_density.py:223-273: one tesseroid, quadratic density
+    b, t = VD_QUADRATIC[3:]
+    out["vd_quadratic_discretization"] = np.array(
+        vd._density_based_discretization([-3.0, 2.0, -4.0, 5.0, b, t], fns["quadratic"]))
+    out["vd_quadratic_minmax"] = np.array(vd.density_minmax(fns["quadratic"], b, t))
+    out["vd_quadratic_max_abs_diff"] = np.array(vd.maximum_absolute_diff(fns["quadratic"], b, t))
+    return out
+
+
 def main():
     ref = ref_shim.load()
     tg = ref.tesseroid.tesseroid_gravity
@@ -78,6 +142,7 @@ def main():
         n = ad(np.array(point), tess, ratio, stack, small, radial)
         data[tag] = small[:n].copy()
         data[tag + "_setup"] = np.array(point + [ratio])
+    data.update(variable_density_cases(ref))
     np.savez(os.path.join(OUT, "tesseroid.npz"), **data)
     print("wrote", os.path.join(OUT, "tesseroid.npz"), os.path.getsize(os.path.join(OUT, "tesseroid.npz")), "bytes")
     for k in sorted(data):

@@ -34,6 +34,7 @@ MAG_DEFAULT_FLAGS = 3  # NaN on edges + outside-limit face rule (see choclo_port
 
 _dp = ctypes.POINTER(ctypes.c_double)
 _i64 = ctypes.c_int64
+DENSITY_FN = ctypes.CFUNCTYPE(ctypes.c_double, ctypes.c_double)  # density(radius), tesseroids
 
 
 def build():
@@ -106,6 +107,10 @@ def lib():
         L.hbo_tesseroid_loop.argtypes = [
             ctypes.c_int, _i64, _dp, _dp, _dp, _i64, _dp, _dp, ctypes.c_double, ctypes.c_int, _dp,
             ctypes.POINTER(ctypes.c_int64), ctypes.c_int,
+        ]  # fmt: skip
+        L.hbo_tesseroid_loop_variable_density.restype = ctypes.c_int
+        L.hbo_tesseroid_loop_variable_density.argtypes = [
+            ctypes.c_int, _i64, _dp, _dp, _dp, _i64, _dp, DENSITY_FN, ctypes.c_double, ctypes.c_int, _dp,
         ]  # fmt: skip
         L.hbo_adaptive_discretization.restype = ctypes.c_int64
         L.hbo_adaptive_discretization.argtypes = [
@@ -407,3 +412,96 @@ def tesseroid_gravity(coordinates, tesseroids, density, field, radial_adaptive_d
         out *= 1e5
     out = out.reshape(cast.shape)
     return (out, counts) if return_counts else out
+
+
+# ---- tesseroids with a density function (_forward/_tesseroid_variable_density.py)
+DELTA_RATIO = 0.1  # _tesseroid_variable_density.py:17
+
+
+def density_minmax(density, bottom, top):
+    """:159-199: extrema of the density inside [bottom, top] (bounded scalar minimisation, and
+    the values at the two ends)."""
+    from scipy.optimize import minimize_scalar
+
+    ends = sorted([density(bottom), density(top)])
+    kwargs = {"bounds": [bottom, top], "method": "bounded"}
+    minimum = min(minimize_scalar(density, **kwargs).fun, ends[0])
+    maximum = max(-minimize_scalar(lambda radius: -density(radius), **kwargs).fun, ends[1])
+    return minimum, maximum
+
+
+def straight_line(radius, normalized_density, bottom, top):
+    """:238-259: the chord of the normalised density between the two ends."""
+    at_bottom, at_top = normalized_density(bottom), normalized_density(top)
+    slope = (at_top - at_bottom) / (top - bottom)
+    return slope * (radius - bottom) + at_bottom
+
+
+def maximum_absolute_diff(normalized_density, bottom, top):
+    """:202-235: where the normalised density is farthest from its chord, and by how much."""
+    from scipy.optimize import minimize_scalar
+
+    result = minimize_scalar(
+        lambda radius: -np.abs(normalized_density(radius) - straight_line(radius, normalized_density, bottom, top)),
+        bounds=[bottom, top], method="bounded",
+    )  # fmt: skip
+    return result.x, -result.fun
+
+
+def density_based_discretization_single(tesseroid, density):
+    """:125-157: radial splits of one tesseroid until the density is close to linear in each."""
+    w, e, s, n, bottom, top = tesseroid[:]
+    density_min, density_max = density_minmax(density, bottom, top)
+    if np.isclose(density_min, density_max):
+        return [tesseroid]
+
+    def normalized_density(radius):
+        return (density(radius) - density_min) / (density_max - density_min)
+
+    size_original = top - bottom
+    pending, done = [tesseroid], []
+    while pending:
+        bottom, top = pending.pop(0)[-2:]
+        radius_split, max_diff = maximum_absolute_diff(normalized_density, bottom, top)
+        if max_diff * ((top - bottom) / size_original) > DELTA_RATIO:
+            pending.append([w, e, s, n, radius_split, top])
+            pending.append([w, e, s, n, bottom, radius_split])
+        else:
+            done.append([w, e, s, n, bottom, top])
+    return done
+
+
+def density_based_discretization(tesseroids, density):
+    """:108-122."""
+    out = []
+    for tesseroid in tesseroids:
+        out.extend(density_based_discretization_single(tesseroid, density))
+    return np.atleast_2d(out)
+
+
+def tesseroid_gravity_variable_density(coordinates, tesseroids, density, field,
+                                       radial_adaptive_discretization=False):
+    """Restatement of ``tesseroid_gravity`` for a callable ``density(radius)``
+    (tesseroid_gravity.py:182-183, 342-445): density-based radial discretisation, then the pair
+    loop with the density evaluated at every radial quadrature node (through a C callback)."""
+    if field not in TESSEROID_RATII:
+        raise ValueError(f"Gravitational field {field} not recognized")
+    cast, (lon, lat, rad) = _coords(coordinates)
+    tesseroids = np.atleast_2d(np.asarray(tesseroids, dtype=np.float64))
+    if (tesseroids[:, 0] > tesseroids[:, 1]).any():
+        tesseroids = longitude_continuity(tesseroids)
+    tesseroids = _f64(density_based_discretization(tesseroids, density))
+    out = np.zeros(lon.size, dtype=np.float64)
+    callback = DENSITY_FN(lambda radius: float(density(radius)))
+    status = lib().hbo_tesseroid_loop_variable_density(
+        FIELD_IDS[field], lon.size, _p(lon), _p(lat), _p(rad), tesseroids.shape[0], _p(tesseroids),
+        callback, TESSEROID_RATII[field], int(bool(radial_adaptive_discretization)), _p(out),
+    )  # fmt: skip
+    if status & 3:
+        raise OverflowError("adaptive discretisation overflow")
+    if status & 4:
+        raise ZeroDivisionError("division by zero")
+    if field == "g_z":
+        out *= -1
+        out *= 1e5
+    return out.reshape(cast.shape)

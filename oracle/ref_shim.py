@@ -95,6 +95,9 @@ def load():
     _loaded["dipole"] = importlib.import_module("harmonica._forward.dipole")
     _loaded["tesseroid_utils"] = importlib.import_module("harmonica._forward._tesseroid_utils")
     _loaded["tesseroid"] = importlib.import_module("harmonica._forward.tesseroid_gravity")
+    _loaded["tesseroid_variable_density"] = importlib.import_module(
+        "harmonica._forward._tesseroid_variable_density"
+    )
     return types.SimpleNamespace(**_loaded)
 
 

@@ -228,3 +228,77 @@ int hbo_tesseroid_loop(int field, int64_t n_obs, const double* lon, const double
     }
     return status;
 }
+
+/* ---- variable density (density is a function of the radius) ------------------------------------
+ * gauss_legendre_quadrature_variable_density, _forward/_tesseroid_variable_density.py:20-106, and
+ * jit_tesseroid_gravity_variable_density, _forward/tesseroid_gravity.py:342-445. The density
+ * function is called back once per (latitude node, radial node) like the reference does. Serial
+ * (the callback may be a Python function). */
+typedef double (*hbo_density_fn)(double radius);
+
+double hbo_glq_tesseroid_variable_density(int field, double longitude, double cosphi, double sinphi,
+                                          double radius, const double* t, hbo_density_fn density,
+                                          int* zero_div)
+{
+    double w = t[0], e = t[1], s = t[2], n = t[3], bottom = t[4], top = t[5];
+    double a_factor = 1.0 / 8 * radians(e - w) * radians(n - s) * (top - bottom);
+    double result = 0.0;
+    for (int j = 0; j < 2; j++) {
+        double latitude_p = radians(0.5 * (n - s) * GLQ_NODES[j] + 0.5 * (n + s));
+        double cosphi_p = cos(latitude_p), sinphi_p = sin(latitude_p);
+        for (int k = 0; k < 2; k++) {
+            double radius_p = 0.5 * (top - bottom) * GLQ_NODES[k] + 0.5 * (top + bottom);
+            double density_p = density(radius_p);
+            double kappa = radius_p * radius_p * cosphi_p;
+            for (int i = 0; i < 2; i++) {
+                double longitude_p = radians(0.5 * (e - w) * GLQ_NODES[i] + 0.5 * (e + w));
+                double mass = density_p * a_factor * kappa * GLQ_WEIGHTS[i] * GLQ_WEIGHTS[j] * GLQ_WEIGHTS[k];
+                double cospsi;
+                double dist = distance_spherical_core(longitude, cosphi, sinphi, radius, longitude_p,
+                                                      cosphi_p, sinphi_p, radius_p, &cospsi);
+                double kern;
+                if (dist == 0.0) *zero_div = 1;
+                if (field == 0) {
+                    kern = 1 / dist * HBO_G;
+                } else {
+                    double delta_z = radius - radius_p * cospsi;
+                    kern = -HBO_G * delta_z / (dist * dist * dist);
+                }
+                result += mass * kern;
+            }
+        }
+    }
+    return result;
+}
+
+int hbo_tesseroid_loop_variable_density(int field, int64_t n_obs, const double* lon,
+                                        const double* lat, const double* rad, int64_t n_tess,
+                                        const double* tesseroids, hbo_density_fn density,
+                                        double distance_size_ratio, int radial, double* out)
+{
+    int status = 0;
+    double* stack = (double*)malloc(sizeof(double) * 6 * STACK_SIZE);
+    double* small = (double*)malloc(sizeof(double) * 6 * MAX_DISCRETIZATIONS);
+    for (int64_t i = 0; i < n_obs; i++) {
+        double coordinates[3] = {lon[i], lat[i], rad[i]};
+        double longitude_rad = radians(lon[i]);
+        double cosphi = cos(radians(lat[i])), sinphi = sin(radians(lat[i]));
+        for (int64_t j = 0; j < n_tess; j++) {
+            int64_t n_splits = hbo_adaptive_discretization(coordinates, tesseroids + 6 * j,
+                                                           distance_size_ratio, stack, STACK_SIZE,
+                                                           small, MAX_DISCRETIZATIONS, radial);
+            if (n_splits < 0) {
+                status |= (int)(-n_splits);
+                n_splits = 0;
+            }
+            int zero_div = 0;
+            for (int64_t q = 0; q < n_splits; q++)
+                out[i] += hbo_glq_tesseroid_variable_density(field, longitude_rad, cosphi, sinphi, rad[i],
+                                                             small + 6 * q, density, &zero_div);
+            if (zero_div) status |= HBO_TESS_ZERO_DIVISION;
+        }
+    }
+    free(stack);
+    free(small);
+    return status;
+}

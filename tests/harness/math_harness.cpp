@@ -87,8 +87,8 @@ extern "C" {
 // out[i] = sum_j pair(i, j); counts (may be null): leaves per pair, n_obs x n_tess
 void hbt_tesseroid_loop(int field, int64_t n_obs, const double* lon, const double* lat,
                         const double* rad, int64_t n_tess, const double* tesseroids,
-                        const double* density, int radial, double* out, int64_t* counts,
-                        unsigned* flags)
+                        const double* density, const double* density_upper, int radial, double* out,
+                        int64_t* counts, unsigned* flags)
 {
     double stack[kTessStack * 6];
     unsigned f = 0;
@@ -100,9 +100,9 @@ void hbt_tesseroid_loop(int field, int64_t n_obs, const double* lon, const doubl
         for (int64_t j = 0; j < n_tess; j++) {
             int leaves;
             if (field == F_POT)
-                leaves = tess_pair<F_POT>(o, tesseroids + 6 * j, density[j], ratio, radial != 0, stack, acc, f);
+                leaves = tess_pair<F_POT>(o, tesseroids + 6 * j, density[j], density_upper[j], ratio, radial != 0, stack, acc, f);
             else
-                leaves = tess_pair<F_U>(o, tesseroids + 6 * j, density[j], ratio, radial != 0, stack, acc, f);
+                leaves = tess_pair<F_U>(o, tesseroids + 6 * j, density[j], density_upper[j], ratio, radial != 0, stack, acc, f);
             if (counts) counts[i * n_tess + j] = leaves;
         }
         out[i] = acc;
@@ -115,17 +115,18 @@ void hbt_tesseroid_loop(int field, int64_t n_obs, const double* lon, const doubl
 // of them are pending and at the end (one lane, so no warp vote). leaves: leaves per pair.
 void hbt_tesseroid_loop_deferred(int field, int64_t n_obs, const double* lon, const double* lat,
                                  const double* rad, int64_t n_tess, const double* tesseroids,
-                                 const double* density, int radial, int defer_cap, int fast,
-                                 double* out, int64_t* counts, unsigned* flags)
+                                 const double* density, const double* density_upper, int radial,
+                                 int defer_cap, int fast, double* out, int64_t* counts,
+                                 unsigned* flags)
 {
     double stack[kTessStack * 6];
     double* records = new double[(size_t)(n_tess > 0 ? n_tess : 1) * kTessRec];
     for (int64_t j = 0; j < n_tess; j++) {
         if (fast)
-            tess_pack_record_fast(records + j * kTessRec, tesseroids + 6 * j, density[j],
+            tess_pack_record_fast(records + j * kTessRec, tesseroids + 6 * j, density[j], density_upper[j],
                                   field == F_POT ? 1.0 : 2.5, radial != 0);
         else
-            tess_pack_record(records + j * kTessRec, tesseroids + 6 * j, density[j]);
+            tess_pack_record(records + j * kTessRec, tesseroids + 6 * j, density[j], density_upper[j]);
     }
     int64_t* defer = new int64_t[defer_cap > 0 ? defer_cap : 1];
     unsigned f = 0;
@@ -139,8 +140,9 @@ void hbt_tesseroid_loop_deferred(int field, int64_t n_obs, const double* lon, co
             for (int k = 0; k < n_defer; k++) {
                 const double* rec = records + defer[k] * kTessRec;
                 int leaves;
-                if (field == F_POT) leaves = tess_pair<F_POT>(o, rec, rec[6], ratio, radial != 0, stack, acc, f);
-                else leaves = tess_pair<F_U>(o, rec, rec[6], ratio, radial != 0, stack, acc, f);
+                const double rho1 = rec[fast ? kTessRho1Fast : kTessRho1];
+                if (field == F_POT) leaves = tess_pair<F_POT>(o, rec, rec[6], rho1, ratio, radial != 0, stack, acc, f);
+                else leaves = tess_pair<F_U>(o, rec, rec[6], rho1, ratio, radial != 0, stack, acc, f);
                 if (counts) counts[i * n_tess + defer[k]] = leaves;
             }
             n_defer = 0;
@@ -171,8 +173,8 @@ unsigned hbt_tesseroid_overflow(int which, const double* point, const double* te
     tess_make_obs(o, point[0], point[1], point[2]);
     double acc = 0.0;
     unsigned f = 0;
-    if (which == 0) tess_pair<F_POT, 2, kTessMaxLeaves>(o, tesseroid, 1.0, ratio, false, stack, acc, f);
-    else tess_pair<F_POT, kTessStack, 2>(o, tesseroid, 1.0, ratio, false, stack, acc, f);
+    if (which == 0) tess_pair<F_POT, 2, kTessMaxLeaves>(o, tesseroid, 1.0, 1.0, ratio, false, stack, acc, f);
+    else tess_pair<F_POT, kTessStack, 2>(o, tesseroid, 1.0, 1.0, ratio, false, stack, acc, f);
     return f;
 }
 

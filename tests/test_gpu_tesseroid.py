@@ -18,8 +18,9 @@ import pytest
 
 import oracle as O
 from _common import TOL, max_rel
+from _common import golden
 from test_tesseroid_host import (MEAN_RADIUS, MODES, _cases, _key, _shell, _shell_analytical,
-                                 reference_conditioning)
+                                 reference_conditioning, vd_density_functions)
 
 pytestmark = pytest.mark.gpu
 
@@ -180,3 +181,28 @@ def test_tesseroid_layer_gravity(hb, field):
     want = O.tesseroid_gravity(grid_coords, all_t[sel], density.ravel()[sel], field)
     got = layer.tesseroid_layer.gravity(grid_coords, field=field, thickness_threshold=100.0)
     assert max_rel(got, want) <= TOL
+
+
+@pytest.mark.parametrize("name", ["linear", "exponential"])
+def test_golden_tesseroid_gravity_density_function(hb, tess_variant, name):
+    """variable-density tesseroids (test/test_tesseroid_variable_density.py): the outputs of the
+    reference's unmodified path with numba-jitted density functions"""
+    g = golden("tesseroid")
+    density = vd_density_functions()[name]
+    coords, tesseroids = tuple(g["vd_coords"]), g["vd_tesseroids"]
+    for field in ("potential", "g_z"):
+        got = hb.tesseroid_gravity(coords, tesseroids, density, field)
+        assert max_rel(got, g[f"vd_{name}_{field}"]) <= TOL
+
+
+def test_density_function_rules(hb):
+    """test/test_tesseroid_variable_density.py:322-345: a constant function equals the constant"""
+    bottom, top = 5400e3, 6300e3
+    tesseroid = [-3, 3, -2, 2, bottom, top]
+    lon, lat = np.meshgrid(np.arange(-5, 6, 1.0), np.arange(-5, 6, 1.0))
+    grid = (lon, lat, np.full_like(lon, top))
+    for field in ("potential", "g_z"):
+        npt.assert_allclose(hb.tesseroid_gravity(grid, tesseroid, lambda radius: 2900.0, field),
+                            hb.tesseroid_gravity(grid, tesseroid, 2900.0, field))  # fmt: skip
+    with pytest.raises(NotImplementedError, match="radial_adaptive_discretization"):
+        hb.tesseroid_gravity(grid, tesseroid, lambda radius: 2900.0, "g_z", radial_adaptive_discretization=True)

@@ -45,20 +45,22 @@ def _cases():
     }  # fmt: skip
 
 
-def harness_tesseroid(coordinates, tesseroids, density, field, radial):
-    """Host build of hb200_tess.cuh summed like the kernel (SI, before sign / unit)."""
+def harness_tesseroid(coordinates, tesseroids, density, field, radial, density_upper=None):
+    """Host build of hb200_tess.cuh summed like the kernel (SI, before sign / unit).
+    density / density_upper: per radial quadrature node (equal for homogeneous tesseroids)."""
     H = harness()
     dp = ctypes.POINTER(ctypes.c_double)
     lon, lat, rad = (np.ascontiguousarray(np.atleast_1d(c), dtype=np.float64).ravel() for c in coordinates)
     tesseroids = np.ascontiguousarray(np.atleast_2d(tesseroids), dtype=np.float64)
     density = np.ascontiguousarray(np.atleast_1d(density), dtype=np.float64)
+    upper = density if density_upper is None else np.ascontiguousarray(density_upper, dtype=np.float64)
     out = np.zeros(lon.size)
     counts = np.zeros((lon.size, tesseroids.shape[0]), dtype=np.int64)
     flags = ctypes.c_uint(0)
     H.hbt_tesseroid_loop(
         {"potential": 0, "g_z": 3}[field], ctypes.c_int64(lon.size), lon.ctypes.data_as(dp),
         lat.ctypes.data_as(dp), rad.ctypes.data_as(dp), ctypes.c_int64(tesseroids.shape[0]),
-        tesseroids.ctypes.data_as(dp), density.ctypes.data_as(dp), int(radial),
+        tesseroids.ctypes.data_as(dp), density.ctypes.data_as(dp), upper.ctypes.data_as(dp), int(radial),
         out.ctypes.data_as(dp), counts.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
         ctypes.byref(flags),
     )  # fmt: skip
@@ -342,8 +344,9 @@ def test_argument_errors_need_no_device():
 
     with pytest.raises(ValueError, match="Gravitational field this-field-does-not-exist not recognized"):
         hb.tesseroid_gravity([0, 0, 0], [-10, 10, -10, 10, 100, 200], 1000, "this-field-does-not-exist")
-    with pytest.raises(NotImplementedError, match="constant densities"):
-        hb.tesseroid_gravity([0, 0, 300], [-10, 10, -10, 10, 100, 200], lambda r: 1000.0, "g_z")
+    with pytest.raises(NotImplementedError, match="radial_adaptive_discretization"):
+        hb.tesseroid_gravity([0, 0, 300], [-10, 10, -10, 10, 100, 200], lambda r: 1000.0, "g_z",
+                             radial_adaptive_discretization=True)  # fmt: skip
     with pytest.raises(ValueError, match="The bottom radius boundary can't be greater than the top one"):
         hb.tesseroid_gravity([0.0, 0.0, 10.0], [0.0, 10.0, 0.0, 10.0, 20.0, 10.0], 100.0, "potential")
 
@@ -410,20 +413,23 @@ def test_tesseroid_layer_host_logic():
 
 
 # ------------------------------------------------------------------ deferred kernel algorithm
-def harness_tesseroid_deferred(coordinates, tesseroids, density, field, radial, defer_cap=16, fast=False):
+def harness_tesseroid_deferred(coordinates, tesseroids, density, field, radial, defer_cap=16, fast=False,
+                               density_upper=None):
     """Host emulation of one thread of tesseroid_deferred_kernel (root records + deferred walks)."""
     H = harness()
     dp = ctypes.POINTER(ctypes.c_double)
     lon, lat, rad = (np.ascontiguousarray(np.atleast_1d(c), dtype=np.float64).ravel() for c in coordinates)
     tesseroids = np.ascontiguousarray(np.atleast_2d(tesseroids), dtype=np.float64)
     density = np.ascontiguousarray(np.atleast_1d(density), dtype=np.float64)
+    upper = density if density_upper is None else np.ascontiguousarray(density_upper, dtype=np.float64)
     out = np.zeros(lon.size)
     counts = np.zeros((lon.size, tesseroids.shape[0]), dtype=np.int64)
     flags = ctypes.c_uint(0)
     H.hbt_tesseroid_loop_deferred(
         {"potential": 0, "g_z": 3}[field], ctypes.c_int64(lon.size), lon.ctypes.data_as(dp),
         lat.ctypes.data_as(dp), rad.ctypes.data_as(dp), ctypes.c_int64(tesseroids.shape[0]),
-        tesseroids.ctypes.data_as(dp), density.ctypes.data_as(dp), int(radial), int(defer_cap),
+        tesseroids.ctypes.data_as(dp), density.ctypes.data_as(dp), upper.ctypes.data_as(dp),
+        int(radial), int(defer_cap),
         int(fast), out.ctypes.data_as(dp), counts.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
         ctypes.byref(flags),
     )  # fmt: skip
@@ -482,6 +488,18 @@ class _StandInLibrary:
         got, _, flag_bits = harness_tesseroid_deferred(
             (self._array(lon, n), self._array(lat, n), self._array(rad, n)), tesseroids,
             self._array(rho, n_tess), {0: "potential", 3: "g_z"}[field], radial)  # fmt: skip
+        result[:] = got * (-1e5 if field == 3 else 1.0)
+        flags._obj.value = flag_bits
+        return 0
+
+    def hb200_tesseroid_gravity_variable_density(self, lon, lat, rad, n, tess, rho0, rho1, n_tess, field, shard,
+                                                 out, flags):
+        result = np.ctypeslib.as_array(out, shape=(n,))
+        tesseroids = self._array(tess, n_tess * 6).reshape(n_tess, 6)
+        got, _, flag_bits = harness_tesseroid_deferred(
+            (self._array(lon, n), self._array(lat, n), self._array(rad, n)), tesseroids,
+            self._array(rho0, n_tess), {0: "potential", 3: "g_z"}[field], False,
+            density_upper=self._array(rho1, n_tess))  # fmt: skip
         result[:] = got * (-1e5 if field == 3 else 1.0)
         flags._obj.value = flag_bits
         return 0
@@ -579,3 +597,121 @@ def test_fast_far_field_accuracy_on_far_and_regional_models():
         bar = max(1e-9, 4 * reference_conditioning(near, small, rho, field, False, trials=2))
         assert flags == 0 and np.array_equal(counts, want_counts)
         assert np.max(np.abs(got - want)) <= bar * np.max(np.abs(want)), (field, bar)
+
+
+# ------------------------------------------------------------------ density given as a function
+VD_TOP, VD_BOTTOM = 6371e3, 6371e3 - 3e4
+
+
+def vd_density_functions():
+    """Plain-Python versions of the density functions the fixtures were generated with
+    (oracle/make_golden_tesseroid.py: numba-jitted there; same float64 operations)."""
+    top, bottom = VD_TOP, VD_BOTTOM
+    slope = (2500.0 - 3300.0) / (top - bottom)
+    constant_term = 2500.0 - slope * top
+    outer, inner, b_factor = 2670.0, 3300.0, 5.0
+    a_factor = (inner - outer) / (1 - np.exp(-b_factor))
+    exp_constant = inner - a_factor
+    thickness = top - bottom
+    return {
+        "linear": lambda radius: slope * radius + constant_term,
+        "exponential": lambda radius: a_factor * np.exp(-b_factor * (radius - bottom) / thickness) + exp_constant,
+        "quadratic": lambda radius: 1e-3 * ((radius - 3e3) * (radius - 3e3)) + 1900.0,
+    }
+
+
+@pytest.mark.parametrize("name", ["linear", "exponential"])
+def test_variable_density_oracle_is_bit_identical_to_the_reference(name):
+    g = golden("tesseroid")
+    density = vd_density_functions()[name]
+    coords, tesseroids = tuple(g["vd_coords"]), g["vd_tesseroids"]
+    disc = O.density_based_discretization(O.longitude_continuity(tesseroids), density)
+    assert np.array_equal(disc, g[f"vd_{name}_discretization"])
+    for field in ("potential", "g_z"):
+        got = O.tesseroid_gravity_variable_density(coords, tesseroids, density, field)
+        assert np.array_equal(got, g[f"vd_{name}_{field}"])
+
+
+def test_density_based_discretization_of_the_product():
+    """harmonica_b200/_tesseroid_density.py against the reference's outputs and against the
+    closed forms of test/test_tesseroid_variable_density.py:103-320"""
+    from harmonica_b200 import _tesseroid_density as D
+
+    g = golden("tesseroid")
+    fns = vd_density_functions()
+    for name in ("linear", "exponential"):
+        disc = D.density_based_discretization(O.longitude_continuity(g["vd_tesseroids"]), fns[name])
+        assert np.array_equal(disc, g[f"vd_{name}_discretization"])
+    quadratic, bottom, top = fns["quadratic"], 2e3, 5e3
+    pieces = np.array(D._density_based_discretization([-3.0, 2.0, -4.0, 5.0, bottom, top], quadratic))
+    assert np.array_equal(pieces, g["vd_quadratic_discretization"])
+    npt.assert_allclose(D.density_minmax(quadratic, bottom, top), (1900.0, quadratic(top)))
+    assert np.array_equal(D.density_minmax(quadratic, bottom, top), g["vd_quadratic_minmax"])
+    slope = (quadratic(top) - quadratic(bottom)) / (top - bottom)
+    radius_split = 0.5 * slope / 1e-3 + 3e3
+    line = lambda radius: slope * (radius - bottom) + quadratic(bottom)  # noqa: E731
+    npt.assert_allclose(D.straight_line(3.7e3, quadratic, bottom, top), line(3.7e3))
+    npt.assert_allclose(D.maximum_absolute_diff(quadratic, bottom, top),
+                        (radius_split, abs(quadratic(radius_split) - line(radius_split))), rtol=1e-6)  # fmt: skip
+    # linear and constant densities are never split (:276-320)
+    assert len(D._density_based_discretization([-3, 2, -4, 5, 30, 50], lambda radius: 3)) == 1
+    assert len(D._density_based_discretization([-3, 2, -4, 5, 30.0, 50.0], lambda radius: 3.1 * radius + 0.4)) == 1
+    # the two radial quadrature nodes of every piece
+    lower, upper = D.density_at_radial_nodes(pieces, quadratic)
+    mid, half = 0.5 * (pieces[:, 5] + pieces[:, 4]), 0.5 * (pieces[:, 5] - pieces[:, 4])
+    npt.assert_allclose(lower, [quadratic(r) for r in mid - half / np.sqrt(3)], rtol=1e-15)
+    npt.assert_allclose(upper, [quadratic(r) for r in mid + half / np.sqrt(3)], rtol=1e-15)
+
+
+@pytest.mark.parametrize("fast", [False, True])
+@pytest.mark.parametrize("name", ["linear", "exponential"])
+def test_variable_density_pair_function_matches_the_reference(name, fast):
+    """two densities per tesseroid (host-evaluated at its radial nodes) through the host build of
+    the kernel's per-thread algorithm, against the reference's outputs"""
+    from harmonica_b200 import _tesseroid_density as D
+
+    g = golden("tesseroid")
+    density = vd_density_functions()[name]
+    coords = tuple(g["vd_coords"])
+    disc = D.density_based_discretization(O.longitude_continuity(g["vd_tesseroids"]), density)
+    lower, upper = D.density_at_radial_nodes(disc, density)
+    for field in ("potential", "g_z"):
+        want = g[f"vd_{name}_{field}"]
+        got, _, flags = harness_tesseroid_deferred(coords, disc, lower, field, False, 64, fast=fast,
+                                                   density_upper=upper)  # fmt: skip
+        if field == "g_z":
+            got *= -1e5
+        assert flags == 0
+        bar = 1e-13 if not fast else 1e-9
+        assert np.max(np.abs(got - want)) <= bar * np.max(np.abs(want))
+        plain, _, _ = harness_tesseroid(coords, disc, lower, field, False, density_upper=upper)
+        if field == "g_z":
+            plain *= -1
+            plain *= 1e5
+        assert np.array_equal(plain, want)  # reference order of additions: bit for bit
+
+
+def test_variable_density_wrapper_with_a_stand_in_library(monkeypatch):
+    """test/test_tesseroid_variable_density.py:322-345 and the wrapper's own rules"""
+    import harmonica_b200 as hb
+    from harmonica_b200 import _lib
+
+    monkeypatch.setattr(_lib, "ensure_init", lambda: _StandInLibrary())
+    g = golden("tesseroid")
+    fns = vd_density_functions()
+    coords, tesseroids = tuple(g["vd_coords"]), g["vd_tesseroids"]
+    for name in ("linear", "exponential"):
+        for field in ("potential", "g_z"):
+            got = hb.tesseroid_gravity(coords, tesseroids, fns[name], field)
+            want = g[f"vd_{name}_{field}"]
+            assert np.max(np.abs(got - want)) <= 1e-13 * np.max(np.abs(want))
+    # a constant density function gives what the constant density gives
+    bottom, top = 5400e3, 6300e3
+    tesseroid = [-3, 3, -2, 2, bottom, top]
+    lon, lat = np.meshgrid(np.arange(-5, 6, 2.0), np.arange(-5, 6, 2.0))
+    grid = (lon, lat, np.full_like(lon, top))
+    for field in ("potential", "g_z"):
+        npt.assert_allclose(hb.tesseroid_gravity(grid, tesseroid, lambda radius: 2900.0, field),
+                            hb.tesseroid_gravity(grid, tesseroid, 2900.0, field))  # fmt: skip
+    with pytest.raises(NotImplementedError, match="radial_adaptive_discretization"):
+        hb.tesseroid_gravity(grid, tesseroid, lambda radius: 2900.0, "g_z", radial_adaptive_discretization=True)
