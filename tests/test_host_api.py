@@ -58,6 +58,24 @@ def test_signatures_match_the_reference():
                                                "thickness_threshold", "parallel", "progressbar"]
     sig = inspect.signature(hb.prism_gravity)
     assert sig.parameters["dtype"].default == "float64" and sig.parameters["parallel"].default is True
+    # dipole.py:27-35, tesseroid_gravity.py:36-46, tesseroid_layer.py:282-290,
+    # cartesian.py:170-178, gradient_boosted.py:98-108, spherical.py:111-117
+    assert names(hb.dipole_magnetic, 8) == ["coordinates", "dipoles", "magnetic_moments", "field",
+                                            "parallel", "dtype", "progressbar", "disable_checks"]
+    assert names(hb.tesseroid_gravity, 9) == ["coordinates", "tesseroids", "density", "field", "parallel",
+                                              "radial_adaptive_discretization", "dtype", "progressbar",
+                                              "disable_checks"]
+    assert names(hb.TesseroidLayer.gravity, 6) == ["self", "coordinates", "field", "progressbar",
+                                                   "density_name", "thickness_threshold"]
+    assert names(hb.EquivalentSources.__init__, 7) == ["self", "damping", "points", "depth", "block_size",
+                                                       "parallel", "dtype"]
+    assert names(hb.EquivalentSourcesGB.__init__, 9) == ["self", "damping", "points", "depth", "block_size",
+                                                         "window_size", "parallel", "random_state", "dtype"]
+    assert names(hb.EquivalentSourcesSph.__init__, 5) == ["self", "damping", "points", "relative_depth",
+                                                          "parallel"]
+    for cls in (hb.EquivalentSources, hb.EquivalentSourcesGB, hb.EquivalentSourcesSph):
+        assert names(cls.fit, 4) == ["self", "coordinates", "data", "weights"]
+        assert names(cls.predict, 2) == ["self", "coordinates"]
 
 
 COORDS = ([0.0, 10.0], [0.0, 5.0], [10.0, 20.0])
