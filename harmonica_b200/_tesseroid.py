@@ -19,7 +19,7 @@ import numpy as np
 
 from . import _lib
 from ._tesseroid_density import density_at_radial_nodes, density_based_discretization
-from ._utils import broadcast_coordinates
+from ._utils import broadcast_coordinates, observer_chunks, progress
 
 _FIELDS = {"potential": 0, "g_z": 3}
 
@@ -203,9 +203,9 @@ def tesseroid_gravity(
     ``sort_observers`` (extension): hand the computation points to the device in a locality
     preserving order (and return the result in the caller's order); it only affects speed.
 
-    ``parallel`` and ``progressbar`` are accepted for signature compatibility (the device is
-    always parallel; one launch reports no intermediate progress). All arithmetic is float64 and
-    the result is cast to ``dtype`` at the end.
+    ``parallel`` is accepted for signature compatibility (the device is always parallel). With
+    ``progressbar=True`` the computation points are processed in ~20 chunks and a ``tqdm`` bar
+    advances per chunk. All arithmetic is float64 and the result is cast to ``dtype`` at the end.
     """
     if field not in _FIELDS:
         raise ValueError(f"Gravitational field {field} not recognized")
@@ -241,22 +241,38 @@ def tesseroid_gravity(
         order = _locality_order(coords[0], coords[1])
         coords = tuple(np.ascontiguousarray(c[order]) for c in coords)
     out = np.empty(coords[0].size, dtype=np.float64)
-    flags = ctypes.c_uint32(0)
-    if density_upper is None:
-        rc = lib.hb200_tesseroid_gravity(
-            _lib.ptr(coords[0]), _lib.ptr(coords[1]), _lib.ptr(coords[2]), coords[0].size,
-            _lib.ptr(tesseroids), _lib.ptr(density), tesseroids.shape[0], _FIELDS[field],
-            int(bool(radial_adaptive_discretization)), _lib.shard_mode(shard), _lib.ptr(out),
-            ctypes.byref(flags),
-        )  # fmt: skip
-    else:
+    all_flags = 0
+    if density_upper is not None:
         density_upper = _lib.f64(density_upper)
-        rc = lib.hb200_tesseroid_gravity_variable_density(
-            _lib.ptr(coords[0]), _lib.ptr(coords[1]), _lib.ptr(coords[2]), coords[0].size,
-            _lib.ptr(tesseroids), _lib.ptr(density), _lib.ptr(density_upper), tesseroids.shape[0],
-            _FIELDS[field], _lib.shard_mode(shard), _lib.ptr(out), ctypes.byref(flags),
-        )  # fmt: skip
-    _lib.check(rc)
+    # tesseroid_gravity.py:191-207: the reference's bar advances per computation point from inside
+    # the jitted loop; here the call is split in ~20 chunks of computation points
+    with progress(coords[0].size, progressbar) as proxy:
+        for lo, hi in observer_chunks(coords[0].size, proxy):
+            whole = lo == 0 and hi == coords[0].size
+            part = coords if whole else tuple(np.ascontiguousarray(c[lo:hi]) for c in coords)
+            part_out = out if whole else np.empty(hi - lo, dtype=np.float64)
+            flags = ctypes.c_uint32(0)
+            if density_upper is None:
+                rc = lib.hb200_tesseroid_gravity(
+                    _lib.ptr(part[0]), _lib.ptr(part[1]), _lib.ptr(part[2]), hi - lo,
+                    _lib.ptr(tesseroids), _lib.ptr(density), tesseroids.shape[0], _FIELDS[field],
+                    int(bool(radial_adaptive_discretization)), _lib.shard_mode(shard),
+                    _lib.ptr(part_out), ctypes.byref(flags),
+                )  # fmt: skip
+            else:
+                rc = lib.hb200_tesseroid_gravity_variable_density(
+                    _lib.ptr(part[0]), _lib.ptr(part[1]), _lib.ptr(part[2]), hi - lo,
+                    _lib.ptr(tesseroids), _lib.ptr(density), _lib.ptr(density_upper),
+                    tesseroids.shape[0], _FIELDS[field], _lib.shard_mode(shard), _lib.ptr(part_out),
+                    ctypes.byref(flags),
+                )  # fmt: skip
+            _lib.check(rc)
+            if not whole:
+                out[lo:hi] = part_out
+            all_flags |= flags.value
+            if proxy is not None:
+                proxy.update(hi - lo)
+    flags = ctypes.c_uint32(all_flags)
     # the reference raises from inside the jitted loop: numba's float division raises on a zero
     # divisor (a computation point on a corner that 3-D discretisation splits without end, or
     # on a quadrature node); _tesseroid_utils.py:192-207 raise OverflowError

@@ -195,6 +195,19 @@ def test_golden_tesseroid_gravity_density_function(hb, tess_variant, name):
         assert max_rel(got, g[f"vd_{name}_{field}"]) <= TOL
 
 
+def test_progressbar_gives_identical_results(hb):
+    """test/test_tesseroid.py:771-818"""
+    tesseroids = [[30.3, 50.5, -72.2, -34.2, 6e4, 6.1e4], [30.3, 50.5, 20.1, 32.3, 6.1e4, 6.2e4],
+                  [-10.3, 5.3, 20.1, 32.3, 6.2e4, 6.3e4]]  # fmt: skip
+    densities = [2000, 3000, 4000]
+    lon, lat = np.meshgrid(np.arange(-15, 56, 10.0), np.arange(-80, 41, 10.0))
+    coordinates = (lon, lat, np.full_like(lon, 6.5e4))
+    for field in ("potential", "g_z"):
+        plain = hb.tesseroid_gravity(coordinates, tesseroids, densities, field)
+        with_bar = hb.tesseroid_gravity(coordinates, tesseroids, densities, field, progressbar=True)
+        npt.assert_allclose(plain, with_bar)
+
+
 def test_density_function_rules(hb):
     """test/test_tesseroid_variable_density.py:322-345: a constant function equals the constant"""
     bottom, top = 5400e3, 6300e3

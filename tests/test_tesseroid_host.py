@@ -532,6 +532,8 @@ def test_wrapper_logic_with_a_stand_in_library(monkeypatch):
     plain = hb.tesseroid_gravity(coords, tesseroids, density, "g_z", sort_observers=False)
     assert np.array_equal(ordered, plain)  # the order of the observers never changes a value
     assert np.max(np.abs(ordered - want)) <= 1e-13 * np.max(np.abs(want))
+    with_bar = hb.tesseroid_gravity(coords, tesseroids, density, "g_z", progressbar=True)
+    assert np.array_equal(with_bar, ordered)  # ~20 chunks of computation points, same values
     grid = tuple(c.reshape(50, 60) for c in coords)
     out = hb.tesseroid_gravity(grid, tesseroids, density, "potential", dtype="float32")
     assert out.shape == (50, 60) and out.dtype == np.float32
