@@ -27,9 +27,11 @@
  * doctests and the Bouguer-slab limit, Laplace identity, finite differences,
  * an mpmath quadrature of the potential, and bit-comparison against the
  * reference's UNMODIFIED wrappers+loops driven through oracle/ref_shim.py.
- * "parity unpinned" items (no reference test pins them): absolute values of
- * prism_magnetic, NaN-on-edge and +4pi face rules of the magnetic kernels, the
- * digits of choclo's mu_0.
+ * "parity unpinned" items (no reference test pins them): NaN-on-edge and +4pi
+ * face rules of the magnetic kernels, the digits of choclo's mu_0. The
+ * absolute values / units / signs of prism_magnetic (which the reference only
+ * compares with choclo) are pinned formula-independently by a Gauss-Legendre
+ * quadrature of the dipole field over the prism volume (test_oracle_pins.py).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline/reference
  * arm may load this library.

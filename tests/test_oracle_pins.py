@@ -205,3 +205,74 @@ def test_dipole_closed_forms():
     npt.assert_allclose(b, [0.0, 0.0, -1e-7 * m / 150.0**3 * 1e9], rtol=1e-14, atol=1e-20)
     with pytest.raises(ZeroDivisionError):
         O.dipole_magnetic(([1.0], [2.0], [3.0]), ([1.0], [2.0], [3.0]), ([1.0], [0.0], [0.0]), "b")
+
+
+def _gauss_legendre_box(bounds, order=64):
+    """Tensor Gauss-Legendre nodes and weights of a box (formula-independent volume integrals)."""
+    nodes, weights = np.polynomial.legendre.leggauss(order)
+    axes = []
+    for lo, hi in bounds:
+        axes.append((0.5 * (hi - lo) * nodes + 0.5 * (hi + lo), 0.5 * (hi - lo) * weights))
+    x, y, z = np.meshgrid(axes[0][0], axes[1][0], axes[2][0], indexing="ij")
+    w = axes[0][1][:, None, None] * axes[1][1][None, :, None] * axes[2][1][None, None, :]
+    return x, y, z, w
+
+
+def test_prism_magnetic_against_volume_quadrature():
+    """formula-independent pin of the ABSOLUTE values, units and signs of prism_magnetic (the
+    reference's tests only compare with choclo, which is absent): B = mu0 / 4 pi times the volume
+    integral of the dipole field 3 (M.R) R / R^5 - M / R^3, in nT, outside the prism"""
+    prism = [-30.0, 50.0, -20.0, 40.0, -80.0, -10.0]
+    magnetization = (1.7, -0.6, 2.3)  # A/m
+    x, y, z, w = _gauss_legendre_box([(prism[0], prism[1]), (prism[2], prism[3]), (prism[4], prism[5])])
+    for obs in ((120.0, -75.0, 60.0), (-110.0, 95.0, -40.0), (10.0, 15.0, 70.0)):
+        rx, ry, rz = obs[0] - x, obs[1] - y, obs[2] - z
+        r2 = rx * rx + ry * ry + rz * rz
+        r5 = r2 ** 2.5
+        m_dot_r = magnetization[0] * rx + magnetization[1] * ry + magnetization[2] * rz
+        want = [1e-7 * 1e9 * np.sum(w * (3 * m_dot_r * rc / r5 - mc / r2 ** 1.5))
+                for rc, mc in zip((rx, ry, rz), magnetization)]  # fmt: skip
+        m = tuple(np.array([c]) for c in magnetization)
+        got = O.prism_magnetic(obs, [prism], m, "b")
+        npt.assert_allclose([float(np.ravel(c)[0]) for c in got], want, rtol=1e-9)
+        for k, name in enumerate(("b_e", "b_n", "b_u")):
+            npt.assert_allclose(float(np.ravel(O.prism_magnetic(obs, [prism], m, name))[0]), want[k], rtol=1e-9)
+
+
+def test_prism_gravity_fields_against_volume_quadrature():
+    """the same pin for the accelerations and the tensor: units (mGal, Eotvos) and signs
+    (g_z down, g_ez / g_nz with the z axis down) straight from Newton's integral"""
+    prism = [-30.0, 50.0, -20.0, 40.0, -80.0, -10.0]
+    rho = 2670.0
+    x, y, z, w = _gauss_legendre_box([(prism[0], prism[1]), (prism[2], prism[3]), (prism[4], prism[5])])
+    for obs in ((120.0, -75.0, 60.0), (10.0, 15.0, 70.0)):
+        dx, dy, dz = x - obs[0], y - obs[1], z - obs[2]  # from the observer to the mass
+        r2 = dx * dx + dy * dy + dz * dz
+        r3, r5 = r2 ** 1.5, r2 ** 2.5
+        acc = {"g_e": dx / r3, "g_n": dy / r3, "g_z": -dz / r3}  # z axis DOWN: g_z = -g_u
+        for field, integrand in acc.items():
+            want = G * rho * 1e5 * np.sum(w * integrand)
+            npt.assert_allclose(float(O.prism_gravity(obs, [prism], rho, field)), want, rtol=1e-9)
+        tensor = {
+            "g_ee": (3 * dx * dx - r2) / r5, "g_nn": (3 * dy * dy - r2) / r5, "g_zz": (3 * dz * dz - r2) / r5,
+            "g_en": 3 * dx * dy / r5, "g_ez": -3 * dx * dz / r5, "g_nz": -3 * dy * dz / r5,
+        }  # fmt: skip
+        for field, integrand in tensor.items():
+            want = G * rho * 1e9 * np.sum(w * integrand)
+            npt.assert_allclose(float(O.prism_gravity(obs, [prism], rho, field)), want, rtol=1e-8,
+                                atol=1e-12 * abs(want) + 1e-9)  # fmt: skip
+
+
+def test_dipole_magnetic_against_prism_limit():
+    """dipole_magnetic pinned on prism_magnetic: a small cube with magnetization M is the dipole
+    m = M * volume seen from far away (relative difference ~ (size / distance)^2)"""
+    half = 0.05
+    prism = [-half, half, -half, half, -half, half]
+    magnetization = (1.7, -0.6, 2.3)
+    volume = (2 * half) ** 3
+    obs = (40.0, -25.0, 30.0)
+    m = tuple(np.array([c]) for c in magnetization)
+    want = [float(np.ravel(c)[0]) for c in O.prism_magnetic(obs, [prism], m, "b")]
+    moments = tuple(np.array([c * volume]) for c in magnetization)
+    got = O.dipole_magnetic(obs, (np.array([0.0]), np.array([0.0]), np.array([0.0])), moments, "b")
+    npt.assert_allclose([float(np.ravel(c)[0]) for c in got], want, rtol=1e-5)
