@@ -82,6 +82,21 @@ def density_based_discretization(tesseroids, density):
     return np.atleast_2d(pieces)
 
 
+def _evaluate(density, radii):
+    """``density`` at every radius: one vectorised call when the function accepts arrays (checked
+    against scalar calls at both ends), otherwise one call per radius (numba-jitted scalar
+    functions, functions with branches)."""
+    if radii.size > 64:
+        try:
+            values = np.asarray(density(radii), dtype=np.float64)
+            if (values.shape == radii.shape and values[0] == density(float(radii[0]))
+                    and values[-1] == density(float(radii[-1]))):  # fmt: skip
+                return values
+        except Exception:  # noqa: BLE001, S110 - any failure means "not vectorisable"
+            pass
+    return np.array([density(r) for r in radii.tolist()], dtype=np.float64)
+
+
 def density_at_radial_nodes(tesseroids, density):
     """``density(radius_p)`` at the two radial Gauss-Legendre nodes of every tesseroid
     (``radius_p`` as in :55-57)."""
@@ -89,5 +104,5 @@ def density_at_radial_nodes(tesseroids, density):
     values = []
     for node in (-GLQ_NODE, GLQ_NODE):
         radius_p = 0.5 * (top - bottom) * node + 0.5 * (top + bottom)
-        values.append(np.array([density(r) for r in radius_p.tolist()], dtype=np.float64))
+        values.append(_evaluate(density, radius_p))
     return values[0], values[1]
