@@ -521,7 +521,8 @@ int dipole_magnetic_dev_impl(const double* oe, const double* on, const double* o
 }
 
 // tesseroid_gravity: one field per pass (potential or g_z); workspace = [packed][partials]
-int g_tess_variant = 2;  // 0: first build; 1: root records + deferred walks; 2: 1 + fast far field
+int g_tess_variant = 2;  // 0: first build; 1: root records + deferred walks; 2: 1 + fast far field;
+                         // 3: 2 + the library's own sin / cos / acos in the walks (not yet measured)
 
 size_t tesseroid_ws_bytes(int64_t n_obs, int64_t n_src, int sms)
 {
@@ -581,9 +582,12 @@ int tesseroid_dev_impl(const double* lon, const double* lat, const double* rad, 
     } else if (variant == 1) {
         if (field == F_POT) tesseroid_deferred_kernel<F_POT, false><<<grid, kTessBlock, 0, st>>>(a);
         else tesseroid_deferred_kernel<F_U, false><<<grid, kTessBlock, 0, st>>>(a);
-    } else {
+    } else if (variant == 2) {
         if (field == F_POT) tesseroid_deferred_kernel<F_POT, true><<<grid, kTessBlock, 0, st>>>(a);
         else tesseroid_deferred_kernel<F_U, true><<<grid, kTessBlock, 0, st>>>(a);
+    } else {
+        if (field == F_POT) tesseroid_deferred_kernel<F_POT, true, OwnTrig><<<grid, kTessBlock, 0, st>>>(a);
+        else tesseroid_deferred_kernel<F_U, true, OwnTrig><<<grid, kTessBlock, 0, st>>>(a);
     }
     CU(cudaGetLastError());
     g_launches += chunks > 1 ? 3 : 2;
@@ -843,7 +847,7 @@ int hb200_set_variant(int variant)
 int hb200_get_variant(void) { return g_variant; }
 int hb200_set_tesseroid_variant(int variant)
 {
-    if (variant < 0 || variant > 2) return fail(HB200_EINVAL, "tesseroid variant must be 0, 1 or 2");
+    if (variant < 0 || variant > 3) return fail(HB200_EINVAL, "tesseroid variant must be 0 .. 3");
     g_tess_variant = variant;
     return HB200_OK;
 }

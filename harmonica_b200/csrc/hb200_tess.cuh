@@ -29,6 +29,7 @@
 // Only the ORDER in which a thread adds its pairs changes with the last item.
 #pragma once
 #include "hb200_math.cuh"
+#include "hb200_trig.cuh"
 #include "hb200_xmath.cuh"
 
 namespace hb {
@@ -82,6 +83,21 @@ HB_HD void tess_make_obs(TessObs& o, double lon, double lat, double rad)
     o.slam = sin(o.lam);
 }
 
+// Where the walk takes its sin / cos / acos from: CUDA's (glibc's in the host build) or the
+// library's own bounded-angle sequences (hb200_trig.cuh; kernel variant 3).
+struct LibmTrig {
+    static HB_HD double sin_(double x) { return sin(x); }
+    static HB_HD double cos_(double x) { return cos(x); }
+    static HB_HD void sincos_(double x, double& s, double& c) { s = sin(x); c = cos(x); }
+    static HB_HD double acos_(double x) { return acos(x); }
+};
+struct OwnTrig {
+    static HB_HD double sin_(double x) { double s, c; fast_sincos(x, s, c); return s; }
+    static HB_HD double cos_(double x) { return fast_cos(x); }
+    static HB_HD void sincos_(double x, double& s, double& c) { fast_sincos(x, s, c); }
+    static HB_HD double acos_(double x) { return fast_acos(x); }
+};
+
 // ---- the observer-independent parts of one tesseroid -----------------------------------------
 struct TessDims {
     double l_lon, l_lat, l_rad;  // _tesseroid_dimensions
@@ -97,31 +113,35 @@ struct TessNodes {
 };
 
 // _tesseroid_utils.py:261-279
+template <class TRIG = LibmTrig>
 HB_HD void tess_dims(TessDims& d, double w, double e, double s, double n, double bottom, double top)
 {
     const double wr = w * kDeg2Rad, er = e * kDeg2Rad, sr = s * kDeg2Rad, nr = n * kDeg2Rad;
     const double latitude_center = (nr + sr) / 2;
-    d.l_lat = top * acos(sin(nr) * sin(sr) + cos(nr) * cos(sr));
-    const double sc = sin(latitude_center), cc = cos(latitude_center);
-    d.l_lon = top * acos(sc * sc + cc * cc * cos(er - wr));
+    double sin_n, cos_n, sin_s, cos_s, sc, cc;
+    TRIG::sincos_(nr, sin_n, cos_n);
+    TRIG::sincos_(sr, sin_s, cos_s);
+    d.l_lat = top * TRIG::acos_(sin_n * sin_s + cos_n * cos_s);
+    TRIG::sincos_(latitude_center, sc, cc);
+    d.l_lon = top * TRIG::acos_(sc * sc + cc * cc * TRIG::cos_(er - wr));
     d.l_rad = top - bottom;
 }
 
 // the point _distance_tesseroid_point (:282-300) measures to, as distance_spherical sees it
+template <class TRIG = LibmTrig>
 HB_HD void tess_centre(TessCentre& c, double w, double e, double s, double n, double bottom,
                        double top)
 {
     c.lam = ((w + e) / 2) * kDeg2Rad;
     const double latitude_p = ((s + n) / 2) * kDeg2Rad;
     c.rad = (bottom + top) / 2;
-    c.cphi = cos(latitude_p);
-    c.sphi = sin(latitude_p);
+    TRIG::sincos_(latitude_p, c.sphi, c.cphi);
 }
 
 // utils.py:164-201 between the observer and the centre
-HB_HD double tess_distance(const TessObs& o, const TessCentre& c)
+template <class TRIG = LibmTrig> HB_HD double tess_distance(const TessObs& o, const TessCentre& c)
 {
-    const double coslambda = cos(c.lam - o.lam);
+    const double coslambda = TRIG::cos_(c.lam - o.lam);
     const double cospsi = c.sphi * o.sphi + c.cphi * o.cphi * coslambda;
     const double dr = o.rad - c.rad;
     return sqrt(dr * dr + 2 * o.rad * c.rad * (1 - cospsi));
@@ -143,6 +163,7 @@ HB_HD bool tess_split_counts(double distance, const TessDims& d, double ratio, b
 // the node coordinates and masses of gauss_legendre_quadrature (:19-107). density[k] belongs to
 // the radial node k: equal for a homogeneous tesseroid; density(radius_p) of the variable-density
 // quadrature (_tesseroid_variable_density.py:20-106) otherwise.
+template <class TRIG = LibmTrig>
 HB_HD void tess_nodes(TessNodes& q, double w, double e, double s, double n, double bottom,
                       double top, const double* density)
 {
@@ -152,8 +173,7 @@ HB_HD void tess_nodes(TessNodes& q, double w, double e, double s, double n, doub
         const double node = i ? kGlqNode : -kGlqNode;
         q.lam[i] = (0.5 * (e - w) * node + 0.5 * (e + w)) * kDeg2Rad;
         const double latitude_p = (0.5 * (n - s) * node + 0.5 * (n + s)) * kDeg2Rad;
-        q.cphi[i] = cos(latitude_p);
-        q.sphi[i] = sin(latitude_p);
+        TRIG::sincos_(latitude_p, q.sphi[i], q.cphi[i]);
         q.rad[i] = 0.5 * (top - bottom) * node + 0.5 * (top + bottom);
     }
 #pragma unroll
@@ -167,11 +187,12 @@ HB_HD void tess_nodes(TessNodes& q, double w, double e, double s, double n, doub
 
 // sum over the eight nodes in the reference's order (latitude, radius, longitude) with the
 // kernels of point.py:324-354. FIELD: F_POT or F_U (radial component).
-template <int FIELD> HB_HD double tess_glq_nodes(const TessObs& o, const TessNodes& q, unsigned& flags)
+template <int FIELD, class TRIG = LibmTrig>
+HB_HD double tess_glq_nodes(const TessObs& o, const TessNodes& q, unsigned& flags)
 {
     double coslambda[2];
 #pragma unroll
-    for (int i = 0; i < 2; i++) coslambda[i] = cos(q.lam[i] - o.lam);
+    for (int i = 0; i < 2; i++) coslambda[i] = TRIG::cos_(q.lam[i] - o.lam);
     double result = 0.0;
 #pragma unroll
     for (int j = 0; j < 2; j++)
@@ -220,7 +241,7 @@ HB_HD void tess_walk_begin(TessWalk& w, const double* tess, double density0, dou
 // this pair ends. `stack` holds STACK x 6 doubles and is private to the caller. (STACK /
 // MAX_LEAVES are template parameters only so that the tests can provoke the overflow errors like
 // the reference's do.)
-template <int FIELD, int STACK = kTessStack, int MAX_LEAVES = kTessMaxLeaves>
+template <int FIELD, int STACK = kTessStack, int MAX_LEAVES = kTessMaxLeaves, class TRIG = LibmTrig>
 HB_HD void tess_walk_step(const TessObs& o, double ratio, bool radial, double* stack, TessWalk& wk,
                           double& acc, unsigned& flags)
 {
@@ -228,10 +249,10 @@ HB_HD void tess_walk_step(const TessObs& o, double ratio, bool radial, double* s
     const double w = q[0], e = q[1], s = q[2], n = q[3], bottom = q[4], top = q[5];
     wk.stack_top -= 1;
     TessDims dims;
-    tess_dims(dims, w, e, s, n, bottom, top);
+    tess_dims<TRIG>(dims, w, e, s, n, bottom, top);
     TessCentre centre;
-    tess_centre(centre, w, e, s, n, bottom, top);
-    const double distance = tess_distance(o, centre);
+    tess_centre<TRIG>(centre, w, e, s, n, bottom, top);
+    const double distance = tess_distance<TRIG>(o, centre);
     int n_lon, n_lat, n_rad;
     if (!tess_split_counts(distance, dims, ratio, radial, n_lon, n_lat, n_rad)) {
         flags |= FLAG_ZERO_DIV;
@@ -265,22 +286,22 @@ HB_HD void tess_walk_step(const TessObs& o, double ratio, bool radial, double* s
             return;
         }
         TessNodes nodes;
-        tess_nodes(nodes, w, e, s, n, bottom, top, wk.density);
-        acc += tess_glq_nodes<FIELD>(o, nodes, flags);
+        tess_nodes<TRIG>(nodes, w, e, s, n, bottom, top, wk.density);
+        acc += tess_glq_nodes<FIELD, TRIG>(o, nodes, flags);
         wk.n_leaves += 1;
     }
 }
 
 // One (observer, tesseroid) pair: adds the quadrature of every leaf of the adaptive
 // discretisation to `acc` in the reference's order. Returns the number of leaves.
-template <int FIELD, int STACK = kTessStack, int MAX_LEAVES = kTessMaxLeaves>
+template <int FIELD, int STACK = kTessStack, int MAX_LEAVES = kTessMaxLeaves, class TRIG = LibmTrig>
 HB_HD int tess_pair(const TessObs& o, const double* tess, double density0, double density1,
                     double ratio, bool radial, double* stack, double& acc, unsigned& flags)
 {
     TessWalk wk;
     tess_walk_begin(wk, tess, density0, density1, stack);
     while (wk.stack_top >= 0)
-        tess_walk_step<FIELD, STACK, MAX_LEAVES>(o, ratio, radial, stack, wk, acc, flags);
+        tess_walk_step<FIELD, STACK, MAX_LEAVES, TRIG>(o, ratio, radial, stack, wk, acc, flags);
     return wk.n_leaves;
 }
 
@@ -538,7 +559,7 @@ __global__ void __launch_bounds__(kTessBlock) tesseroid_kernel(const TessArgs a)
 // Walk the pairs a thread has deferred: every lane goes through ITS list with ITS stack, one pop
 // per trip of a single loop, so the lanes of a warp work concurrently whatever the shapes of
 // their discretisation trees.
-template <int FIELD, bool FAST>
+template <int FIELD, bool FAST, class TRIG>
 __device__ __forceinline__ void tess_walk_deferred(const TessObs& o, const TessArgs& a,
                                                    const int* defer, int& n_defer, int64_t begin,
                                                    double* stack, double& acc, unsigned& flags)
@@ -554,16 +575,18 @@ __device__ __forceinline__ void tess_walk_deferred(const TessObs& o, const TessA
             const double* rec = a.packed + (begin + defer[k++]) * kTessRec;
             tess_walk_begin(wk, rec, rec[6], rec[FAST ? kTessRho1Fast : kTessRho1], stack);
         }
-        tess_walk_step<FIELD>(o, a.ratio, a.radial != 0, stack, wk, acc, flags);
+        tess_walk_step<FIELD, kTessStack, kTessMaxLeaves, TRIG>(o, a.ratio, a.radial != 0, stack, wk, acc,
+                                                                flags);
     }
     n_defer = 0;
 }
 
-// Variants 1 and 2 (FAST): root records + deferred walks. The loop over a tile is uniform (root
+// Variants 1, 2 (FAST) and 3 (FAST + the library's own trig in the walks): root records +
+// deferred walks. The loop over a tile is uniform (root
 // decision from the record, unsplit pairs integrated at once, three cosines per pair); a pair
 // that splits is only noted. When any lane of the warp has kTessDefer pairs noted, and at the
 // end, all lanes walk their lists together.
-template <int FIELD, bool FAST>
+template <int FIELD, bool FAST, class TRIG = LibmTrig>
 __global__ void __launch_bounds__(kTessBlock) tesseroid_deferred_kernel(const TessArgs a)
 {
     __shared__ double tile[kTessTile * kTessRec];
@@ -592,10 +615,10 @@ __global__ void __launch_bounds__(kTessBlock) tesseroid_deferred_kernel(const Te
                             : tess_root<FIELD>(o, tile + s * kTessRec, a.ratio, a.radial != 0, acc, flags);
             if (root == 0) defer[n_defer++] = (int)(t0 - begin) + s;
             if (__any_sync(0xffffffffu, n_defer == kTessDefer))
-                tess_walk_deferred<FIELD, FAST>(o, a, defer, n_defer, begin, stack, acc, flags);
+                tess_walk_deferred<FIELD, FAST, TRIG>(o, a, defer, n_defer, begin, stack, acc, flags);
         }
     }
-    tess_walk_deferred<FIELD, FAST>(o, a, defer, n_defer, begin, stack, acc, flags);
+    tess_walk_deferred<FIELD, FAST, TRIG>(o, a, defer, n_defer, begin, stack, acc, flags);
     if (live) {
         if (gridDim.y == 1) a.out[i] = acc * a.scale;
         else a.out[(int64_t)blockIdx.y * a.n_obs + i] = acc;

@@ -89,8 +89,10 @@ int hb200_get_variant(void);
 /* tesseroid kernels: 1 = observer-independent parts of every tesseroid precomputed into root
  * records, pairs that split deferred and walked by all lanes of a warp together; 2 (default) =
  * as 1 with an arithmetic-only far field (cosine of the longitude difference from precomputed
- * factors, the library's reciprocal square root, squared split thresholds); 0 = first build
- * (every pair walked where it is met) */
+ * factors, the library's reciprocal square root, squared split thresholds); 3 = as 2 with the
+ * library's own bounded-angle sin / cos / acos in the walks (written after the round-1 GPU budget
+ * ended: validated on the host build only, not the default); 0 = first build (every pair walked
+ * where it is met) */
 int hb200_set_tesseroid_variant(int variant);
 int hb200_get_tesseroid_variant(void);
 /* number of CUDA kernels this library has launched so far (all entry points) */

@@ -141,7 +141,10 @@ void hbt_tesseroid_loop_deferred(int field, int64_t n_obs, const double* lon, co
                 const double* rec = records + defer[k] * kTessRec;
                 int leaves;
                 const double rho1 = rec[fast ? kTessRho1Fast : kTessRho1];
-                if (field == F_POT) leaves = tess_pair<F_POT>(o, rec, rec[6], rho1, ratio, radial != 0, stack, acc, f);
+                if (fast == 2) {
+                    if (field == F_POT) leaves = tess_pair<F_POT, kTessStack, kTessMaxLeaves, OwnTrig>(o, rec, rec[6], rho1, ratio, radial != 0, stack, acc, f);
+                    else leaves = tess_pair<F_U, kTessStack, kTessMaxLeaves, OwnTrig>(o, rec, rec[6], rho1, ratio, radial != 0, stack, acc, f);
+                } else if (field == F_POT) leaves = tess_pair<F_POT>(o, rec, rec[6], rho1, ratio, radial != 0, stack, acc, f);
                 else leaves = tess_pair<F_U>(o, rec, rec[6], rho1, ratio, radial != 0, stack, acc, f);
                 if (counts) counts[i * n_tess + defer[k]] = leaves;
             }
@@ -179,3 +182,19 @@ unsigned hbt_tesseroid_overflow(int which, const double* point, const double* te
 }
 
 }  // extern "C"
+
+#include "../../harmonica_b200/csrc/hb200_trig.cuh"
+extern "C" {
+// op 0 sin, 1 cos (fast_sincos), 2 acos (fast_acos)
+void hbt_trig(int op, int64_t n, const double* a, double* out)
+{
+    for (int64_t i = 0; i < n; i++) {
+        if (op == 2) out[i] = hb::fast_acos(a[i]);
+        else {
+            double s, c;
+            hb::fast_sincos(a[i], s, c);
+            out[i] = op == 0 ? s : c;
+        }
+    }
+}
+}

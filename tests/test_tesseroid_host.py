@@ -717,3 +717,60 @@ def test_variable_density_wrapper_with_a_stand_in_library(monkeypatch):
                             hb.tesseroid_gravity(grid, tesseroid, 2900.0, field))  # fmt: skip
     with pytest.raises(NotImplementedError, match="radial_adaptive_discretization"):
         hb.tesseroid_gravity(grid, tesseroid, lambda radius: 2900.0, "g_z", radial_adaptive_discretization=True)
+
+
+# ------------------------------------------------------------------ own trig in the walks (variant 3)
+def harness_trig(op, values):
+    H = harness()
+    dp = ctypes.POINTER(ctypes.c_double)
+    a = np.ascontiguousarray(values, dtype=np.float64)
+    out = np.empty_like(a)
+    H.hbt_trig(int(op), ctypes.c_int64(a.size), a.ctypes.data_as(dp), out.ctypes.data_as(dp))
+    return out
+
+
+def test_own_trig_sequences_accuracy():
+    """hb200_trig.cuh against glibc: sin / cos for |x| < 4 pi and acos on [-1, 1] within 1 ulp;
+    acos beyond 1 is NaN like libm's (the split test then reads "no split")"""
+    rng = np.random.default_rng(0)
+
+    def ulps(got, want):
+        spacing = np.spacing(np.abs(want))
+        spacing[spacing == 0] = 5e-324
+        return np.abs(got - want) / spacing
+
+    x = np.concatenate([rng.uniform(-4 * np.pi, 4 * np.pi, 400_000), rng.uniform(-1e-3, 1e-3, 50_000),
+                        np.arange(-8, 9) * np.pi / 2, np.arange(-8, 9) * np.pi / 2 + 1e-9])  # fmt: skip
+    assert ulps(harness_trig(0, x), np.sin(x)).max() <= 1.0
+    assert ulps(harness_trig(1, x), np.cos(x)).max() <= 1.0
+    c = np.concatenate([rng.uniform(-1, 1, 300_000), 1 - 10.0 ** rng.uniform(-16, -1, 200_000),
+                        -1 + 10.0 ** rng.uniform(-16, -1, 100_000),
+                        [1.0, -1.0, 0.0, 0.5, -0.5, 1 + 2.3e-16, -1 - 2.3e-16]])  # fmt: skip
+    got = harness_trig(2, c)
+    with np.errstate(invalid="ignore"):
+        want = np.arccos(c)
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    ok = np.isfinite(want)
+    assert ulps(got[ok], want[ok]).max() <= 1.0
+
+
+@pytest.mark.parametrize("field,radial", MODES)
+def test_own_trig_walks_match_the_oracle(field, radial):
+    """kernel variant 3 (host emulation): the walks take sin / cos / acos from hb200_trig.cuh. Same
+    leaves as the reference in these models, values within the parity bar"""
+    g, cases = _cases()
+    for name in ("random", "four", "wrapped"):
+        coords, tesseroids, density = cases[name]
+        tesseroids = np.atleast_2d(np.asarray(tesseroids, dtype=float))
+        if (tesseroids[:, 0] > tesseroids[:, 1]).any():
+            tesseroids = O.longitude_continuity(tesseroids)
+        density = np.atleast_1d(np.asarray(density, dtype=float))
+        want, want_counts = O.tesseroid_gravity(coords, tesseroids, density, field, radial, return_counts=True)
+        got, counts, flags = harness_tesseroid_deferred(coords, tesseroids, density, field, radial, 64, fast=2)
+        if field == "g_z":
+            got *= -1e5
+        assert flags == 0
+        assert np.array_equal(counts, want_counts)
+        want = np.asarray(want).ravel()
+        bar = max(1e-9, 4 * reference_conditioning(coords, tesseroids, density, field, radial, trials=2))
+        assert np.max(np.abs(got - want)) <= bar * np.max(np.abs(want))
