@@ -3,29 +3,44 @@
 bench.py -- throughput of the pairwise forward-modelling hot path on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
-                    [--workload layer_gz|c1_gz|tensor|mag_b|eqs] [--scaling weak|strong]
+                    [--workload layer_gz|c1_gz|tensor|mag_b|eqs|tess_gz]
+                    [--scaling strong|weak] [--shard observers|sources]
 
 A "step" is one pass of the hot path over one batch of synthetic input. The
 default workload is BASELINE.json configs[1]: `prism_layer.gravity()` (g_z) of
 a 500x500 topography layer (250k prisms) on a 500x500 observation grid at
-1 km height = 6.25e10 prism-observer pairs per step and per GPU.
+1 km height. With N > 1 ranks (torchrun, one process per GPU) the default is
+STRONG scaling of that fixed problem through the repo's own multi-GPU API
+(harmonica_b200/distributed.py): observers sharded over the ranks, sources
+replicated, the result gathered on rank 0 over NCCL inside the timed region.
 
 Prints ONE JSON line (rank 0):
   value        pair evaluations / s, whole job, inputs resident in HBM, CUDA
-               events on the launching stream, max over ranks
+               events on the launching stream, max over ranks (N > 1: kernels +
+               NCCL gather)
   e2e          the same metric through the public API on host (numpy) buffers,
-               host<->device copies inside the timed region
-  roofline     FP64-vector-pipe roofline of the dominant kernel: algorithmic
-               flops (2 x I_pair of SURVEY 8d) per second over the FP64 FMA
-               peak measured on this device by the library's DFMA probe
-  cpu_baseline the CPU oracle (port of the reference's loop) on the host cores
-`--impl reference` times the reference's CPU algorithm (oracle port, OpenMP on
-all host cores, the reference's prange-over-observers loop shape) on a bounded
+               host<->device copies (and the gather) inside the timed region
+  roofline     FP64-vector-pipe roofline of the dominant kernel: EXECUTED FP64
+               instructions (ncu source-page counts of this very kernel build,
+               profiles/executed_per_pair.json) x 2 flop over the FP64 FMA peak
+               measured on this device by the library's DFMA probe;
+               `algorithmic` carries the SURVEY 8d convention (instructions of
+               the REFERENCE algorithm), which exceeds 1 because the merged
+               kernels execute fewer instructions per pair
+  also         short runs of the other BASELINE configs (tensor, mag_b, eqs)
+  north_star   BASELINE configs[2]: the six tensor components of 1M prisms on 1M
+               observers, end to end through the (sharded) public API, 1 step
+  cpu_baseline the reference's CPU path on the host cores: the Numba
+               parallel=True restatement (oracle/numba_loops.py) and the
+               C/OpenMP port (oracle/choclo_port.c), both reported
+`--impl reference` times the reference's CPU algorithm (Numba prange over
+observers, all host cores, OMP_NUM_THREADS of torchrun ignored) on a bounded
 observer sample of the same workload.
 """
 
 import argparse
 import ctypes
+import hashlib
 import json
 import os
 import statistics
@@ -40,61 +55,93 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+METRIC = "prism-observer pair evals/sec"
 # FP64-pipe instruction equivalents per pair of the REFERENCE algorithm
 I_PAIR = {"layer_gz": 1068, "c1_gz": 1068, "tensor": 2020, "mag_b": 2100, "eqs": 26.5,
-          # tesseroids: one stack pop (7 sin/cos, 2 acos, the distance to the
-          # centre, 3 divisions) ~ 390 and one 2x2x2 quadrature leaf ~ 456 FP64 instructions of the
-          # reference algorithm; an unsplit pair is one pop + one leaf, near pairs cost more (the
-          # measured leaves per pair of the CPU sample are reported next to the rate)
-          "tess_gz": 390 + 456}
+          # tesseroids: one stack pop ~ 390 and one 2x2x2 quadrature leaf
+          # ~ 456 FP64 instructions of the reference algorithm per unsplit pair
+          "tess_gz": 390 + 456}  # fmt: skip
 NOMINAL_FP64_FLOPS = 148 * 64 * 2 * 1.965e9  # 37.2 TFLOP/s
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE prism_kernel launch of the default workload
-# at full size (profiles/r1_traffic_layer_gz_full_launch.csv; 22.6 MB read + 1.5 MB written;
-# algorithmic: 6 MB observers + 16 MB packed prisms + 2 MB result). L2 serves 31.8 GB of tile loads.
-DRAM_TRAFFIC_PER_LAUNCH = {"layer_gz": 22625024 + 1515776}
-# executed thread-instructions per pair of the CURRENT kernels, from the committed ncu source
-# pages (profiles/r1_opmix_*_final.txt): (FP64 pipe, all other pipes)
-EXECUTED_PER_PAIR = {"layer_gz": (224.7, 147.4), "c1_gz": (224.7, 147.4), "tensor": (284.1, 171.6),
-                     "eqs": (12.0, 5.1)}
+EXECUTED_FILE = os.path.join(ROOT, "profiles", "executed_per_pair.json")
+CSRC = os.path.join(ROOT, "harmonica_b200", "csrc")
+
+
+def host_cores():
+    """Host threads this process may use (torchrun's OMP_NUM_THREADS=1 is ignored on purpose)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def csrc_sha16(files):
+    h = hashlib.sha256()
+    for name in sorted(files):
+        with open(os.path.join(CSRC, name), "rb") as f:
+            h.update(name.encode() + b"\0" + f.read())
+    return h.hexdigest()[:16]
+
+
+def executed_for(workload):
+    """ncu-measured executed instructions per pair of the CURRENT kernel build, or a note saying
+    that the committed numbers belong to another build (then nothing is printed as measured)."""
+    try:
+        with open(EXECUTED_FILE) as f:
+            table = json.load(f)
+    except OSError:
+        return None, "profiles/executed_per_pair.json missing"
+    entry = table.get(workload)
+    if not entry:
+        return None, f"no ncu capture recorded for workload {workload}"
+    sha = csrc_sha16(entry["files"])
+    if sha != entry["sha16"]:
+        return None, (f"stale: {entry['source']} was captured on kernel sources {entry['sha16']}, "
+                      f"this build is {sha}")
+    return entry, None
 
 
 # ------------------------------------------------------------------ workloads
-def make_workload(name, n_obs, n_src, rank):
+def make_workload(name, n_obs=0, n_src=0, shift=0):
     """Synthetic inputs (SURVEY 8d seeds). Returns dict of host float64 arrays + meta."""
-    from _common import config1, layer_config2, random_prisms
+    from _common import config1, layer_config2
 
     if name == "layer_gz":
         coords, east_c, north_c, bottom, top, density = layer_config2()
-        # weak scaling: every rank owns its own 500x500 observation grid (a different height)
-        coords = (coords[0], coords[1], coords[2] + 25.0 * rank)
+        coords = (coords[0], coords[1], coords[2] + 25.0 * shift)
         if n_obs:  # profiling runs: a strided subset of the observation grid
             pick = np.linspace(0, coords[0].size - 1, n_obs).astype(np.int64)
             coords = tuple(np.ascontiguousarray(c[pick]) for c in coords)
-        return dict(kind="layer", coords=coords, east_c=east_c, north_c=north_c, bottom=bottom,
-                    top=top, density=density, n_src=east_c.size * north_c.size, mask=1 << 3,
-                    nf=1, desc="prism_layer.gravity g_z, 500x500 layer (250k prisms, 1% NaN, "
-                    "1% zero density) x 500x500 grid at 1 km")  # fmt: skip
+        skipped = (density == 0) | np.isnan(density) | np.isnan(top) | np.isnan(bottom) | (top - bottom < 0)
+        n_eval = int(east_c.size * north_c.size - skipped.sum())
+        return dict(kind="prism_layer", coords=coords, n_src=east_c.size * north_c.size, n_eval=n_eval,
+                    sources=dict(easting=east_c, northing=north_c, bottom=bottom, top=top, density=density),
+                    fields="g_z", nf=1, launches=2,
+                    desc="prism_layer.gravity g_z, 500x500 layer (250k prisms, 1% NaN, 1% zero density) "
+                         "x 500x500 grid at 1 km")  # fmt: skip
     if name == "c1_gz":
         coords, prisms, density = config1(n_src or 10_000, n_obs or 10_000, seed=1)
-        return dict(kind="prism", coords=coords, prisms=prisms, density=density,
-                    n_src=prisms.shape[0], mask=1 << 3, nf=1,
+        return dict(kind="prism_gravity", coords=coords, sources=dict(prisms=prisms, density=density),
+                    n_src=prisms.shape[0], n_eval=prisms.shape[0], fields="g_z", nf=1, launches=3,
                     desc="prism_gravity g_z, 10k random prisms x 10k observers")
-    if name == "tensor":
-        n_src, n_obs = n_src or 1_000_000, n_obs or 65_536
-        coords, prisms, density = config1(n_src, n_obs, seed=3 + 100 * rank, scale=10.0)
-        return dict(kind="prism", coords=coords, prisms=prisms, density=density, n_src=n_src,
-                    mask=0x3F0, nf=6,
+    if name in ("tensor", "tensor_1m"):
+        n_src = n_src or 1_000_000
+        n_obs = n_obs or (1_000_000 if name == "tensor_1m" else 65_536)
+        coords, prisms, density = config1(n_src, n_obs, seed=3 + 100 * shift, scale=10.0)
+        return dict(kind="prism_gravity", coords=coords, sources=dict(prisms=prisms, density=density),
+                    n_src=n_src, n_eval=n_src, nf=6, launches=2,
+                    fields=("g_ee", "g_nn", "g_zz", "g_en", "g_ez", "g_nz"),
                     desc=f"prism_gravity 6 tensor components fused, {n_src} prisms x {n_obs} observers")
     if name == "mag_b":
         n_src, n_obs = n_src or 200_000, n_obs or 131_072
-        coords, prisms, _ = config1(n_src, n_obs, seed=4 + 100 * rank, scale=4.0)
+        coords, prisms, _ = config1(n_src, n_obs, seed=4 + 100 * shift, scale=4.0)
         rng = np.random.default_rng(4)
         mag = tuple(rng.normal(size=n_src) for _ in range(3))
-        return dict(kind="mag", coords=coords, prisms=prisms, mag=mag, n_src=n_src, mask=7, nf=3,
+        return dict(kind="prism_magnetic", coords=coords, sources=dict(prisms=prisms, magnetization=mag),
+                    n_src=n_src, n_eval=n_src, fields="b", nf=3, launches=2,
                     desc=f"prism_magnetic b, {n_src} prisms x {n_obs} observers")
     if name == "eqs":
         n_src, n_obs = n_src or 4_000_000, n_obs or 262_144
-        rng = np.random.default_rng(5 + 100 * rank)
+        rng = np.random.default_rng(5 + 100 * shift)
         side = int(np.ceil(np.sqrt(n_src)))
         gx, gy = np.meshgrid(np.arange(side), np.arange(side))
         pe = (gx.ravel()[:n_src] + rng.uniform(-0.3, 0.3, n_src)) * 500.0
@@ -103,14 +150,14 @@ def make_workload(name, n_obs, n_src, rank):
         coefs = rng.normal(size=n_src)
         coords = (rng.uniform(0, side * 500.0, n_obs), rng.uniform(0, side * 500.0, n_obs),
                   rng.uniform(0, 500.0, n_obs))  # fmt: skip
-        return dict(kind="eqs", coords=coords, points=(pe, pn, pu), coefs=coefs, n_src=n_src,
-                    mask=1, nf=1,
+        return dict(kind="eqs_predict", coords=coords, sources=dict(points=(pe, pn, pu), coefs=coefs),
+                    n_src=n_src, n_eval=n_src, fields="potential", nf=1, launches=3,
                     desc=f"EquivalentSources.predict (sum coef/r), {n_src} sources x {n_obs} observers")
     if name == "tess_gz":
         # a 2 x 2 degree global layer of tesseroids (topography-like tops) seen from 10 km above
         # the reference sphere: most pairs are far (one leaf), the ones below each observer split
         n_obs = n_obs or 65_536
-        rng = np.random.default_rng(6 + 100 * rank)
+        rng = np.random.default_rng(6 + 100 * shift)
         R = 6371008.771415059
         lon_c, lat_c = np.meshgrid(np.arange(-179.0, 180.0, 2.0), np.arange(-89.0, 90.0, 2.0))
         top = R + 2e3 * np.sin(np.radians(3 * lon_c)) * np.cos(np.radians(2 * lat_c)) - 3e3
@@ -119,11 +166,31 @@ def make_workload(name, n_obs, n_src, rank):
         density = rng.uniform(2500, 3300, lon_c.size)
         coords = (rng.uniform(-180, 180, n_obs), np.degrees(np.arcsin(rng.uniform(-1, 1, n_obs))),
                   np.full(n_obs, R + 10e3))  # fmt: skip
-        return dict(kind="tess", coords=coords, tesseroids=np.ascontiguousarray(tess),
-                    density=density, n_src=tess.shape[0], mask=1 << 3, nf=1,
+        return dict(kind="tess", coords=coords, tesseroids=np.ascontiguousarray(tess), density=density,
+                    n_src=tess.shape[0], n_eval=tess.shape[0], fields="g_z", nf=1, launches=3,
                     desc=f"tesseroid_gravity g_z, {tess.shape[0]} tesseroids (2x2 degree global layer) "
-                    f"x {n_obs} observers at 10 km")  # fmt: skip
+                         f"x {n_obs} observers at 10 km")  # fmt: skip
     raise SystemExit(f"unknown workload {name}")
+
+
+def config_for(wl, name, args, world):
+    """The `config` object: identical in the B200 arm and the reference arm."""
+    if world == 1:
+        sharding = "single GPU"
+    elif args.shard == "sources":
+        sharding = f"sources sharded over {world} ranks, float64 reduce-sum to rank 0 (NCCL)"
+    elif args.scaling == "strong":
+        sharding = f"observers sharded over {world} ranks, sources replicated, gather to rank 0 (NCCL)"
+    else:
+        sharding = f"{world} independent replicas (weak), no collective"
+    n_obs = wl["coords"][0].size
+    replicas = world if (world > 1 and args.scaling == "weak" and args.shard != "sources") else 1
+    return {"workload": wl["desc"], "name": name, "observers": n_obs, "sources": wl["n_src"],
+            "pairs_per_step": float(n_obs) * wl["n_eval"] * replicas,
+            "pairs_counted": "observers x sources that pass the reference's skip rules "
+                             f"({wl['n_eval']} of {wl['n_src']})",
+            "sharding": sharding,
+            "l2": "GPU arm: flushed between timed iterations (256 MiB write); CPU arm: n/a"}  # fmt: skip
 
 
 # ------------------------------------------------------------- clock sampling
@@ -178,70 +245,135 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}  # fmt: skip
 
 
-# ------------------------------------------------------------------ reference arm
-def cpu_rate(wl, n_obs_sample, nthreads):
-    """Time the oracle (port of the reference's CPU loop) on the first n_obs_sample observers."""
+# ------------------------------------------------------------------ CPU arms
+def _oracle_modules():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O  # bench.py's cpu_baseline / reference legs may execute the oracle
 
-    sub = tuple(np.ascontiguousarray(c[:n_obs_sample]) for c in wl["coords"])
-    t0 = time.perf_counter()
-    if wl["kind"] == "layer":
-        O.prism_layer_gravity(sub, wl["east_c"], wl["north_c"], wl["bottom"], wl["top"],
-                              wl["density"], "g_z", nthreads=nthreads)
-    elif wl["kind"] == "prism":
-        fields = ("g_z",) if wl["nf"] == 1 else ("g_ee", "g_nn", "g_zz", "g_en", "g_ez", "g_nz")
-        for f in fields:  # the reference computes one field per call
-            O.prism_gravity(sub, wl["prisms"], wl["density"], f, nthreads=nthreads)
-    elif wl["kind"] == "mag":
-        O.prism_magnetic(sub, wl["prisms"], wl["mag"], "b", nthreads=nthreads)
-    elif wl["kind"] == "tess":
-        O.tesseroid_gravity(sub, wl["tesseroids"], wl["density"], "g_z", nthreads=nthreads)
+    O.build()
+    return O
+
+
+def _numba_loops(nthreads):
+    """The Numba restatement, on `nthreads` threads whatever torchrun exported."""
+    os.environ["NUMBA_NUM_THREADS"] = str(nthreads)
+    os.environ["OMP_NUM_THREADS"] = str(nthreads)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numba  # noqa: PLC0415
+    import numba_loops as NL  # noqa: PLC0415
+
+    numba.set_num_threads(min(nthreads, numba.config.NUMBA_NUM_THREADS))
+    return NL
+
+
+def cpu_rate(wl, n_sample, nthreads, kind):
+    """Time one CPU pass (Numba loops or the C/OpenMP port) on the first n_sample observers."""
+    sub = tuple(np.ascontiguousarray(c[:n_sample]) for c in wl["coords"])
+    s = wl.get("sources", {})
+    if kind == "numba":
+        NL = _numba_loops(nthreads)
+        t0 = time.perf_counter()
+        if wl["kind"] == "prism_layer":
+            NL.prism_layer_gravity(sub, s["easting"], s["northing"], s["bottom"], s["top"], s["density"], "g_z")
+        elif wl["kind"] == "prism_gravity":
+            fields = (wl["fields"],) if isinstance(wl["fields"], str) else wl["fields"]
+            for f in fields:  # the reference computes one field per call
+                NL.prism_gravity(sub, s["prisms"], s["density"], f)
+        elif wl["kind"] == "prism_magnetic":
+            NL.prism_magnetic_field(sub, s["prisms"], s["magnetization"])
+        elif wl["kind"] == "eqs_predict":
+            NL.eqs_predict(sub, s["points"], s["coefs"])
+        else:
+            raise ValueError("no Numba restatement of this workload")
     else:
-        O.eqs_predict(sub, wl["points"], wl["coefs"], nthreads=nthreads)
+        O = _oracle_modules()
+        t0 = time.perf_counter()
+        if wl["kind"] == "prism_layer":
+            O.prism_layer_gravity(sub, s["easting"], s["northing"], s["bottom"], s["top"], s["density"],
+                                  "g_z", nthreads=nthreads)
+        elif wl["kind"] == "prism_gravity":
+            fields = (wl["fields"],) if isinstance(wl["fields"], str) else wl["fields"]
+            for f in fields:
+                O.prism_gravity(sub, s["prisms"], s["density"], f, nthreads=nthreads)
+        elif wl["kind"] == "prism_magnetic":
+            O.prism_magnetic(sub, s["prisms"], s["magnetization"], "b", nthreads=nthreads)
+        elif wl["kind"] == "tess":
+            O.tesseroid_gravity(sub, wl["tesseroids"], wl["density"], "g_z", nthreads=nthreads)
+        else:
+            O.eqs_predict(sub, s["points"], s["coefs"], nthreads=nthreads)
     dt = time.perf_counter() - t0
-    return n_obs_sample * wl["n_src"] / dt, dt
+    return n_sample * wl["n_eval"] / dt, dt
 
 
-def size_cpu_sample(wl, target_s, nthreads):
-    """Observer sample sized for ~target_s seconds of CPU work (probe first)."""
+def size_cpu_sample(wl, target_s, nthreads, kind):
+    """Observer sample sized for ~target_s seconds of CPU work (probe first; the probe also
+    JIT-compiles the Numba loops / warms the thread pool)."""
     n_total = wl["coords"][0].size
     probe = max(nthreads, min(n_total, int(4e7 / wl["n_src"]) + 1))
-    rate, _ = cpu_rate(wl, probe, nthreads)  # also warms the thread pool
-    n = int(rate * target_s / wl["n_src"])
+    cpu_rate(wl, probe, nthreads, kind)  # compile / warm up
+    rate, _ = cpu_rate(wl, probe, nthreads, kind)
+    n = int(rate * target_s / wl["n_eval"])
     n = max(nthreads, min(n_total, n))
     return max(1, n // nthreads * nthreads) if n >= nthreads else n
+
+
+def cpu_kinds(wl):
+    kinds = []
+    if wl["kind"] != "tess":
+        try:
+            import numba  # noqa: F401, PLC0415
+
+            kinds.append("numba")
+        except ImportError:
+            pass
+    kinds.append("port")
+    return kinds
+
+
+CPU_DESCRIPTION = {
+    "numba": "oracle/numba_loops.py: Numba parallel=True restatement of the reference's jitted loop "
+             "(prange over observers) over the restated choclo kernels; bit-identical to the "
+             "reference's unmodified loops run through oracle/ref_shim.py",
+    "port": "oracle/*_port.c: C restatement of the same loop, OpenMP over observers",
+}  # fmt: skip
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # under torchrun only rank 0 runs the CPU arm
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle as O
-
-    O.build()
-    wl = make_workload(args.workload, args.n_obs, args.n_src, 0)
-    nthreads = O.max_threads()
-    n_sample = size_cpu_sample(wl, args.cpu_seconds, nthreads)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    wl = make_workload(args.workload, args.n_obs, args.n_src)
+    nthreads = host_cores()
+    kinds = cpu_kinds(wl)
+    kind = kinds[0]
+    n_sample = size_cpu_sample(wl, args.cpu_seconds, nthreads, kind)
     for _ in range(args.warmup):
-        cpu_rate(wl, n_sample, nthreads)
+        cpu_rate(wl, n_sample, nthreads, kind)
     t_total = 0.0
     for _ in range(args.steps):
-        _, dt = cpu_rate(wl, n_sample, nthreads)
+        _, dt = cpu_rate(wl, n_sample, nthreads, kind)
         t_total += dt
-    value = args.steps * n_sample * wl["n_src"] / t_total
+    value = args.steps * n_sample * wl["n_eval"] / t_total
+    other = None
+    if len(kinds) > 1:  # the other CPU implementation, one pass, for the record
+        n_other = size_cpu_sample(wl, min(args.cpu_seconds, 4.0), nthreads, kinds[1])
+        rate, dt = cpu_rate(wl, n_other, nthreads, kinds[1])
+        other = {"value": rate, "unit": "pair/s", "cores": nthreads, "kind": kinds[1],
+                 "sample": f"first {n_other} observers, one pass ({dt:.1f} s); {CPU_DESCRIPTION[kinds[1]]}"}
     line = {
-        "impl": "reference", "metric": "prism-observer pair evals/sec", "value": value,
+        "impl": "reference", "metric": METRIC, "value": value,
         "unit": "pair/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True,
+        "scaling": "strong" if args.shard == "sources" else args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["desc"], "name": args.workload},
+        "config": config_for(wl, args.workload, args, world),
         "cpu_baseline": {
-            "value": value, "unit": "pair/s", "cores": nthreads, "kind": "port",
+            "value": value, "unit": "pair/s", "cores": nthreads, "kind": kind,
             "sample": f"first {n_sample} of {wl['coords'][0].size} observers x all {wl['n_src']} "
-                      "sources per step; oracle/choclo_port.c (C restatement of the reference's "
-                      "numba prange-over-observers loop + choclo kernels), OpenMP, all host threads",
+                      f"sources per step; {CPU_DESCRIPTION[kind]}; {nthreads} host threads "
+                      f"(os.sched_getaffinity; OMP_NUM_THREADS of the launcher ignored)",
+            "also": other,
         },
         "e2e": {"value": value, "unit": "pair/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }  # fmt: skip
@@ -249,6 +381,181 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------ B200 arm
+class Stepper:
+    """step_dev(): one pass with device-resident inputs (async on torch's current stream,
+    collective included); step_host(): the end-to-end call on host numpy buffers."""
+
+    def __init__(self, wl, rank, world, scaling, shard):
+        import torch
+
+        import harmonica_b200 as hb
+        from harmonica_b200 import distributed as hbd
+
+        self.wl, self.hb, self.world = wl, hb, world
+        lib = hb._lib.load()
+        self.lib = lib
+        sharded = world > 1 and (scaling == "strong" or shard == "sources")
+        self.sharded = sharded
+        n_obs = wl["coords"][0].size
+        if wl["kind"] == "tess":
+            dev = torch.device("cuda", torch.cuda.current_device())
+            t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)  # noqa: E731
+            self.t = [t(c) for c in wl["coords"]] + [t(wl["tesseroids"]), t(wl["density"])]
+            self.out = torch.empty((1, n_obs), dtype=torch.float64, device=dev)
+            self.flags_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+            self.ws_bytes = lib.hb200_tesseroid_ws_bytes(n_obs, wl["n_src"])
+            self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
+            self.job = None
+            self.h2d = 8 * (3 * n_obs + 7 * wl["n_src"])
+            self.d2h = 8 * n_obs
+            self.pairs_per_step = float(n_obs) * wl["n_eval"] * (world if not sharded else 1)
+            return
+        group = None if sharded else "local"
+        self.job = hbd.ShardedJob(wl["kind"], wl["coords"], wl["sources"], wl["fields"],
+                                  shard if sharded else "observers", group=group, dst=0)
+        self.job.upload()
+        self.h2d = self.job.h2d_bytes
+        self.d2h = self.job.d2h_bytes if (not sharded or rank == 0) else 0
+        self.pairs_per_step = float(n_obs) * wl["n_eval"] * (world if not sharded else 1)
+
+    def step_dev(self):
+        import torch
+
+        if self.job is not None:
+            self.job.launch()
+            return
+        P = lambda x: ctypes.c_void_p(x.data_ptr())  # noqa: E731
+        t = self.t
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        self.hb._lib.check(self.lib.hb200_tesseroid_gravity_dev(
+            P(t[0]), P(t[1]), P(t[2]), t[0].numel(), P(t[3]), P(t[4]), self.wl["n_src"], 3, 0,
+            P(self.out), P(self.flags_dev), P(self.ws), self.ws_bytes, st))  # fmt: skip
+
+    def step_host(self):
+        import warnings
+
+        hb, wl, s = self.hb, self.wl, self.wl.get("sources", {})
+        if self.sharded:
+            return self.job.run()  # upload + kernels + NCCL collective + download on rank 0
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            if wl["kind"] == "prism_layer":
+                return hb.prism_layer_gravity(wl["coords"], s["easting"], s["northing"], s["bottom"],
+                                              s["top"], s["density"], "g_z")
+            if wl["kind"] == "prism_gravity":
+                return hb.prism_gravity(wl["coords"], s["prisms"], s["density"], wl["fields"],
+                                        disable_checks=True)
+            if wl["kind"] == "prism_magnetic":
+                return hb.prism_magnetic(wl["coords"], s["prisms"], s["magnetization"], "b",
+                                         disable_checks=True)
+            if wl["kind"] == "tess":
+                return hb.tesseroid_gravity(wl["coords"], wl["tesseroids"], wl["density"], "g_z",
+                                            disable_checks=True)
+            return hb.eqs_predict(wl["coords"], s["points"], s["coefs"])
+
+    def flags(self):
+        if self.job is not None:
+            return int(self.job.d["flags"].item())
+        return int(self.flags_dev.item())
+
+
+def measure(stepper, steps, warmup, rank, world, local, sample_clocks, e2e_steps=None):
+    """Device-timed steps (CUDA events, L2 flushed in between, max over ranks) + e2e steps."""
+    import torch
+    import torch.distributed as dist
+
+    dev = torch.device("cuda", local)
+    lib = stepper.lib
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    for _ in range(warmup):
+        stepper.step_dev()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local) if (sample_clocks and rank == 0) else None
+    if sampler:
+        sampler.start()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    barrier()
+    launches_before = lib.hb200_launch_count()
+    for k in range(steps):
+        l2_flush.fill_(k)  # flush L2 between timed iterations (outside the events)
+        starts[k].record()
+        stepper.step_dev()
+        ends[k].record()
+    barrier()
+    gpu_launches = int(lib.hb200_launch_count() - launches_before)  # counted by the library
+    clocks = sampler.stop() if sampler else None
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_s = float(total_ms.item()) * 1e-3
+    if stepper.flags() & 2:
+        raise SystemExit("zero-distance pair in the synthetic workload")
+    del l2_flush
+
+    # end to end through the public API: host numpy buffers in, host result out
+    e2e_steps = e2e_steps or steps
+    for _ in range(min(warmup, 2)):
+        stepper.step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        stepper.step_host()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_s.item())
+    pairs = stepper.pairs_per_step
+    return {"value": pairs * steps / total_s, "ms_per_step": 1e3 * total_s / steps,
+            "step_ms_min_max": [min(step_ms), max(step_ms)],
+            "e2e_value": pairs * e2e_steps / e2e_s, "e2e_ms_per_step": 1e3 * e2e_s / e2e_steps,
+            "gpu_launches": gpu_launches, "clocks": clocks}  # fmt: skip
+
+
+def roofline_for(name, per_gpu_rate, fp64_peak, clocks, full_size):
+    f_alg = 2.0 * I_PAIR[name]
+    alg = per_gpu_rate * f_alg
+    entry, why = executed_for(name)
+    roof = {"bound": "fp64", "unit": "TFLOP/s", "peak": fp64_peak / 1e12,
+            "peak_source": "measured on this device in this run: hb200_fp64_peak DFMA probe "
+                           "(MEASURED_PEAKS.json carries no FP64 entry; nominal 148 SM x 64 lanes x 2 x "
+                           "1.965 GHz = 37.2 TFLOP/s)"}  # fmt: skip
+    if entry:
+        f64, other = entry["fp64"], entry["other"]
+        achieved = per_gpu_rate * 2.0 * f64
+        roof.update({
+            "achieved": achieved / 1e12, "frac": achieved / fp64_peak,
+            "frac_of_nominal": achieved / NOMINAL_FP64_FLOPS,
+            "definition": "EXECUTED FP64-pipe thread instructions per pair (ncu source page of this "
+                          "kernel build) x 2 flop x pairs/s per GPU / peak: hardware utilisation of "
+                          "the FP64 vector pipe",
+            "executed": {"fp64_instr_per_pair": f64, "other_instr_per_pair": other,
+                         "kernel": entry["kernel"], "source": entry["source"], "sha16": entry["sha16"]},
+            "traffic": entry.get("dram_bytes_per_launch") if full_size else None,
+        })  # fmt: skip
+        if clocks and clocks.get("sm_mhz"):
+            slots = 148 * 4 * clocks["sm_mhz"] * 1e6 * 32  # thread-level issue slots / s
+            roof["executed"]["issue_bound_frac"] = per_gpu_rate * (2 * f64 + other) / slots
+            roof["executed"]["note"] = ("an FP64 warp instruction occupies 2 issue slots: time ~ "
+                                        "(2 FP64 + other) / issue rate (DESIGN.md section 4)")
+    else:
+        roof.update({"achieved": None, "frac": None, "traffic": None, "executed": None, "stale": why})
+    roof["algorithmic"] = {
+        "flops_per_pair": f_alg, "achieved": alg / 1e12, "speedup_over_peak": alg / fp64_peak,
+        "note": "SURVEY 8d convention: 2 x FP64-pipe instructions of the REFERENCE algorithm per pair; "
+                "> 1 means the merged-transcendental kernel needs fewer instructions than the "
+                "reference formulation would at 100 % of peak. NOT a hardware fraction."}  # fmt: skip
+    return roof
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -261,237 +568,102 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     torch.cuda.set_device(local)
-    dev = torch.device(f"cuda:{local}")
     lib = hb._lib.load()
     hb.init([local])
+    sharded = world > 1 and (args.scaling == "strong" or args.shard == "sources")
 
-    wl = make_workload(args.workload, args.n_obs, args.n_src, 0 if args.shard == "sources" else rank)
-    coords = wl["coords"]
-    if args.scaling == "strong" and world > 1:
-        n = coords[0].size
-        lo, hi = n * rank // world, n * (rank + 1) // world
-        coords = tuple(np.ascontiguousarray(c[lo:hi]) for c in coords)
-    n_obs, n_src, nf = coords[0].size, wl["n_src"], wl["nf"]
-    pairs_per_step_rank = float(n_obs) * float(n_src)
-
-    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)  # noqa: E731
-    oe, on, ou = (t(c) for c in coords)
-    out = torch.empty((nf, n_obs), dtype=torch.float64, device=dev)
-    flags = torch.zeros(1, dtype=torch.int32, device=dev)
-    src_sharded = args.shard == "sources" and world > 1
-    if src_sharded:
-        if wl["kind"] != "eqs":
-            raise SystemExit("--shard sources is implemented for the eqs workload")
-        # BASELINE config 5: every rank owns a slice of the sources and ALL observers; the
-        # partial fields are summed with an NCCL reduce (float64) inside the timed region
-        s_lo, s_hi = n_src * rank // world, n_src * (rank + 1) // world
-        wl["points"] = tuple(np.ascontiguousarray(p[s_lo:s_hi]) for p in wl["points"])
-        wl["coefs"] = np.ascontiguousarray(wl["coefs"][s_lo:s_hi])
-        n_src = s_hi - s_lo
-        pairs_per_step_rank = float(n_obs) * float(n_src)
-    if wl["kind"] == "eqs":
-        ws_bytes = lib.hb200_point_ws_bytes(n_obs, n_src)
-    elif wl["kind"] == "tess":
-        ws_bytes = lib.hb200_tesseroid_ws_bytes(n_obs, n_src)
-    else:
-        ws_bytes = lib.hb200_prism_ws_bytes(n_obs, n_src, nf)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    P = lambda x: ctypes.c_void_p(x.data_ptr())  # noqa: E731
-
-    if wl["kind"] == "layer":
-        d = {k: t(wl[k]) for k in ("east_c", "north_c", "bottom", "top", "density")}
-
-        def step_dev():
-            return lib.hb200_prism_layer_gravity_dev(
-                P(oe), P(on), P(ou), n_obs, P(d["east_c"]), wl["east_c"].size, P(d["north_c"]),
-                wl["north_c"].size, P(d["bottom"]), P(d["top"]), P(d["density"]), 0.0, wl["mask"],
-                P(out), P(flags), P(ws), ws_bytes, stream)  # fmt: skip
-
-        def step_host():
-            import warnings
-            with warnings.catch_warnings():
-                warnings.simplefilter("ignore")
-                return hb.prism_layer_gravity(coords, wl["east_c"], wl["north_c"], wl["bottom"],
-                                              wl["top"], wl["density"], "g_z")
-        h2d = 8 * (3 * n_obs + wl["east_c"].size + wl["north_c"].size + 3 * n_src)
-        launches_per_step = 2  # pack_layer_kernel + prism_kernel
-    elif wl["kind"] == "prism":
-        pr, rho = t(wl["prisms"]), t(wl["density"])
-
-        def step_dev():
-            return lib.hb200_prism_gravity_dev(P(oe), P(on), P(ou), n_obs, P(pr), P(rho), n_src,
-                                               wl["mask"], P(out), P(flags), P(ws), ws_bytes, stream)
-        fields = "g_z" if nf == 1 else ("g_ee", "g_nn", "g_zz", "g_en", "g_ez", "g_nz")
-
-        def step_host():
-            return hb.prism_gravity(coords, wl["prisms"], wl["density"], fields, disable_checks=True)
-        h2d = 8 * (3 * n_obs + 7 * n_src)
-        launches_per_step = 2  # pack_prisms_kernel + prism_kernel (+1 reduce when sources are chunked)
-    elif wl["kind"] == "tess":
-        ts, rho = t(wl["tesseroids"]), t(wl["density"])
-
-        def step_dev():
-            return lib.hb200_tesseroid_gravity_dev(P(oe), P(on), P(ou), n_obs, P(ts), P(rho), n_src,
-                                                   3, 0, P(out), P(flags), P(ws), ws_bytes, stream)
-
-        def step_host():
-            return hb.tesseroid_gravity(coords, wl["tesseroids"], wl["density"], "g_z",
-                                        disable_checks=True)
-        h2d = 8 * (3 * n_obs + 7 * n_src)
-        launches_per_step = 2  # pack_tesseroids_kernel + tesseroid_kernel
-    elif wl["kind"] == "mag":
-        pr = t(wl["prisms"])
-        m = [t(x) for x in wl["mag"]]
-
-        def step_dev():
-            return lib.hb200_prism_magnetic_dev(P(oe), P(on), P(ou), n_obs, P(pr), P(m[0]), P(m[1]),
-                                                P(m[2]), n_src, 7, 3, P(out), P(flags), P(ws),
-                                                ws_bytes, stream)
-
-        def step_host():
-            return hb.prism_magnetic(coords, wl["prisms"], wl["mag"], "b", disable_checks=True)
-        h2d = 8 * (3 * n_obs + 9 * n_src)
-        launches_per_step = 2
-    else:
-        pts = [t(x) for x in wl["points"]]
-        cf = t(wl["coefs"])
-
-        def step_dev():
-            rc = lib.hb200_point_gravity_dev(P(oe), P(on), P(ou), n_obs, P(pts[0]), P(pts[1]),
-                                             P(pts[2]), P(cf), n_src, 1, 0, 0, P(out), P(flags),
-                                             P(ws), ws_bytes, stream)
-            if src_sharded:  # reduce-sum of the partial fields over NVLink (NCCL)
-                dist.reduce(out, dst=0, op=dist.ReduceOp.SUM)
-            return rc
-
-        def step_host():
-            res = hb.eqs_predict(coords, wl["points"], wl["coefs"])
-            if src_sharded:
-                part = torch.from_numpy(res).to(dev)
-                dist.reduce(part, dst=0, op=dist.ReduceOp.SUM)
-                res = part.cpu().numpy()
-            return res
-        h2d = 8 * (3 * n_obs + 4 * n_src)
-        launches_per_step = 2 + (1 if n_obs < 512 * 148 * 120 else 0)  # + chunk reduce
-    d2h = 8 * nf * n_obs
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    wl = make_workload(args.workload, args.n_obs, args.n_src, 0 if sharded else rank)
+    if wl["kind"] == "tess" and sharded:
+        raise SystemExit("tess_gz: use --scaling weak (replicas) with several ranks")
+    stepper = Stepper(wl, rank, world, args.scaling, args.shard)
 
     # FP64 FMA peak of this device, measured now (MEASURED_PEAKS.json has no FP64 entry)
     flops, secs = ctypes.c_double(0), ctypes.c_double(0)
     hb._lib.check(lib.hb200_fp64_peak(args.peak_iters, ctypes.byref(flops), ctypes.byref(secs)))
     fp64_peak = flops.value
 
-    l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    for _ in range(args.warmup):
-        hb._lib.check(step_dev())
-    torch.cuda.synchronize()
+    main = measure(stepper, args.steps, args.warmup, rank, world, local, True)
+    h2d, d2h = stepper.h2d, stepper.d2h
+    del stepper
+    torch.cuda.empty_cache()
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    barrier()
-    launches_before = lib.hb200_launch_count()
-    for k in range(args.steps):
-        l2_flush.fill_(k)  # flush L2 between timed iterations (outside the events)
-        starts[k].record()
-        hb._lib.check(step_dev())
-        ends[k].record()
-    barrier()
-    gpu_launches = int(lib.hb200_launch_count() - launches_before)  # counted by the library
-    clocks = sampler.stop() if rank == 0 else None
-    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_s = float(total_ms.item()) * 1e-3
-    if int(flags.item()) & 2:
-        raise SystemExit("zero-distance pair in the synthetic workload")
+    also = []
+    if world == 1 and not args.no_also and args.workload == "layer_gz" and not args.n_obs:
+        for name in ("tensor", "mag_b", "eqs"):
+            w2 = make_workload(name)
+            st2 = Stepper(w2, 0, 1, "strong", "observers")
+            m2 = measure(st2, 3, 3, 0, 1, local, False, e2e_steps=2)
+            roof2 = roofline_for(name, m2["value"], fp64_peak, main["clocks"], True)
+            also.append({"name": name, "workload": w2["desc"], "value": m2["value"], "unit": "pair/s",
+                         "steps": 3, "warmup": 3, "ms_per_step": m2["ms_per_step"],
+                         "e2e": m2["e2e_value"], "gpu_launches": m2["gpu_launches"],
+                         "roofline_frac": roof2.get("frac"),
+                         "fp64_instr_per_pair": (roof2.get("executed") or {}).get("fp64_instr_per_pair"),
+                         "algorithmic_speedup_over_peak": roof2["algorithmic"]["speedup_over_peak"]})
+            del st2, w2
+            torch.cuda.empty_cache()
 
-    # end to end through the public API: host numpy buffers in, host result out
-    for _ in range(min(args.warmup, 2)):
-        step_host()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_host()
-    barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_s = float(e2e_s.item())
+    north_star = None
+    if not args.no_north_star and args.workload == "layer_gz" and not args.n_obs:
+        # BASELINE configs[2]: six tensor components, 1M prisms x 1M observers, observers sharded
+        # over the ranks, result gathered on rank 0; end to end on host buffers, 1 step
+        w3 = make_workload("tensor_1m")
+        st3 = Stepper(w3, rank, world, "strong", "observers")
+        m3 = measure(st3, 1, 1, rank, world, local, False, e2e_steps=1)
+        north_star = {"workload": w3["desc"], "scaling": "strong", "n_gpus": world, "steps": 1,
+                      "warmup": 1, "value": m3["value"], "unit": "pair/s",
+                      "ms_per_step": m3["ms_per_step"], "e2e": m3["e2e_value"],
+                      "e2e_ms_per_step": m3["e2e_ms_per_step"],
+                      "sharding": "single GPU" if world == 1 else
+                      f"observers over {world} ranks, gather to rank 0 (NCCL) inside the timed region"}
+        del st3, w3
+        torch.cuda.empty_cache()
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        sys.path.insert(0, os.path.join(ROOT, "oracle"))
-        import oracle as O
-
-        O.build()
-        nthreads = O.max_threads()
-        n_sample = size_cpu_sample(wl, args.cpu_seconds, nthreads)
-        rate, dt = cpu_rate(wl, n_sample, nthreads)
-        cpu_baseline = {
-            "value": rate, "unit": "pair/s", "cores": nthreads, "kind": "port",
-            "sample": f"first {n_sample} of {wl['coords'][0].size} observers x all {n_src} sources "
-                      f"({dt:.1f} s); oracle/*_port.c (C restatement of the reference's loop), OpenMP "
-                      "over observers like the reference's numba prange",
-        }  # fmt: skip
+        nthreads = host_cores()
+        for kind in cpu_kinds(wl):
+            n_sample = size_cpu_sample(wl, args.cpu_seconds, nthreads, kind)
+            rate, dt = cpu_rate(wl, n_sample, nthreads, kind)
+            entry = {"value": rate, "unit": "pair/s", "cores": nthreads, "kind": kind,
+                     "sample": f"first {n_sample} of {wl['coords'][0].size} observers x all "
+                               f"{wl['n_src']} sources ({dt:.1f} s); {CPU_DESCRIPTION[kind]}"}
+            if cpu_baseline is None:
+                cpu_baseline = entry
+            else:
+                cpu_baseline["also"] = entry
 
     if rank == 0:
-        pairs_total = pairs_per_step_rank * world * args.steps
-        value = pairs_total / total_s
+        value = main["value"]
         per_gpu = value / world
-        f_pair = 2.0 * I_PAIR[args.workload]
-        achieved = per_gpu * f_pair / 1e12
-        executed = None
-        if args.workload in EXECUTED_PER_PAIR and clocks and clocks.get("sm_mhz"):
-            f64, other = EXECUTED_PER_PAIR[args.workload]
-            slots = 148 * 4 * clocks["sm_mhz"] * 1e6 * 32  # thread-level issue slots / s
-            executed = {
-                "fp64_instr_per_pair": f64, "other_instr_per_pair": other,
-                "source": "ncu source-page counts of this kernel build, profiles/r1_opmix_*",
-                "fp64_pipe_frac": per_gpu * f64 * 2 / fp64_peak,
-                "issue_bound_frac": per_gpu * (2 * f64 + other) / slots,
-                "note": "an FP64 warp instruction occupies 2 issue slots on this part: time ~ "
-                        "(2*FP64 + other) / issue rate (DESIGN.md section 4); the slot rate uses "
-                        "nvidia-smi's SM clock, ncu's cycle counter runs ~1.3 % faster (1.99 GHz), "
-                        "so ~1.0 means: at the issue bound",
-            }
+        full_size = not args.n_obs and not args.n_src
         line = {
-            "metric": "prism-observer pair evals/sec", "value": value, "unit": "pair/s",
+            "metric": METRIC, "value": value, "unit": "pair/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True,
-            "scaling": "strong" if src_sharded else args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl["desc"], "name": args.workload, "pairs_per_step_per_gpu":
-                       pairs_per_step_rank, "l2": "flushed between timed iterations (256 MiB write)",
-                       "kernel_variant": int(lib.hb200_get_variant()),
-                       "sharding": "sources + NCCL reduce-sum" if src_sharded else
-                       ("observers, no collective" if world > 1 else "single GPU")},
-            "e2e": {"value": pairs_total / e2e_s, "unit": "pair/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps,
-                    "api": "harmonica_b200 public API on numpy buffers (ctypes -> C ABI), blocking"},
-            "gpu_launches": gpu_launches,
-            "clocks": clocks,
-            "roofline": {
-                "bound": "fp64", "achieved": achieved, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
-                "frac": achieved * 1e12 / fp64_peak,
-                "frac_of_nominal": achieved * 1e12 / NOMINAL_FP64_FLOPS,
-                "peak_source": "measured on this device in this run: hb200_fp64_peak DFMA probe "
-                               "(MEASURED_PEAKS.json carries no FP64 entry; nominal 37.2 TFLOP/s)",
-                "flops_per_pair": f_pair,
-                "note": "algorithmic flops = 2 x I_pair of the REFERENCE algorithm (SURVEY 8d); "
-                        "the merged-transcendental kernel executes fewer instructions per pair, "
-                        "pipe utilisation is in profiles/",
-                "traffic": DRAM_TRAFFIC_PER_LAUNCH.get(args.workload) if not args.n_obs else None,
-                "executed": executed,
-            },
+            "ms_per_step": main["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong" if sharded else args.scaling, "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": config_for(wl, args.workload, args, world),
+            "run": {"kernel_variant": int(lib.hb200_get_variant()),
+                    "tesseroid_variant": int(lib.hb200_get_tesseroid_variant()),
+                    "step_ms_min_max": main["step_ms_min_max"],
+                    "collective": ("none" if not sharded else
+                                   "torch.distributed NCCL gather of the observer slices" if
+                                   args.shard != "sources" else "torch.distributed NCCL reduce(sum, f64)"),
+                    "in_library_multi_gpu": "hb200_init(devices): one process, peer copies + fixed-order "
+                                            "reduce kernel instead of NCCL (SURVEY 8e alternative)"},
+            "e2e": {"value": main["e2e_value"], "unit": "pair/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": main["e2e_ms_per_step"],
+                    "api": ("harmonica_b200 public API on numpy buffers (ctypes -> C ABI), blocking"
+                            if not sharded else
+                            "harmonica_b200.distributed.ShardedJob.run() on numpy buffers: H2D of the "
+                            "rank's shard, kernels, NCCL collective, D2H on rank 0")},
+            "gpu_launches": main["gpu_launches"],
+            "clocks": main["clocks"],
+            "roofline": roofline_for(args.workload, per_gpu, fp64_peak, main["clocks"], full_size),
             "cpu_baseline": cpu_baseline,
+            "also": also,
+            "north_star": north_star,
         }  # fmt: skip
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -505,16 +677,18 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="layer_gz", choices=sorted(I_PAIR))
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"])
     ap.add_argument("--shard", default="observers", choices=["observers", "sources"])
     ap.add_argument("--n-obs", type=int, default=0)
     ap.add_argument("--n-src", type=int, default=0)
-    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--peak-iters", type=int, default=20000)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-also", action="store_true")
+    ap.add_argument("--no-north-star", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
-        args.cpu_seconds = min(args.cpu_seconds, 8.0)
+        args.cpu_seconds = min(args.cpu_seconds, 6.0)
         run_reference(args)
     else:
         run_b200(args)

@@ -899,7 +899,8 @@ int hb200_init(const int* devices, int n_devices)
     // peer access towards device 0 (source-sharded reduce)
     for (size_t a = 1; a < g_devs.size(); a++) {
         int can = 0;
-        cudaDeviceCanAccessPeer(&can, g_devs[0].id, g_devs[a].id);
+        if (g_devs[a].id == g_devs[0].id) continue;  // several shards on one device (tests)
+        if (cudaDeviceCanAccessPeer(&can, g_devs[0].id, g_devs[a].id) != cudaSuccess) cudaGetLastError();
         if (can) {
             cudaSetDevice(g_devs[0].id);
             if (cudaDeviceEnablePeerAccess(g_devs[a].id, 0) != cudaSuccess) cudaGetLastError();

@@ -40,7 +40,15 @@ def _worker(rank, world, port, queue):
         lambda lo, hi: O.eqs_predict(coords, tuple(p[lo:hi] for p in pts), density[lo:hi]),
         n_sources=301, n_obs=203)
     lo, hi = hbd.shard_bounds(203, rank, world)
-    queue.put((rank, full, part, (lo, hi)))
+    # the collectives ShardedJob uses on the device tensors: gather to dst only / reduce to dst only
+    import torch
+
+    local = torch.from_numpy(np.arange(3 * (hi - lo), dtype=np.float64).reshape(3, hi - lo) + 1000 * rank)
+    to0 = hbd.gather_observer_slices(local, 203, dst=0)
+    to1 = hbd.reduce_source_partials(torch.full((2, 5), float(rank + 1), dtype=torch.float64), dst=1)
+    even = hbd.gather_observer_slices(torch.full((1, 4), float(rank), dtype=torch.float64), 8, dst=None)
+    extra = (None if to0 is None else to0.numpy(), None if to1 is None else to1.numpy(), even.numpy())
+    queue.put((rank, full, part, (lo, hi), extra))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -65,9 +73,31 @@ def test_observer_and_source_sharding_world2():
     want_eqs = O.eqs_predict(coords, pts, density)
     bounds = sorted(r[3] for r in results)
     assert bounds == [(0, 101), (101, 203)]
-    for _, full, part, _ in results:
+    for rank, full, part, _, extra in results:
         np.testing.assert_array_equal(full, want)          # disjoint slices: bit-exact
         assert max_rel(part[0], want_eqs) <= TOL            # re-associated sum
+        to0, to1, even = extra
+        if rank == 0:  # ragged gather on dst: rank 0 owns 101 columns, rank 1 owns 102
+            assert to1 is None and to0.shape == (3, 203)
+            np.testing.assert_array_equal(to0[:, :101], np.arange(303.0).reshape(3, 101))
+            np.testing.assert_array_equal(to0[:, 101:], np.arange(306.0).reshape(3, 102) + 1000)
+        else:
+            assert to0 is None
+            np.testing.assert_array_equal(to1, np.full((2, 5), 3.0))
+        np.testing.assert_array_equal(even, [[0, 0, 0, 0, 1, 1, 1, 1]])
+
+
+def test_sharded_job_needs_the_gpu_library():
+    """No CPU fallback: a ShardedJob cannot be built without a CUDA device."""
+    import torch
+
+    from harmonica_b200 import distributed as hbd
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    coords, prisms, density = config1(10, 10, seed=1)
+    with pytest.raises(Exception):
+        hbd.ShardedJob("prism_gravity", coords, dict(prisms=prisms, density=density), "g_z").upload()
 
 
 def test_shard_bounds_cover_everything():

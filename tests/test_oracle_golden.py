@@ -89,3 +89,25 @@ def test_eqs_predict_spherical():
     got = O.eqs_predict_spherical(tuple(g["obs"]), tuple(g["points"]), g["coefs"])
     # numpy's SIMD cos/sin inside numba may differ from glibc's scalar ones in the last ulp
     npt.assert_allclose(got, g["predicted"], rtol=1e-11)
+
+
+def test_numba_loops_match_the_port_bit_for_bit():
+    """oracle/numba_loops.py (bench.py's Numba CPU arm) == oracle/choclo_port.c, which the tests
+    above pin bit-for-bit on the reference's unmodified loops (golden fixtures)."""
+    pytest.importorskip("numba")
+    import numba_loops as NL
+    from _common import config1, layer_config2
+
+    coords, prisms, density = config1(300, 64, seed=17)
+    for field, scale in (("g_z", -1e5), ("potential", 1.0), ("g_ee", 1e9), ("g_ez", -1e9)):
+        got = NL.prism_gravity(coords, prisms, density, field) * scale
+        np.testing.assert_array_equal(got, O.prism_gravity(coords, prisms, density, field))
+    lc, ec, nc, bottom, top, rho = layer_config2(n=24)
+    sub = tuple(c[:40] for c in lc)
+    got = NL.prism_layer_gravity(sub, ec, nc, bottom, top, rho, "g_z") * -1e5
+    np.testing.assert_array_equal(got, O.prism_layer_gravity(sub, ec, nc, bottom, top, rho, "g_z"))
+    mag = tuple(np.random.default_rng(3).normal(size=300) for _ in range(3))
+    got = np.array(NL.prism_magnetic_field(coords, prisms, mag)) * 1e9
+    np.testing.assert_array_equal(got, np.array(O.prism_magnetic(coords, prisms, mag, "b")))
+    pts = (prisms[:, 0], prisms[:, 2], prisms[:, 4])
+    np.testing.assert_array_equal(NL.eqs_predict(coords, pts, density), O.eqs_predict(coords, pts, density))
