@@ -585,9 +585,15 @@ int tesseroid_dev_impl(const double* lon, const double* lat, const double* rad, 
     } else if (variant == 2) {
         if (field == F_POT) tesseroid_deferred_kernel<F_POT, true><<<grid, kTessBlock, 0, st>>>(a);
         else tesseroid_deferred_kernel<F_U, true><<<grid, kTessBlock, 0, st>>>(a);
-    } else {
+    } else if (variant == 3) {
         if (field == F_POT) tesseroid_deferred_kernel<F_POT, true, OwnTrig><<<grid, kTessBlock, 0, st>>>(a);
         else tesseroid_deferred_kernel<F_U, true, OwnTrig><<<grid, kTessBlock, 0, st>>>(a);
+    } else if (variant == 4) {  // experiment: 80 registers, 24 resident warps
+        if (field == F_POT) tesseroid_deferred_kernel<F_POT, true, OwnTrig, 12><<<grid, kTessBlock, 0, st>>>(a);
+        else tesseroid_deferred_kernel<F_U, true, OwnTrig, 12><<<grid, kTessBlock, 0, st>>>(a);
+    } else {  // experiment: 64 registers, 32 resident warps
+        if (field == F_POT) tesseroid_deferred_kernel<F_POT, true, OwnTrig, 16><<<grid, kTessBlock, 0, st>>>(a);
+        else tesseroid_deferred_kernel<F_U, true, OwnTrig, 16><<<grid, kTessBlock, 0, st>>>(a);
     }
     CU(cudaGetLastError());
     g_launches += chunks > 1 ? 3 : 2;
@@ -847,7 +853,7 @@ int hb200_set_variant(int variant)
 int hb200_get_variant(void) { return g_variant; }
 int hb200_set_tesseroid_variant(int variant)
 {
-    if (variant < 0 || variant > 3) return fail(HB200_EINVAL, "tesseroid variant must be 0 .. 3");
+    if (variant < 0 || variant > 5) return fail(HB200_EINVAL, "tesseroid variant must be 0 .. 5");
     g_tess_variant = variant;
     return HB200_OK;
 }

@@ -31,56 +31,60 @@ namespace hb {
 // XM = false: CUDA libm; XM = true: the sequences of hb200_xmath.cuh
 template <bool XM> HB_HD double x_sqrt(double x) { return XM ? fast_sqrt_1ulp(x) : sqrt(x); }
 
-// true when the predicate holds for every lane that is executing this code together: used to
-// pick a shorter far-field sequence without any divergence (the general sequence is valid
-// everywhere, so the choice never changes which formula applies, only its cost)
-HB_HD bool warp_all(bool p)
+// Far-field shortcuts (log1p / small-angle atan without the table reductions) are chosen PER
+// LANE from the lane's own arguments: the value of an (observer, prism) pair never depends on
+// which other observers share its warp, so results are bit-reproducible under any batching,
+// chunking or sharding of the observers. (A warp whose lanes all agree issues one side only.)
+
+// |z| class of a merged log ratio top / bot = 1 + z, from the exponent of z (integer pipe)
+constexpr int kLogTiny = 0x3f400000;   // |z| < 2^-11: degree-5 log1p
+constexpr int kLogSmall = 0x3f700000;  // |z| < 2^-8: degree-7 log1p
+constexpr int kLogMid = 0x3fa00000;    // |z| < 2^-5: degree-11 log1p
+
+HB_HD double log1p_class(double z, double ratio, int m)
 {
-#if defined(__CUDA_ARCH__)
-    return __all_sync(__activemask(), p);
-#else
-    return p;
-#endif
+    if (m < kLogSmall) return log1p_small(z);
+    if (m < kLogMid) return log1p_mid(z);
+    return fast_log(ratio);
 }
 
-// log(top / bot): far from the prism the merged ratio is 1 + z with |z| < 2^-8 and the table
-// reduction of fast_log is not needed (degree-7 log1p directly)
+// log(top / bot)
 template <bool XM> HB_HD double x_log_ratio(double top, double bot)
 {
     if (!XM) return log(top / bot);
     const double y = fast_rcp(bot);
     const double z = fma(top, y, -1.0);
-    if (warp_all((hi_word(z) & 0x7fffffff) < 0x3f700000)) return log1p_small(z);
-    return fast_log(top * y);
+    const int m = hi_word(z) & 0x7fffffff;
+    if (m < kLogTiny) return log1p_tiny(z);
+    return log1p_class(z, top * y, m);
 }
 
 // atan2(y, x): far from the prism x > 0 and |y| < x / 32, no quadrant or table reduction
 template <bool XM> HB_HD double x_atan2(double y, double x)
 {
     if (!XM) return atan2(y, x);
-    if (warp_all(small_angle(y, x))) return atan_small(y, x);
+    if (tiny_angle(y, x)) return atan_tiny(y, x);
+    if (small_angle(y, x)) return atan_small(y, x);
     return fast_atan2(y, x);
 }
 
-HB_HD bool is_neg(double x)
+// sign bit of x as a mask for the upper word of a double
+HB_HD unsigned sign_mask(double x) { return (unsigned)hi_word(x) & 0x80000000u; }
+HB_HD bool is_neg(double x) { return hi_word(x) < 0; }
+HB_HD double flip_by(double x, unsigned mask)
 {
-#if defined(__CUDA_ARCH__)
-    return __double2hiint(x) < 0;
-#else
-    return signbit(x);
-#endif
+    return make_double((int)((unsigned)hi_word(x) ^ mask), lo_word(x));
 }
 
 struct FastCtx {
     double se[2], sn[2], su[2];
     double se2[2], sn2[2], su2[2];
-    double en2[2][2], eu2[2][2], nu2[2][2];
+    double en2[2][2];
     double r[2][2][2];
 };
 
 template <int FS, bool XM> HB_HD void make_fast_ctx(FastCtx& c, const PairGeom& g)
 {
-    typedef Traits<FS> T;
 #pragma unroll
     for (int i = 0; i < 2; i++) {
         c.se[i] = g.se[i]; c.sn[i] = g.sn[i]; c.su[i] = g.su[i];
@@ -89,11 +93,7 @@ template <int FS, bool XM> HB_HD void make_fast_ctx(FastCtx& c, const PairGeom& 
 #pragma unroll
     for (int a = 0; a < 2; a++)
 #pragma unroll
-        for (int b = 0; b < 2; b++) {
-            c.en2[a][b] = add_rn(g.se2[a], g.sn2[b]);
-            if (T::ln) c.eu2[a][b] = add_rn(g.se2[a], g.su2[b]);
-            if (T::le) c.nu2[a][b] = add_rn(g.sn2[a], g.su2[b]);
-        }
+        for (int b = 0; b < 2; b++) c.en2[a][b] = add_rn(g.se2[a], g.sn2[b]);
 #pragma unroll
     for (int i = 0; i < 2; i++)
 #pragma unroll
@@ -102,18 +102,33 @@ template <int FS, bool XM> HB_HD void make_fast_ctx(FastCtx& c, const PairGeom& 
             for (int k = 0; k < 2; k++) c.r[i][j][k] = x_sqrt<XM>(add_rn(c.en2[i][j], g.su2[k]));
 }
 
-// T = r + |x| and Y = y^2 + z^2 of safe_log type X (0: x = e, 1: x = n, 2: x = u) at vertex
-// ijk. safe_log(x, y, z, r) = log(T) for x >= 0 and log(Y / T) for x < 0; the on-axis and r == 0
-// branches cannot occur on this path (needs_exact_path() sends such pairs to the direct path).
+// safe_log type X (0: x = e, 1: x = n, 2: x = u) at vertex ijk:
+//   safe_log(x, y, z, r) = log(T) for x >= 0 and log(Y / T) for x < 0, T = r + |x|, Y = y^2 + z^2
+// (the on-axis and r == 0 branches cannot occur on this path: classify_pair() sends such pairs
+// to the direct path). Y does not depend on the X index, so in every alternating sum in which
+// both X indices carry the SAME sign of x the Y factors cancel identically and
+//   sum over a sign-symmetric vertex set of s L  =  sigma * log(prod T^s),  sigma = -1 for x < 0:
+// no selects and no Y at all (SAME = true below). Only when the observer lies strictly inside the
+// prism's extent on an axis (x_0 and x_1 of opposite sign: rare; ONE test per pair decides for
+// all of its logs) do the Y factors stay: the general arrangement with selects (SAME = false),
+//   x >= 0: (num, den) = (T, 1);   x < 0: (num, den) = (Y, T).
 template <int X> HB_HD double log_x(const FastCtx& c, int xi)
 {
     return (X == 0) ? c.se[xi] : (X == 1) ? c.sn[xi] : c.su[xi];
 }
-template <int X> HB_HD void log_TY(const FastCtx& c, int i, int j, int k, double& T, double& Y)
+template <int X> HB_HD double log_T(const FastCtx& c, int i, int j, int k)
 {
     const double x = (X == 0) ? c.se[i] : (X == 1) ? c.sn[j] : c.su[k];
-    Y = (X == 0) ? c.nu2[j][k] : (X == 1) ? c.eu2[i][k] : c.en2[i][j];
-    T = c.r[i][j][k] + fabs(x);
+    return c.r[i][j][k] + fabs(x);
+}
+template <int X> HB_HD double log_Y(const FastCtx& c, int i, int j, int k)
+{
+    return (X == 0) ? add_rn(c.sn2[j], c.su2[k]) : (X == 1) ? add_rn(c.se2[i], c.su2[k]) : c.en2[i][j];
+}
+// true when x_0 and x_1 of axis X have different sign bits
+template <int X> HB_HD bool log_mixed(const FastCtx& c)
+{
+    return (hi_word(log_x<X>(c, 0)) ^ hi_word(log_x<X>(c, 1))) < 0;
 }
 
 // map (fixed axis F with index f, the other two indices a, b in axis order) -> ijk
@@ -124,96 +139,208 @@ template <int F> HB_HD void ijk_of(int f, int a, int b, int& i, int& j, int& k)
     else { i = a; j = b; k = f; }
 }
 
-// top/bot products of the 4 vertices with index f fixed on axis F (F != X), signs (-1)^(a+b).
-// The sign of x depends only on the X index xi, so the safe_log branch is selected once per
-// xi on products of two vertices (o = the remaining index):
-//   x >= 0: (T[xi][0], T[xi][1]);   x < 0: (Y[xi][0] T[xi][1], T[xi][0] Y[xi][1])
-template <int X, int F>
-HB_HD void log_group4_tb(const FastCtx& c, int f, double& top, double& bot)
+// The 4 vertices with index f fixed on axis F (F != X), signs (-1)^(a+b):
+//   sum = +- log(top / bot), the sign flipped where the bit of `flip` is set
+// [xi][o] = [X index][remaining index]
+template <int X, int F, bool SAME>
+HB_HD void log_group4_tb(const FastCtx& c, int f, double& top, double& bot, unsigned& flip)
 {
     constexpr bool x_first = (X == (F == 0 ? 1 : 0));
-    double P[2], Q[2];
+    double T[2][2];
 #pragma unroll
-    for (int xi = 0; xi < 2; xi++) {
-        double T[2], Y[2];
+    for (int xi = 0; xi < 2; xi++)
 #pragma unroll
         for (int o = 0; o < 2; o++) {
             int i, j, k;
             ijk_of<F>(f, x_first ? xi : o, x_first ? o : xi, i, j, k);
-            log_TY<X>(c, i, j, k, T[o], Y[o]);
+            T[xi][o] = log_T<X>(c, i, j, k);
         }
-        const bool neg = is_neg(log_x<X>(c, xi));
-        P[xi] = neg ? Y[0] * T[1] : T[0];
-        Q[xi] = neg ? T[0] * Y[1] : T[1];
+    if (SAME) {
+        top = T[0][0] * T[1][1];
+        bot = T[0][1] * T[1][0];
+        flip = sign_mask(log_x<X>(c, 0));
+    } else {
+        double P[2], Q[2];
+#pragma unroll
+        for (int xi = 0; xi < 2; xi++) {
+            double Y[2];
+#pragma unroll
+            for (int o = 0; o < 2; o++) {
+                int i, j, k;
+                ijk_of<F>(f, x_first ? xi : o, x_first ? o : xi, i, j, k);
+                Y[o] = log_Y<X>(c, i, j, k);
+            }
+            const bool neg = is_neg(log_x<X>(c, xi));
+            P[xi] = neg ? Y[0] * T[xi][1] : T[xi][0];
+            Q[xi] = neg ? T[xi][0] * Y[1] : T[xi][1];
+        }
+        top = P[0] * Q[1];
+        bot = Q[0] * P[1];
+        flip = 0u;
     }
-    top = P[0] * Q[1];
-    bot = Q[0] * P[1];
 }
 
-// sum_{a,b} (-1)^(a+b) L^X over the 4 vertices with index f on axis F
-template <int X, int F, bool XM> HB_HD double log_group4(const FastCtx& c, int f)
+// sum over all 8 vertices of s_ijk L^X = +- log(top / bot): per X index xi the four vertices
+// split by parity of the other two indices into side A (00, 11) and side B (01, 10)
+template <int X, bool SAME>
+HB_HD void log_sum8_tb(const FastCtx& c, double& top, double& bot, unsigned& flip)
 {
-    double top, bot;
-    log_group4_tb<X, F>(c, f, top, bot);
-    return x_log_ratio<XM>(top, bot);
-}
-
-// sum over all 8 vertices of s_ijk L^X: per X index xi the four vertices split by parity of
-// the other two indices into side A (00, 11) and side B (01, 10)
-template <int X> HB_HD void log_sum8_tb(const FastCtx& c, double& top, double& bot)
-{
-    double P[2], Q[2];
+    double TA[2], TB[2], YA = 1.0, YB = 1.0;
 #pragma unroll
     for (int xi = 0; xi < 2; xi++) {
-        double T[2][2], Y[2][2];
+        double T[2][2];
 #pragma unroll
         for (int a = 0; a < 2; a++)
 #pragma unroll
             for (int b = 0; b < 2; b++) {
                 int i, j, k;
                 ijk_of<X>(xi, a, b, i, j, k);
-                log_TY<X>(c, i, j, k, T[a][b], Y[a][b]);
+                T[a][b] = log_T<X>(c, i, j, k);
             }
-        const double TA = T[0][0] * T[1][1], TB = T[0][1] * T[1][0];
-        const double YA = Y[0][0] * Y[1][1], YB = Y[0][1] * Y[1][0];
-        const bool neg = is_neg(log_x<X>(c, xi));
-        P[xi] = neg ? YA * TB : TA;
-        Q[xi] = neg ? TA * YB : TB;
+        TA[xi] = T[0][0] * T[1][1];
+        TB[xi] = T[0][1] * T[1][0];
     }
-    top = P[0] * Q[1];
-    bot = Q[0] * P[1];
+    if (SAME) {
+        top = TA[0] * TB[1];
+        bot = TB[0] * TA[1];
+        flip = sign_mask(log_x<X>(c, 0));
+    } else {
+        double Y[2][2];
+#pragma unroll
+        for (int a = 0; a < 2; a++)
+#pragma unroll
+            for (int b = 0; b < 2; b++) {
+                int i, j, k;
+                ijk_of<X>(0, a, b, i, j, k);
+                Y[a][b] = log_Y<X>(c, i, j, k);  // independent of the X index
+            }
+        YA = Y[0][0] * Y[1][1];
+        YB = Y[0][1] * Y[1][0];
+        double P[2], Q[2];
+#pragma unroll
+        for (int xi = 0; xi < 2; xi++) {
+            const bool neg = is_neg(log_x<X>(c, xi));
+            P[xi] = neg ? YA * TB[xi] : TA[xi];
+            Q[xi] = neg ? TA[xi] * YB : TB[xi];
+        }
+        top = P[0] * Q[1];
+        bot = Q[0] * P[1];
+        flip = 0u;
+    }
 }
+
+// L^X(x_0) - L^X(x_1) along X's own axis; (a, b) = the other two indices in axis order:
+// same signs: -+ log(T0 / T1); general: (num, den) per vertex as above (Y is shared)
+template <int X, bool SAME>
+HB_HD void log_pair_tb(const FastCtx& c, int a, int b, double& top, double& bot, unsigned& flip)
+{
+    int i0, j0, k0, i1, j1, k1;
+    ijk_of<X>(0, a, b, i0, j0, k0);
+    ijk_of<X>(1, a, b, i1, j1, k1);
+    const double T0 = log_T<X>(c, i0, j0, k0), T1 = log_T<X>(c, i1, j1, k1);
+    if (SAME) {
+        top = T0;
+        bot = T1;
+        flip = sign_mask(log_x<X>(c, 0));
+    } else {
+        const double Y = log_Y<X>(c, i0, j0, k0);
+        const bool neg0 = is_neg(log_x<X>(c, 0)), neg1 = is_neg(log_x<X>(c, 1));
+        const double n0 = neg0 ? Y : T0, d0 = neg0 ? T0 : 1.0;
+        const double n1 = neg1 ? Y : T1, d1 = neg1 ? T1 : 1.0;
+        top = n0 * d1;
+        bot = n1 * d0;
+        flip = 0u;
+    }
+}
+
+HB_HD bool any_mixed(const FastCtx& c) { return log_mixed<0>(c) | log_mixed<1>(c) | log_mixed<2>(c); }
+
+// NQ merged log ratios with ONE class decision per lane: out[q] = +-log(top[q] / bot[q])
+template <bool XM, int NQ>
+HB_HD void x_log_ratio4(const double (&top)[NQ], const double (&bot)[NQ], const unsigned (&flip)[NQ],
+                        double (&out)[NQ])
+{
+    if (!XM) {
+#pragma unroll
+        for (int q = 0; q < NQ; q++) out[q] = flip_by(log(top[q] / bot[q]), flip[q]);
+        return;
+    }
+    double y[NQ], z[NQ];
+    int worst = 0;
+#pragma unroll
+    for (int q = 0; q < NQ; q++) {
+        y[q] = fast_rcp(bot[q]);
+        z[q] = fma(top[q], y[q], -1.0);
+        const int m = hi_word(z[q]) & 0x7fffffff;
+        worst = m > worst ? m : worst;
+    }
+    if (worst < kLogTiny) {  // every |z| < 2^-11: the far field, almost all pairs
+#pragma unroll
+        for (int q = 0; q < NQ; q++) out[q] = flip_by(log1p_tiny(z[q]), flip[q]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < NQ; q++) out[q] = flip_by(log1p_class(z[q], top[q] * y[q], worst), flip[q]);
+    }
+}
+
+// sufficient for re > |im| (both finite), i.e. for the angle of (re, im) to lie inside
+// (-pi/4, pi/4): compared on the upper words only (integer pipe, one instruction). Pairs that
+// fail the test take the general sequence, which is valid everywhere.
+HB_HD bool angle_below_quarter_pi(double im, double re)
+{
+    return hi_word(re) > (hi_word(im) & 0x7fffffff);
+}
+
 template <int X, bool XM> HB_HD double log_sum8(const FastCtx& c)
 {
     double top, bot;
-    log_sum8_tb<X>(c, top, bot);
-    return x_log_ratio<XM>(top, bot);
+    unsigned flip;
+    if (!log_mixed<X>(c)) log_sum8_tb<X, true>(c, top, bot, flip);
+    else log_sum8_tb<X, false>(c, top, bot, flip);
+    return flip_by(x_log_ratio<XM>(top, bot), flip);
 }
 
-// L^X(x_0) - L^X(x_1) along X's own axis; (a, b) = the other two indices in axis order.
-// Y does not depend on the X index.
-template <int X, bool XM> HB_HD double log_pair(const FastCtx& c, int a, int b)
+// the 12 four-vertex log groups of the three acceleration components, slots as used by
+// prism_pair_fast (FS_ACC3)
+template <bool SAME>
+HB_HD void acc3_logs_t(const FastCtx& c, double (&top)[12], double (&bot)[12], unsigned (&flip)[12])
 {
-    int i, j, k;
-    double T0, T1, Y;
-    ijk_of<X>(0, a, b, i, j, k);
-    log_TY<X>(c, i, j, k, T0, Y);
-    ijk_of<X>(1, a, b, i, j, k);
-    log_TY<X>(c, i, j, k, T1, Y);
-    const bool neg0 = is_neg(log_x<X>(c, 0)), neg1 = is_neg(log_x<X>(c, 1));
-    const double n0 = neg0 ? Y : T0, d0 = neg0 ? T0 : 1.0;
-    const double n1 = neg1 ? Y : T1, d1 = neg1 ? T1 : 1.0;
-    return x_log_ratio<XM>(n0 * d1, n1 * d0);
+#pragma unroll
+    for (int f = 0; f < 2; f++) {
+        log_group4_tb<2, 1, SAME>(c, f, top[0 + f], bot[0 + f], flip[0 + f]);     // E: n * L^u over (i, k)
+        log_group4_tb<1, 2, SAME>(c, f, top[2 + f], bot[2 + f], flip[2 + f]);     // E: u * L^n over (i, j)
+        log_group4_tb<0, 2, SAME>(c, f, top[4 + f], bot[4 + f], flip[4 + f]);     // N: u * L^e over (i, j)
+        log_group4_tb<2, 0, SAME>(c, f, top[6 + f], bot[6 + f], flip[6 + f]);     // N: e * L^u over (j, k)
+        log_group4_tb<1, 0, SAME>(c, f, top[8 + f], bot[8 + f], flip[8 + f]);     // U: e * L^n over (j, k)
+        log_group4_tb<0, 1, SAME>(c, f, top[10 + f], bot[10 + f], flip[10 + f]);  // U: n * L^e over (i, k)
+    }
+}
+template <bool XM>
+HB_HD void acc3_logs(const FastCtx& c, double (&top)[12], double (&bot)[12], unsigned (&flip)[12])
+{
+    if (!any_mixed(c)) acc3_logs_t<true>(c, top, bot, flip);
+    else acc3_logs_t<false>(c, top, bot, flip);
 }
 
-// re > |im| (both finite), i.e. the angle of (re, im) lies inside (-pi/4, pi/4); integer pipe
-HB_HD bool angle_below_quarter_pi(double im, double re)
+// the 12 vertex-pair logs of the potential: [0..3] L^u over [i][j], [4..7] L^e over [j][k],
+// [8..11] L^n over [i][k]
+template <bool SAME>
+HB_HD void pot_logs_t(const FastCtx& c, double (&top)[12], double (&bot)[12], unsigned (&flip)[12])
 {
-#if defined(__CUDA_ARCH__)
-    return __double_as_longlong(re) > (__double_as_longlong(im) & 0x7fffffffffffffffLL);
-#else
-    return re > fabs(im);
-#endif
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+            const int q = 2 * a + b;
+            log_pair_tb<2, SAME>(c, a, b, top[q], bot[q], flip[q]);
+            log_pair_tb<0, SAME>(c, a, b, top[4 + q], bot[4 + q], flip[4 + q]);
+            log_pair_tb<1, SAME>(c, a, b, top[8 + q], bot[8 + q], flip[8 + q]);
+        }
+}
+HB_HD void pot_logs(const FastCtx& c, double (&top)[12], double (&bot)[12], unsigned (&flip)[12])
+{
+    if (!any_mixed(c)) pot_logs_t<true>(c, top, bot, flip);
+    else pot_logs_t<false>(c, top, bot, flip);
 }
 
 // (im, re) with atan2(im, re) = A^X(b_0) - A^X(b_1) at fixed index f on axis X and index m on the
@@ -270,35 +397,8 @@ template <int X, bool XM> HB_HD double atan_sum8(const FastCtx& c)
     return atan_sum4<X, XM>(c, 0) - atan_sum4<X, XM>(c, 1);
 }
 
-// NQ merged log ratios with ONE warp vote: log(top[q] / bot[q]).
-template <bool XM, int NQ>
-HB_HD void x_log_ratio4(const double (&top)[NQ], const double (&bot)[NQ], double (&out)[NQ])
-{
-    if (!XM) {
-#pragma unroll
-        for (int q = 0; q < NQ; q++) out[q] = log(top[q] / bot[q]);
-        return;
-    }
-    double y[NQ], z[NQ];
-    int worst = 0;
-#pragma unroll
-    for (int q = 0; q < NQ; q++) {
-        y[q] = fast_rcp(bot[q]);
-        z[q] = fma(top[q], y[q], -1.0);
-        const int m = hi_word(z[q]) & 0x7fffffff;
-        worst = m > worst ? m : worst;
-    }
-    if (warp_all(worst < 0x3f700000)) {  // every |z| < 2^-8
-#pragma unroll
-        for (int q = 0; q < NQ; q++) out[q] = log1p_small(z[q]);
-    } else {
-#pragma unroll
-        for (int q = 0; q < NQ; q++) out[q] = fast_log(top[q] * y[q]);
-    }
-}
-
 // The 8-vertex atan sums of two diagonal kernels (types XA, XB) with one branch for the merge
-// test and one warp vote for the far-field sequence.
+// test and one (per-lane) decision for the far-field sequence.
 template <int XA, int XB, bool XM> HB_HD void atan_sum8_two(const FastCtx& c, double& sa, double& sb)
 {
     if (!XM) {
@@ -326,7 +426,10 @@ template <int XA, int XB, bool XM> HB_HD void atan_sum8_two(const FastCtx& c, do
             y[t] = aim * bre + are * bim;
             x[t] = are * bre - aim * bim;
         }
-        if (warp_all(small_angle(y[0], x[0]) && small_angle(y[1], x[1]))) {
+        if (tiny_angle(y[0], x[0]) && tiny_angle(y[1], x[1])) {
+            sa = atan_tiny(y[0], x[0]);
+            sb = atan_tiny(y[1], x[1]);
+        } else if (small_angle(y[0], x[0]) && small_angle(y[1], x[1])) {
             sa = atan_small(y[0], x[0]);
             sb = atan_small(y[1], x[1]);
         } else {
@@ -340,7 +443,7 @@ template <int XA, int XB, bool XM> HB_HD void atan_sum8_two(const FastCtx& c, do
 }
 
 // S[0], S[1] of atan_sum4 (both indices of axis X) with one branch for the merge test and one
-// warp vote for the far-field sequence.
+// (per-lane) decision for the far-field sequence.
 template <int X, bool XM> HB_HD void atan_sum4_both(const FastCtx& c, double (&S)[2])
 {
     if (!XM) {
@@ -364,7 +467,10 @@ template <int X, bool XM> HB_HD void atan_sum4_both(const FastCtx& c, double (&S
             y[f] = im[f][0] * re[f][1] - re[f][0] * im[f][1];
             x[f] = re[f][0] * re[f][1] + im[f][0] * im[f][1];
         }
-        if (warp_all(small_angle(y[0], x[0]) && small_angle(y[1], x[1]))) {
+        if (tiny_angle(y[0], x[0]) && tiny_angle(y[1], x[1])) {
+            S[0] = atan_tiny(y[0], x[0]);
+            S[1] = atan_tiny(y[1], x[1]);
+        } else if (small_angle(y[0], x[0]) && small_angle(y[1], x[1])) {
             S[0] = atan_small(y[0], x[0]);
             S[1] = atan_small(y[1], x[1]);
         } else {
@@ -383,19 +489,39 @@ template <int LA, int FA, int LB, int FB, int AX, bool XM>
 HB_HD double accel_component(const FastCtx& c, const double* pa, const double* pb, const double* px)
 {
     double top[4], bot[4], L[4], S[2];
-    log_group4_tb<LA, FA>(c, 0, top[0], bot[0]);
-    log_group4_tb<LA, FA>(c, 1, top[1], bot[1]);
-    log_group4_tb<LB, FB>(c, 0, top[2], bot[2]);
-    log_group4_tb<LB, FB>(c, 1, top[3], bot[3]);
-    x_log_ratio4<XM, 4>(top, bot, L);
+    unsigned flip[4];
+    if (!(log_mixed<LA>(c) | log_mixed<LB>(c))) {
+        log_group4_tb<LA, FA, true>(c, 0, top[0], bot[0], flip[0]);
+        log_group4_tb<LA, FA, true>(c, 1, top[1], bot[1], flip[1]);
+        log_group4_tb<LB, FB, true>(c, 0, top[2], bot[2], flip[2]);
+        log_group4_tb<LB, FB, true>(c, 1, top[3], bot[3], flip[3]);
+    } else {  // observer inside the prism's extent on one of the two axes
+        log_group4_tb<LA, FA, false>(c, 0, top[0], bot[0], flip[0]);
+        log_group4_tb<LA, FA, false>(c, 1, top[1], bot[1], flip[1]);
+        log_group4_tb<LB, FB, false>(c, 0, top[2], bot[2], flip[2]);
+        log_group4_tb<LB, FB, false>(c, 1, top[3], bot[3], flip[3]);
+    }
+    x_log_ratio4<XM, 4>(top, bot, flip, L);
     atan_sum4_both<AX, XM>(c, S);
     return pa[0] * L[0] - pa[1] * L[1] + pb[0] * L[2] - pb[1] * L[3] - (px[0] * S[0] - px[1] * S[1]);
 }
 
+// +0.0 for x == -0.0 (a shift bound - observer is -0 when the bound is -0 and the coordinate +0):
+// the sign-bit tests of the merged path must see a zero shift as non-negative
+HB_HD double plus_zero(double x) { return x == 0.0 ? 0.0 : x; }
+
 template <int FS, bool XM>
-HB_HD void prism_pair_fast(const PairGeom& g, const double* prm, double* acc)
+HB_HD void prism_pair_fast(const PairGeom& g0, const double* prm, double* acc, int cls = PAIR_FAST,
+                           unsigned mag_rules = 0u, unsigned* flags = nullptr)
 {
     typedef Traits<FS> T;
+    PairGeom g = g0;
+    if (cls == PAIR_FAST_CHECK) {
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            g.se[i] = plus_zero(g.se[i]); g.sn[i] = plus_zero(g.sn[i]); g.su[i] = plus_zero(g.su[i]);
+        }
+    }
     FastCtx c;
     make_fast_ctx<FS, XM>(c, g);
     const double* e = c.se;
@@ -411,16 +537,9 @@ HB_HD void prism_pair_fast(const PairGeom& g, const double* prm, double* acc)
         // the three single-component formulas on one shared context: second differences
         // (4-vertex groups), so the far-field log1p shortcut applies; one vote for all 12 logs
         double top[12], bot[12], L[12], Se[2], Sn[2], Su[2];
-#pragma unroll
-        for (int f = 0; f < 2; f++) {
-            log_group4_tb<2, 1>(c, f, top[0 + f], bot[0 + f]);    // E: n * L^u over (i, k)
-            log_group4_tb<1, 2>(c, f, top[2 + f], bot[2 + f]);    // E: u * L^n over (i, j)
-            log_group4_tb<0, 2>(c, f, top[4 + f], bot[4 + f]);    // N: u * L^e over (i, j)
-            log_group4_tb<2, 0>(c, f, top[6 + f], bot[6 + f]);    // N: e * L^u over (j, k)
-            log_group4_tb<1, 0>(c, f, top[8 + f], bot[8 + f]);    // U: e * L^n over (j, k)
-            log_group4_tb<0, 1>(c, f, top[10 + f], bot[10 + f]);  // U: n * L^e over (i, k)
-        }
-        x_log_ratio4<XM, 12>(top, bot, L);
+        unsigned flip[12];
+        acc3_logs<XM>(c, top, bot, flip);
+        x_log_ratio4<XM, 12>(top, bot, flip, L);
         atan_sum4_both<0, XM>(c, Se);
         atan_sum4_both<1, XM>(c, Sn);
         atan_sum4_both<2, XM>(c, Su);
@@ -435,14 +554,20 @@ HB_HD void prism_pair_fast(const PairGeom& g, const double* prm, double* acc)
         acc[2] += prm[0] * -vu;
     } else if (FS == F_POT || FS == FS_ACC3) {
         double Pu[2][2], Pe[2][2], Pn[2][2], SA[3][2];
+        {
+            double top[12], bot[12], L[12];
+            unsigned flip[12];
+            pot_logs(c, top, bot, flip);
+            x_log_ratio4<XM, 12>(top, bot, flip, L);
 #pragma unroll
-        for (int a = 0; a < 2; a++)
+            for (int a = 0; a < 2; a++)
 #pragma unroll
-            for (int b = 0; b < 2; b++) {
-                Pu[a][b] = log_pair<2, XM>(c, a, b);  // [i][j]
-                Pe[a][b] = log_pair<0, XM>(c, a, b);  // [j][k]
-                Pn[a][b] = log_pair<1, XM>(c, a, b);  // [i][k]
-            }
+                for (int b = 0; b < 2; b++) {
+                    Pu[a][b] = L[2 * a + b];
+                    Pe[a][b] = L[4 + 2 * a + b];
+                    Pn[a][b] = L[8 + 2 * a + b];
+                }
+        }
 #pragma unroll
         for (int f = 0; f < 2; f++) {
             SA[0][f] = atan_sum4<0, XM>(c, f);
@@ -509,10 +634,17 @@ HB_HD void prism_pair_fast(const PairGeom& g, const double* prm, double* acc)
         }
         if (XM && fused) {
             double top[3], bot[3], L[3];
-            log_sum8_tb<2>(c, top[0], bot[0]);
-            log_sum8_tb<1>(c, top[1], bot[1]);
-            log_sum8_tb<0>(c, top[2], bot[2]);
-            x_log_ratio4<XM, 3>(top, bot, L);
+            unsigned flip[3];
+            if (!any_mixed(c)) {
+                log_sum8_tb<2, true>(c, top[0], bot[0], flip[0]);
+                log_sum8_tb<1, true>(c, top[1], bot[1], flip[1]);
+                log_sum8_tb<0, true>(c, top[2], bot[2], flip[2]);
+            } else {  // observer inside the prism's extent on some axis
+                log_sum8_tb<2, false>(c, top[0], bot[0], flip[0]);
+                log_sum8_tb<1, false>(c, top[1], bot[1], flip[1]);
+                log_sum8_tb<0, false>(c, top[2], bot[2], flip[2]);
+            }
+            x_log_ratio4<XM, 3>(top, bot, flip, L);
             ken = L[0];
             keu = L[1];
             knu = L[2];
@@ -520,6 +652,18 @@ HB_HD void prism_pair_fast(const PairGeom& g, const double* prm, double* acc)
             if (T::lu) ken = log_sum8<2, XM>(c);
             if (T::ln) keu = log_sum8<1, XM>(c);
             if (T::le) knu = log_sum8<0, XM>(c);
+        }
+        if (cls == PAIR_FAST_CHECK) {
+            // a shift is exactly zero (observer in the plane of a face): the reference's
+            // outside-limit rule (K3) on top of the plain 8-vertex sum. Two zero shifts (edges,
+            // vertices: the NaN rules) never reach this path.
+            const PairPreds pr = make_preds(g);
+            const bool face_rule = !T::mag || (mag_rules & MAG_FACE_OUTSIDE_LIMIT);
+            if (face_rule) {
+                kee += pr.east_face ? 4 * kPi : 0.0;
+                knn += pr.north_face ? 4 * kPi : 0.0;
+                kuu += pr.top_face ? 4 * kPi : 0.0;
+            }
         }
         if (FS == F_EE) acc[0] += prm[0] * kee;
         else if (FS == F_NN) acc[0] += prm[0] * knn;
@@ -540,4 +684,20 @@ HB_HD void prism_pair_fast(const PairGeom& g, const double* prm, double* acc)
     }
 }
 
+// One (observer, prism) pair of kernel variant VARIANT: 0 = rule-exact direct evaluation for every
+// pair (libm); 1 = merged path on CUDA libm; 2 = merged path on the library's own sequences.
+template <int FS, int VARIANT>
+HB_HD void prism_pair(const PairGeom& g, const double* prm, unsigned mag_rules, double* acc,
+                      unsigned& flags)
+{
+    if (VARIANT == 0) {
+        prism_pair_direct<FS>(g, prm, mag_rules, acc, flags);
+        return;
+    }
+    const int cls = classify_pair<FS>(g);
+    if (cls == PAIR_EXACT) prism_pair_direct<FS, (VARIANT == 2)>(g, prm, mag_rules, acc, flags);
+    else prism_pair_fast<FS, (VARIANT == 2)>(g, prm, acc, cls, mag_rules, &flags);
+}
+
 }  // namespace hb
+

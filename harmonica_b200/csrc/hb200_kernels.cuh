@@ -243,14 +243,7 @@ __global__ void __launch_bounds__(kBlock, 4) prism_kernel(const PrismArgs a)
             }
             PairGeom g;
             make_geom(g, E, N, U, we.x, we.y, sn.x, sn.y, bt.x, bt.y);
-            if (VARIANT == 0) {
-                prism_pair_direct<FS>(g, prm, a.rules, acc, flags);
-            } else {
-                if (needs_exact_path<FS>(g))
-                    prism_pair_direct<FS, (VARIANT == 2)>(g, prm, a.rules, acc, flags);
-                else
-                    prism_pair_fast<FS, (VARIANT == 2)>(g, prm, acc);
-            }
+            prism_pair<FS, VARIANT>(g, prm, a.rules, acc, flags);
         }
         __syncthreads();  // the buffer just read may be refilled in the next iteration
     }

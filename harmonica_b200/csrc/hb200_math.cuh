@@ -220,23 +220,29 @@ HB_HD PairPreds make_preds(const PairGeom& g)
     return p;
 }
 
-// true when the pair must take the rule-exact (direct) path. With h = exponent bits of the six
-// squared shifts (non-negative doubles order like their bit patterns: integer pipe only):
+// Which evaluation a pair gets. With h = exponent bits of the six squared shifts (non-negative
+// doubles order like their bit patterns: integer pipe only):
 //
-//  * tensor and magnetic sets: the smallest square is zero or > 2^50 times smaller than the
-//    largest. An exactly-zero shift puts the observer in the plane of a face (NaN and +4 pi
-//    rules); and the reference's on-axis safe_log branch (r == -x) needs y^2 + z^2 < 2^-52 x^2,
-//    so when all squares are within 2^50 of each other it cannot fire.
-//  * potential and accelerations have no NaN / face rules, and every term that is special at a
-//    zero shift carries that shift as a factor (u * atan(e n / (u r)) etc.), so ONE axis may hold
-//    a zero (or arbitrarily small) shift: only the two axes with the larger minima must satisfy
-//    the 2^50 rule. Then for every vertex and every safe_log type y^2 + z^2 contains a square of
-//    a constrained axis, hence >= 2^-50 x^2: no on-axis branch, r > 0, all merged products
-//    positive. (Observers level with the prism tops, or sharing an easting with a prism edge,
-//    stay on the merged path.)
-//  * pairs at absurd length scales (third clause): the merged products reach the 16th power of
-//    a length; beyond ~1e-18 .. 1e18 m the reference's formulation is used as well.
-template <int FS> HB_HD bool needs_exact_path(const PairGeom& g)
+//  PAIR_EXACT  the rule-exact (direct) path: (a) the MEDIAN of the three per-axis minima is zero
+//    or > 2^50 times smaller than the largest square, i.e. TWO axes carry a (nearly) zero shift:
+//    the observer is on (the extension of) an edge or a vertex, where the reference's on-axis
+//    safe_log branch (r == -x needs y^2 + z^2 < 2^-52 x^2) and r == 0 can fire and the NaN rules
+//    of the tensor / magnetic kernels apply; (b) pairs at absurd length scales (the merged
+//    products reach the 16th power of a length; beyond ~1e-18 .. 1e18 m the reference's
+//    formulation is used as well).
+//  PAIR_FAST / PAIR_FAST_CHECK  the merged path. ONE axis may hold a zero (or arbitrarily small)
+//    shift: for every vertex and every safe_log type y^2 + z^2 then contains a square of a
+//    constrained axis, hence >= 2^-50 x^2: no on-axis branch, r > 0, all merged products
+//    positive; the atan pair terms degenerate correctly (im = +-0 with the right sign, re != 0).
+//    Observers in the plane of a prism face -- stations on flat prism tops, grids aligned with
+//    the prism edges -- therefore stay on the merged path for EVERY field. What the reference
+//    does there beyond the plain 8-vertex sum is a function of the shifts' zero / sign pattern
+//    only (PairPreds: +4 pi on the east / north / top face for the face-normal diagonal
+//    component; NaN needs two zero shifts and cannot occur here), and is applied after the merged
+//    evaluation when the smallest square is zero: PAIR_FAST_CHECK.
+enum : int { PAIR_FAST = 0, PAIR_FAST_CHECK = 1, PAIR_EXACT = 2 };
+
+template <int FS> HB_HD int classify_pair(const PairGeom& g)
 {
     const unsigned e0 = (unsigned)hi_word(g.se2[0]), e1 = (unsigned)hi_word(g.se2[1]);
     const unsigned n0 = (unsigned)hi_word(g.sn2[0]), n1 = (unsigned)hi_word(g.sn2[1]);
@@ -245,17 +251,18 @@ template <int FS> HB_HD bool needs_exact_path(const PairGeom& g)
     const unsigned me = e0 < e1 ? e1 : e0, mn = n0 < n1 ? n1 : n0, mu = u0 < u1 ? u1 : u0;
     const unsigned men = me > mn ? me : mn;
     const unsigned hi = men > mu ? men : mu;
-    constexpr bool one_axis_free =
-        (FS == F_POT || FS == F_E || FS == F_N || FS == F_U || FS == FS_ACC3);
     const unsigned lo_en = he < hn ? he : hn, hi_en = he < hn ? hn : he;
-    unsigned lo;
-    if (one_axis_free) {
-        const unsigned t = hi_en < hu ? hi_en : hu;
-        lo = lo_en > t ? lo_en : t;  // median of (he, hn, hu)
-    } else {
-        lo = lo_en < hu ? lo_en : hu;  // minimum
-    }
-    return (lo + (50u << 20) < hi) | (hi - 0x38800000u > 0x47600000u - 0x38800000u);
+    const unsigned t = hi_en < hu ? hi_en : hu;
+    const unsigned med = lo_en > t ? lo_en : t;    // median of (he, hn, hu)
+    const unsigned low = lo_en < hu ? lo_en : hu;  // minimum
+    if ((med + (50u << 20) < hi) | (hi - 0x38800000u > 0x47600000u - 0x38800000u)) return PAIR_EXACT;
+    constexpr bool has_rules = (FS >= F_EE && FS <= F_NU) || FS == FS_TENSOR6 || FS >= FS_MAG_B;
+    // a square below the normal range: the shift may be exactly zero
+    return (has_rules && low < 0x00100000u) ? PAIR_FAST_CHECK : PAIR_FAST;
+}
+template <int FS> HB_HD bool needs_exact_path(const PairGeom& g)
+{
+    return classify_pair<FS>(g) == PAIR_EXACT;
 }
 
 // NaN rule per field set (gravity.py:272-449 predicate sets == choclo's)

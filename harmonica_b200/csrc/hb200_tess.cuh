@@ -586,8 +586,8 @@ __device__ __forceinline__ void tess_walk_deferred(const TessObs& o, const TessA
 // decision from the record, unsplit pairs integrated at once, three cosines per pair); a pair
 // that splits is only noted. When any lane of the warp has kTessDefer pairs noted, and at the
 // end, all lanes walk their lists together.
-template <int FIELD, bool FAST, class TRIG = LibmTrig>
-__global__ void __launch_bounds__(kTessBlock) tesseroid_deferred_kernel(const TessArgs a)
+template <int FIELD, bool FAST, class TRIG = LibmTrig, int MINB = 1>
+__global__ void __launch_bounds__(kTessBlock, MINB) tesseroid_deferred_kernel(const TessArgs a)
 {
     __shared__ double tile[kTessTile * kTessRec];
     double stack[kTessStack * 6];

@@ -117,8 +117,9 @@ HB_HD double fast_rsqrt(double x)
 
 HB_HD double point_rsqrt(double d2) { return fast_rsqrt(d2); }
 
-// log1p Taylor coefficients z^2 .. z^7
-HB_COEF double kLogC[6] = {-0.5, 1.0 / 3.0, -0.25, 0.2, -1.0 / 6.0, 1.0 / 7.0};
+// log1p Taylor coefficients z^2 .. z^11
+HB_COEF double kLogC[10] = {-0.5, 1.0 / 3.0, -0.25, 0.2, -1.0 / 6.0, 1.0 / 7.0,
+                            -0.125, 1.0 / 9.0, -0.1, 1.0 / 11.0};
 // atan Taylor coefficients s^1 .. s^5 (s = t^2)
 HB_COEF double kAtanC[5] = {-1.0 / 3.0, 0.2, -1.0 / 7.0, 1.0 / 9.0, -1.0 / 11.0};
 HB_COEF double kLn2 = 0.693147180559945309417232121458;
@@ -159,19 +160,42 @@ HB_HD double log1p_small(double z)
     return fma(z2, p, z);
 }
 
-// x > 0 and |y| < x / 32, decided on the integer pipe (positive doubles order like integers;
-// subtracting 5 from the exponent field divides by 32)
+// log1p(z) for |z| < 2^-11: Taylor to z^5 (truncation z^6 / 6 < 2^-57 |z|)
+HB_HD double log1p_tiny(double z)
+{
+    const double z2 = z * z;
+    double p = fma(kLogC[3], z, kLogC[2]);
+    p = fma(p, z, kLogC[1]);
+    p = fma(p, z, kLogC[0]);
+    return fma(z2, p, z);
+}
+
+// log1p(z) for |z| < 2^-5: Taylor to z^11 (truncation z^12 / 12 < 2^-58 |z|), no table
+HB_HD double log1p_mid(double z)
+{
+    const double z2 = z * z;
+    double p = fma(kLogC[9], z, kLogC[8]);
+    p = fma(p, z, kLogC[7]);
+    p = fma(p, z, kLogC[6]);
+    p = fma(p, z, kLogC[5]);
+    p = fma(p, z, kLogC[4]);
+    p = fma(p, z, kLogC[3]);
+    p = fma(p, z, kLogC[2]);
+    p = fma(p, z, kLogC[1]);
+    p = fma(p, z, kLogC[0]);
+    return fma(z2, p, z);
+}
+
+// sufficient for x > 0 and |y| < x / 32 (resp. x / 512): compared on the upper words only
+// (positive doubles order like integers; subtracting 5 (9) from the exponent field divides by 32
+// (512)). Pairs that fail take the general sequence, which is valid everywhere.
 HB_HD bool small_angle(double y, double x)
 {
-    int64_t bx, by;
-#if defined(__CUDA_ARCH__)
-    bx = __double_as_longlong(x);
-    by = __double_as_longlong(y);
-#else
-    memcpy(&bx, &x, 8);
-    memcpy(&by, &y, 8);
-#endif
-    return bx - (5LL << 52) > (by & 0x7fffffffffffffffLL);
+    return hi_word(x) - (5 << 20) > (hi_word(y) & 0x7fffffff);
+}
+HB_HD bool tiny_angle(double y, double x)
+{
+    return hi_word(x) - (9 << 20) > (hi_word(y) & 0x7fffffff);
 }
 
 // atan(y / x) for x > 0, |y| < x / 32: same polynomial as fast_atan2 after its reduction
@@ -183,6 +207,15 @@ HB_HD double atan_small(double y, double x)
     p = fma(p, s, kAtanC[2]);
     p = fma(p, s, kAtanC[1]);
     p = fma(p, s, kAtanC[0]);
+    return fma(a * s, p, a);
+}
+
+// atan(y / x) for x > 0, |y| < x / 512: a (1 - s/3 + s^2/5), truncation s^3 / 7 < 2^-56
+HB_HD double atan_tiny(double y, double x)
+{
+    const double a = y * fast_rcp(x);
+    const double s = a * a;
+    const double p = fma(kAtanC[1], s, kAtanC[0]);
     return fma(a * s, p, a);
 }
 

@@ -19,13 +19,10 @@ static void pair_fs(int variant, const double* o, const double* p, const double*
     PairGeom g;
     make_geom(g, o[0], o[1], o[2], p[0], p[1], p[2], p[3], p[4], p[5]);
     unsigned f = 0;
-    if (variant == 0) prism_pair_direct<FS>(g, prm, rules, acc, f);
-    else if (needs_exact_path<FS>(g)) {
-        if (variant == 2) prism_pair_direct<FS, true>(g, prm, rules, acc, f);
-        else prism_pair_direct<FS>(g, prm, rules, acc, f);
-    }
-    else if (variant == 1) prism_pair_fast<FS, false>(g, prm, acc);
-    else prism_pair_fast<FS, true>(g, prm, acc);
+    // the kernel's own dispatch (hb200_fast.cuh)
+    if (variant == 0) prism_pair<FS, 0>(g, prm, rules, acc, f);
+    else if (variant == 1) prism_pair<FS, 1>(g, prm, rules, acc, f);
+    else prism_pair<FS, 2>(g, prm, rules, acc, f);
     *flags |= f;
 }
 
