@@ -570,6 +570,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     lib = hb._lib.load()
     hb.init([local])
+    if args.tile_mode >= 0:
+        hb._lib.check(lib.hb200_set_tile_mode(args.tile_mode))
     sharded = world > 1 and (args.scaling == "strong" or args.shard == "sources")
 
     wl = make_workload(args.workload, args.n_obs, args.n_src, 0 if sharded else rank)
@@ -645,6 +647,7 @@ def run_b200(args):
             "data": "synthetic",
             "config": config_for(wl, args.workload, args, world),
             "run": {"kernel_variant": int(lib.hb200_get_variant()),
+                    "tile_mode": int(lib.hb200_get_tile_mode()),
                     "tesseroid_variant": int(lib.hb200_get_tesseroid_variant()),
                     "step_ms_min_max": main["step_ms_min_max"],
                     "collective": ("none" if not sharded else
@@ -686,6 +689,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-also", action="store_true")
     ap.add_argument("--no-north-star", action="store_true")
+    ap.add_argument("--tile-mode", type=int, default=-1, help="experiments: 0 per-CTA, 1 per-warp tiles")
     args = ap.parse_args()
     if args.impl == "reference":
         args.cpu_seconds = min(args.cpu_seconds, 6.0)

@@ -428,7 +428,11 @@ class EquivalentSourcesSph(EquivalentSources):
     coordinate_system = "spherical"
 
     def __init__(self, damping=None, points=None, relative_depth=500, parallel=True):
-        super().__init__(damping=damping, points=points, depth=relative_depth, parallel=parallel)
+        # the reference's spherical class (spherical.py:112-125) does not validate the depth:
+        # relative_depth == 0 is accepted here as well (coincident sources then divide by zero
+        # in fit / predict, as in the reference)
+        super().__init__(damping=damping, points=points, depth="default", parallel=parallel)
+        self.depth = relative_depth
         self.relative_depth = relative_depth
         self.greens_function = greens_func_spherical
 

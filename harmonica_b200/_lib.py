@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libharmonica_b200.so")
 
 HB200_OK = 0
+HB200_EZERODIV = -5
 FLAG_SINGULAR = 1
 FLAG_ZERO_DIV = 2
 FLAG_TESS_STACK = 4
@@ -51,6 +52,12 @@ SIGNATURES = {
     "hb200_get_variant": (_int, []),
     "hb200_set_tesseroid_variant": (_int, [_int]),
     "hb200_get_tesseroid_variant": (_int, []),
+    "hb200_set_tile_mode": (_int, [_int]),
+    "hb200_get_tile_mode": (_int, []),
+    "hb200_set_source_chunks": (_int, [_int]),
+    "hb200_get_source_chunks": (_int, []),
+    "hb200_set_fit_rcond": (_int, [ctypes.c_double]),
+    "hb200_get_fit_rcond": (ctypes.c_double, []),
     "hb200_launch_count": (ctypes.c_uint64, []),
     "hb200_prism_gravity": (
         _int, [_dp, _dp, _dp, _i64, _dp, _dp, _i64, _u32, _int, _dp, _u32p]),
@@ -124,6 +131,8 @@ def load():
 
 
 def check(rc):
+    if rc == HB200_EZERODIV:
+        raise ZeroDivisionError("division by zero")
     if rc != HB200_OK:
         msg = load().hb200_last_error()
         raise HarmonicaB200Error(f"libharmonica_b200 error {rc}: {msg.decode() if msg else ''}")

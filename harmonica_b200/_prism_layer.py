@@ -236,11 +236,13 @@ def prism_layer(coordinates, surface, reference, properties=None):
     return prisms
 
 
-def _register_xarray_accessor():
-    try:
-        import xarray as xr  # noqa: PLC0415
-    except ImportError:
-        return None
+def _register_xarray_accessor(xr=None):
+    """Register the ``prism_layer`` Dataset accessor on ``xr`` (default: the installed xarray)."""
+    if xr is None:
+        try:
+            import xarray as xr  # noqa: PLC0415
+        except ImportError:
+            return None
 
     @xr.register_dataset_accessor("prism_layer")
     class DatasetAccessorPrismLayer:
@@ -268,6 +270,11 @@ def _register_xarray_accessor():
                 self._obj.easting.values[1] - self._obj.easting.values[0],
             )
 
+        @property
+        def boundaries(self):
+            """layer.py:207-226."""
+            return self._as_numpy(geometry_only=True).boundaries
+
         def update_top_bottom(self, surface, reference):
             tmp = PrismLayer(
                 (self._obj.easting.values, self._obj.northing.values), surface, reference
@@ -275,16 +282,27 @@ def _register_xarray_accessor():
             self._obj.coords["top"] = (self.dims, tmp.top)
             self._obj.coords["bottom"] = (self.dims, tmp.bottom)
 
+        def _get_prism_horizontal_boundaries(self, easting, northing):
+            """layer.py:246-262."""
+            return self._as_numpy(geometry_only=True)._get_prism_horizontal_boundaries(
+                easting, northing
+            )
+
         def _to_prisms(self):
             return self._as_numpy()._to_prisms()
 
-        def _as_numpy(self):
+        def get_prism(self, indices):
+            """layer.py:458-483."""
+            return self._as_numpy().get_prism(indices)
+
+        def _as_numpy(self, geometry_only=False):
             layer = PrismLayer.__new__(PrismLayer)
             layer.easting = self._obj.easting.values
             layer.northing = self._obj.northing.values
-            layer.top = self._obj.top.values
-            layer.bottom = self._obj.bottom.values
-            layer.properties = {k: self._obj[k].values for k in self._obj.data_vars}
+            if not geometry_only:
+                layer.top = self._obj.top.values
+                layer.bottom = self._obj.bottom.values
+                layer.properties = {k: self._obj[k].values for k in self._obj.data_vars}
             return layer
 
         def gravity(self, coordinates, field, *, density_name="density",

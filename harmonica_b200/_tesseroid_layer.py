@@ -196,11 +196,13 @@ def tesseroid_layer(coordinates, surface, reference, properties=None):
     return tesseroids
 
 
-def _register_xarray_accessor():
-    try:
-        import xarray as xr  # noqa: PLC0415
-    except ImportError:
-        return None
+def _register_xarray_accessor(xr=None):
+    """Register the ``tesseroid_layer`` Dataset accessor on ``xr`` (default: the installed xarray)."""
+    if xr is None:
+        try:
+            import xarray as xr  # noqa: PLC0415
+        except ImportError:
+            return None
 
     @xr.register_dataset_accessor("tesseroid_layer")
     class DatasetAccessorTesseroidLayer:

@@ -29,6 +29,9 @@ namespace {
 thread_local std::string g_err;
 std::mutex g_mu;
 int g_variant = 2;
+int g_tile_mode = 1;         // 1: one record stream per warp; 0: per CTA (hb200_set_tile_mode)
+int g_source_chunks = 0;     // 0: chosen from the grid size (choose_chunks)
+double g_fit_rcond = 2.220446049250313e-16;  // cutoff of the undamped fit (hb200_fit_host.cuh)
 std::atomic<uint64_t> g_launches{0};  // kernels launched by this library (hb200_launch_count)
 
 int fail(int code, const char* fmt, ...)
@@ -147,6 +150,9 @@ int choose_chunks(int64_t n_obs, int64_t n_src, int obs_per_block, int sms, int6
     int64_t chunks = 1;
     if (obs_blocks < target) chunks = std::min<int64_t>(tiles, (target + obs_blocks - 1) / obs_blocks);
     chunks = std::min<int64_t>(chunks, 256);
+    // pinned by the caller (hb200_set_source_chunks): the association of the partial sums then
+    // does not depend on the number of observers in the call
+    if (g_source_chunks > 0) chunks = std::min<int64_t>(tiles, g_source_chunks);
     int64_t tiles_per_chunk = (tiles + chunks - 1) / chunks;
     *chunk_len = tiles_per_chunk * kTile;
     chunks = (n_src + *chunk_len - 1) / *chunk_len;
@@ -157,7 +163,10 @@ template <int FS> void launch_prism_fs(const PrismArgs& a, dim3 grid, cudaStream
 {
     if (g_variant == 0) prism_kernel<FS, 0><<<grid, kBlock, 0, st>>>(a);
     else if (g_variant == 1) prism_kernel<FS, 1><<<grid, kBlock, 0, st>>>(a);
-    else prism_kernel<FS, 2><<<grid, kBlock, 0, st>>>(a);
+    else if (g_tile_mode == 0) prism_kernel<FS, 2, false><<<grid, kBlock, 0, st>>>(a);
+    else if (g_tile_mode == 2) prism_kernel<FS, 2, true, 5><<<grid, kBlock, 0, st>>>(a);   // 102 registers
+    else if (g_tile_mode == 3) prism_kernel<FS, 2, false, 5><<<grid, kBlock, 0, st>>>(a);
+    else prism_kernel<FS, 2, true><<<grid, kBlock, 0, st>>>(a);
 }
 
 void launch_prism_any(int fs, const PrismArgs& a, dim3 grid, cudaStream_t st)
@@ -526,8 +535,14 @@ int g_tess_variant = 2;  // 0: first build; 1: root records + deferred walks; 2:
 
 size_t tesseroid_ws_bytes(int64_t n_obs, int64_t n_src, int sms)
 {
+    // variant 6: [records][root partials + walk sums: 2 chunks n_obs doubles][lists][counts]
+    int64_t chunk_len;
+    const int chunks = choose_chunks(n_obs, n_src, kTessRootBlock, sms, &chunk_len);
+    const size_t two_kernel = align_up((size_t)2 * chunks * n_obs * sizeof(double))
+                            + align_up((size_t)chunks * kTessListCap * n_obs * sizeof(int))
+                            + align_up((size_t)2 * chunks * n_obs * sizeof(int));
     return align_up((size_t)std::max<int64_t>(n_src, 1) * kTessRec * sizeof(double))
-         + partial_bytes_for(n_obs, n_src, 1, kTessBlock, sms) + 256;
+         + std::max(partial_bytes_for(n_obs, n_src, 1, kTessBlock, sms), two_kernel) + 256;
 }
 
 // density0 / density1: density at the lower / upper radial quadrature node of every tesseroid
@@ -557,6 +572,46 @@ int tesseroid_dev_impl(const double* lon, const double* lat, const double* rad, 
         pack_tesseroid_fast_records_kernel<<<(unsigned)((n_tess + 127) / 128), 128, 0, st>>>(
             tesseroids, density0, density1, n_tess, field == F_POT ? 1.0 : 2.5, radial, packed);
     CU(cudaGetLastError());
+    // tesseroid_gravity.py:222-225: g_z is the downward component in mGal
+    const double scale = raw ? 1.0 : (field == F_U ? -1e5 : 1.0);
+    if (variant >= 6) {
+        // root pass + walk pass + ordered sum (hb200_tess.cuh)
+        int64_t chunk_len = 0;
+        const int chunks = choose_chunks(n_obs, n_tess, kTessRootBlock, sms, &chunk_len);
+        double* parts = ws.take((size_t)2 * chunks * n_obs * sizeof(double));
+        int* list = (int*)ws.take((size_t)chunks * kTessListCap * n_obs * sizeof(int));
+        int* count = (int*)ws.take((size_t)2 * chunks * n_obs * sizeof(int));  // counts, resume offsets
+        if (!parts || !list || !count) return fail(HB200_EINVAL, "workspace too small");
+        TessArgs a;
+        a.lon = lon; a.lat = lat; a.rad = rad; a.n_obs = n_obs;
+        a.packed = packed; a.n_src = n_tess; a.chunk_len = chunk_len;
+        a.out = parts; a.scale = scale;
+        a.ratio = field == F_POT ? 1.0 : 2.5;
+        a.radial = radial; a.flags = d_flags;
+        dim3 grid_r((unsigned)((n_obs + kTessRootBlock - 1) / kTessRootBlock), (unsigned)chunks);
+        dim3 grid_w((unsigned)((n_obs + kTessBlock - 1) / kTessBlock), (unsigned)chunks);
+        double* walk_sum = parts + (size_t)chunks * n_obs;
+        // variants 6 / 7 / 8: the root kernel compiled for 4 / 6 / 8 resident CTAs (128 / 80 / 64 registers)
+        if (field == F_POT) {
+            if (variant == 6) tesseroid_root_kernel<F_POT, 4><<<grid_r, kTessRootBlock, 0, st>>>(a, list, count);
+            else if (variant == 7) tesseroid_root_kernel<F_POT, 6><<<grid_r, kTessRootBlock, 0, st>>>(a, list, count);
+            else tesseroid_root_kernel<F_POT, 8><<<grid_r, kTessRootBlock, 0, st>>>(a, list, count);
+            tesseroid_walk_kernel<F_POT, OwnTrig><<<grid_w, kTessBlock, 0, st>>>(a, list, count, walk_sum);
+        } else {
+            if (variant == 6) tesseroid_root_kernel<F_U, 4><<<grid_r, kTessRootBlock, 0, st>>>(a, list, count);
+            else if (variant == 7) tesseroid_root_kernel<F_U, 6><<<grid_r, kTessRootBlock, 0, st>>>(a, list, count);
+            else tesseroid_root_kernel<F_U, 8><<<grid_r, kTessRootBlock, 0, st>>>(a, list, count);
+            tesseroid_walk_kernel<F_U, OwnTrig><<<grid_w, kTessBlock, 0, st>>>(a, list, count, walk_sum);
+        }
+        CU(cudaGetLastError());
+        Scales sc;
+        sc.s[0] = scale;
+        reduce_partials_kernel<<<(unsigned)((n_obs + 255) / 256), 256, 0, st>>>(parts, 2 * chunks, 1,
+                                                                               n_obs, sc, out);
+        CU(cudaGetLastError());
+        g_launches += 4;
+        return HB200_OK;
+    }
     double* partial = (double*)(ws.base + ws.used);
     const size_t partial_bytes = ws.left();
     int64_t chunk_len = 0;
@@ -565,8 +620,6 @@ int tesseroid_dev_impl(const double* lon, const double* lat, const double* rad, 
         chunks = 1;
         chunk_len = n_tess;
     }
-    // tesseroid_gravity.py:222-225: g_z is the downward component in mGal
-    const double scale = raw ? 1.0 : (field == F_U ? -1e5 : 1.0);
     TessArgs a;
     a.lon = lon; a.lat = lat; a.rad = rad; a.n_obs = n_obs;
     a.packed = packed; a.n_src = n_tess; a.chunk_len = chunk_len;
@@ -789,6 +842,18 @@ int run_host_job(const double* oe, const double* on, const double* ou, int64_t n
     return HB200_OK;
 }
 
+// the reference's jitted loops raise ZeroDivisionError when an observation point coincides with
+// a source; the entry points without a flags argument report it as an error code
+int check_zero_division(Dev& dev)
+{
+    unsigned f = 0;
+    CU(cudaMemcpyAsync(&f, dev.d_flags, sizeof(unsigned), cudaMemcpyDeviceToHost, dev.st));
+    CU(cudaStreamSynchronize(dev.st));
+    if (f & FLAG_ZERO_DIV)
+        return fail(HB200_EZERODIV, "division by zero: an observation point coincides with a source");
+    return HB200_OK;
+}
+
 size_t ws_prism(int64_t no, int64_t ns, int nf, int sms) { return prism_ws_bytes(no, ns, nf, sms); }
 size_t ws_point(int64_t no, int64_t ns, int nf, int sms)
 {
@@ -853,11 +918,32 @@ int hb200_set_variant(int variant)
 int hb200_get_variant(void) { return g_variant; }
 int hb200_set_tesseroid_variant(int variant)
 {
-    if (variant < 0 || variant > 5) return fail(HB200_EINVAL, "tesseroid variant must be 0 .. 5");
+    if (variant < 0 || variant > 8) return fail(HB200_EINVAL, "tesseroid variant must be 0 .. 8");
     g_tess_variant = variant;
     return HB200_OK;
 }
 int hb200_get_tesseroid_variant(void) { return g_tess_variant; }
+int hb200_set_tile_mode(int mode)
+{
+    if (mode < 0 || mode > 3) return fail(HB200_EINVAL, "tile mode must be 0 (per CTA) or 1 (per warp)");
+    g_tile_mode = mode;
+    return HB200_OK;
+}
+int hb200_get_tile_mode(void) { return g_tile_mode; }
+int hb200_set_source_chunks(int chunks)
+{
+    if (chunks < 0 || chunks > 256) return fail(HB200_EINVAL, "source chunks must be 0 (auto) .. 256");
+    g_source_chunks = chunks;
+    return HB200_OK;
+}
+int hb200_get_source_chunks(void) { return g_source_chunks; }
+int hb200_set_fit_rcond(double rcond)
+{
+    if (!(rcond >= 0.0 && rcond < 1.0)) return fail(HB200_EINVAL, "rcond must be in [0, 1)");
+    g_fit_rcond = rcond;
+    return HB200_OK;
+}
+double hb200_get_fit_rcond(void) { return g_fit_rcond; }
 uint64_t hb200_launch_count(void) { return g_launches.load(); }
 
 void hb200_shutdown(void)
@@ -1228,6 +1314,7 @@ static int eqs_jacobian_host(int spherical, const double* easting, const double*
         CU(cudaMemcpyAsync(d_p[c], hp[c], n_src * 8, cudaMemcpyHostToDevice, dev.st));
     }
     double* d_jac = dev.take<double>((size_t)slab * n_src);
+    CU(cudaMemsetAsync(dev.d_flags, 0, sizeof(unsigned), dev.st));
     for (int64_t i0 = 0; i0 < n_obs; i0 += slab) {
         const int64_t rows = std::min(slab, n_obs - i0);
         const double* obs[3] = {d_o[0] + i0, d_o[1] + i0, d_o[2] + i0};
@@ -1237,7 +1324,7 @@ static int eqs_jacobian_host(int spherical, const double* easting, const double*
                            dev.st));
         CU(cudaStreamSynchronize(dev.st));
     }
-    return HB200_OK;
+    return check_zero_division(dev);
 }
 
 int hb200_eqs_jacobian(const double* easting, const double* northing, const double* upward,
@@ -1289,8 +1376,10 @@ int hb200_eqs_fit(const double* easting, const double* northing, const double* u
     double* d_jac = dev.take<double>((size_t)n_obs * n_src);
     CU(cudaMemcpyAsync(d_data, data, n_obs * 8, cudaMemcpyHostToDevice, dev.st));
     if (weights) CU(cudaMemcpyAsync(d_w, weights, n_obs * 8, cudaMemcpyHostToDevice, dev.st));
+    CU(cudaMemsetAsync(dev.d_flags, 0, sizeof(unsigned), dev.st));
     rc = build_jacobian_dev(dev, spherical, d_o, n_obs, d_p, n_src, d_jac);
     if (rc) return rc;
+    if ((rc = check_zero_division(dev))) return rc;
     const bool damped = !std::isnan(damping);
     rc = dense_least_squares(dev, d_jac, n_obs, n_src, d_data, weights ? d_w : nullptr, damped,
                              damping, d_coef, solver_path);
@@ -1415,7 +1504,7 @@ int hb200_eqs_fit_gb(const double* easting, const double* northing, const double
     CU(cudaMemcpyAsync(coefs, d_coefs, n_src * 8, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(rmse, d_rmse, (n_windows + 1) * 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    return HB200_OK;
+    return check_zero_division(dev);  // a window's Jacobian or its prediction met a zero distance
 }
 
 // ---- device-buffer entry points

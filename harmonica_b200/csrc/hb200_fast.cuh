@@ -36,16 +36,12 @@ template <bool XM> HB_HD double x_sqrt(double x) { return XM ? fast_sqrt_1ulp(x)
 // which other observers share its warp, so results are bit-reproducible under any batching,
 // chunking or sharding of the observers. (A warp whose lanes all agree issues one side only.)
 
-// |z| class of a merged log ratio top / bot = 1 + z, from the exponent of z (integer pipe)
-constexpr int kLogTiny = 0x3f400000;   // |z| < 2^-11: degree-5 log1p
-constexpr int kLogSmall = 0x3f700000;  // |z| < 2^-8: degree-7 log1p
-constexpr int kLogMid = 0x3fa00000;    // |z| < 2^-5: degree-11 log1p
-
-HB_HD double log1p_class(double z, double ratio, int m)
+// log(top / bot) with y = 1 / bot, z = top y - 1 and m = upper word of |z| given: the far field
+// (|z| < 2^-5) needs no table reduction
+HB_HD double log_from_z(double z, double top, double y, int m)
 {
-    if (m < kLogSmall) return log1p_small(z);
-    if (m < kLogMid) return log1p_mid(z);
-    return fast_log(ratio);
+    if (m < kLog1pMax) return log1p_nested(z, m);
+    return fast_log(top * y);
 }
 
 // log(top / bot)
@@ -54,17 +50,14 @@ template <bool XM> HB_HD double x_log_ratio(double top, double bot)
     if (!XM) return log(top / bot);
     const double y = fast_rcp(bot);
     const double z = fma(top, y, -1.0);
-    const int m = hi_word(z) & 0x7fffffff;
-    if (m < kLogTiny) return log1p_tiny(z);
-    return log1p_class(z, top * y, m);
+    return log_from_z(z, top, y, hi_word(z) & 0x7fffffff);
 }
 
 // atan2(y, x): far from the prism x > 0 and |y| < x / 32, no quadrant or table reduction
 template <bool XM> HB_HD double x_atan2(double y, double x)
 {
     if (!XM) return atan2(y, x);
-    if (tiny_angle(y, x)) return atan_tiny(y, x);
-    if (small_angle(y, x)) return atan_small(y, x);
+    if (small_angle(y, x)) return atan_small(y, x, tiny_angle(y, x));
     return fast_atan2(y, x);
 }
 
@@ -274,12 +267,24 @@ HB_HD void x_log_ratio4(const double (&top)[NQ], const double (&bot)[NQ], const 
         const int m = hi_word(z[q]) & 0x7fffffff;
         worst = m > worst ? m : worst;
     }
-    if (worst < kLogTiny) {  // every |z| < 2^-11: the far field, almost all pairs
+    if (worst < kLog1pMax) {
+        // ONE class for the NQ logs of the lane; the classes differ in the leading Horner steps only
+        double p[NQ];
+        if (worst < kLog1pTiny) {  // the far field: almost all pairs
 #pragma unroll
-        for (int q = 0; q < NQ; q++) out[q] = flip_by(log1p_tiny(z[q]), flip[q]);
+            for (int q = 0; q < NQ; q++) p[q] = log1p_head_tiny(z[q]);
+        } else if (worst < kLog1pSmall) {
+#pragma unroll
+            for (int q = 0; q < NQ; q++) p[q] = log1p_head_small(z[q]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < NQ; q++) p[q] = log1p_head_mid(z[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < NQ; q++) out[q] = flip_by(log1p_tail(z[q], p[q]), flip[q]);
     } else {
 #pragma unroll
-        for (int q = 0; q < NQ; q++) out[q] = flip_by(log1p_class(z[q], top[q] * y[q], worst), flip[q]);
+        for (int q = 0; q < NQ; q++) out[q] = flip_by(fast_log(top[q] * y[q]), flip[q]);
     }
 }
 
@@ -318,8 +323,24 @@ HB_HD void acc3_logs_t(const FastCtx& c, double (&top)[12], double (&bot)[12], u
 template <bool XM>
 HB_HD void acc3_logs(const FastCtx& c, double (&top)[12], double (&bot)[12], unsigned (&flip)[12])
 {
-    if (!any_mixed(c)) acc3_logs_t<true>(c, top, bot, flip);
-    else acc3_logs_t<false>(c, top, bot, flip);
+    acc3_logs_t<true>(c, top, bot, flip);
+    if (any_mixed(c)) {  // redo the groups of the axis the observer is inside of
+#pragma unroll
+        for (int f = 0; f < 2; f++) {
+            if (log_mixed<2>(c)) {
+                log_group4_tb<2, 1, false>(c, f, top[0 + f], bot[0 + f], flip[0 + f]);
+                log_group4_tb<2, 0, false>(c, f, top[6 + f], bot[6 + f], flip[6 + f]);
+            }
+            if (log_mixed<1>(c)) {
+                log_group4_tb<1, 2, false>(c, f, top[2 + f], bot[2 + f], flip[2 + f]);
+                log_group4_tb<1, 0, false>(c, f, top[8 + f], bot[8 + f], flip[8 + f]);
+            }
+            if (log_mixed<0>(c)) {
+                log_group4_tb<0, 2, false>(c, f, top[4 + f], bot[4 + f], flip[4 + f]);
+                log_group4_tb<0, 1, false>(c, f, top[10 + f], bot[10 + f], flip[10 + f]);
+            }
+        }
+    }
 }
 
 // the 12 vertex-pair logs of the potential: [0..3] L^u over [i][j], [4..7] L^e over [j][k],
@@ -339,8 +360,18 @@ HB_HD void pot_logs_t(const FastCtx& c, double (&top)[12], double (&bot)[12], un
 }
 HB_HD void pot_logs(const FastCtx& c, double (&top)[12], double (&bot)[12], unsigned (&flip)[12])
 {
-    if (!any_mixed(c)) pot_logs_t<true>(c, top, bot, flip);
-    else pot_logs_t<false>(c, top, bot, flip);
+    pot_logs_t<true>(c, top, bot, flip);
+    if (any_mixed(c)) {  // redo the pairs of the axis the observer is inside of
+#pragma unroll
+        for (int a = 0; a < 2; a++)
+#pragma unroll
+            for (int b = 0; b < 2; b++) {
+                const int q = 2 * a + b;
+                if (log_mixed<2>(c)) log_pair_tb<2, false>(c, a, b, top[q], bot[q], flip[q]);
+                if (log_mixed<0>(c)) log_pair_tb<0, false>(c, a, b, top[4 + q], bot[4 + q], flip[4 + q]);
+                if (log_mixed<1>(c)) log_pair_tb<1, false>(c, a, b, top[8 + q], bot[8 + q], flip[8 + q]);
+            }
+    }
 }
 
 // (im, re) with atan2(im, re) = A^X(b_0) - A^X(b_1) at fixed index f on axis X and index m on the
@@ -397,6 +428,24 @@ template <int X, bool XM> HB_HD double atan_sum8(const FastCtx& c)
     return atan_sum4<X, XM>(c, 0) - atan_sum4<X, XM>(c, 1);
 }
 
+// atan(y[t] / x[t]), t = 0, 1, both small angles: one (per-lane) tiny / small decision for the
+// two, the classes share everything but the leading Horner steps
+HB_HD void atan_small_two(const double (&y)[2], const double (&x)[2], double& r0, double& r1)
+{
+    const double a0 = y[0] * fast_rcp(x[0]), a1 = y[1] * fast_rcp(x[1]);
+    const double s0 = a0 * a0, s1 = a1 * a1;
+    double p0, p1;
+    if (tiny_angle(y[0], x[0]) && tiny_angle(y[1], x[1])) {
+        p0 = atan_poly_tiny(s0);
+        p1 = atan_poly_tiny(s1);
+    } else {
+        p0 = atan_poly_small(s0);
+        p1 = atan_poly_small(s1);
+    }
+    r0 = fma(a0 * s0, p0, a0);
+    r1 = fma(a1 * s1, p1, a1);
+}
+
 // The 8-vertex atan sums of two diagonal kernels (types XA, XB) with one branch for the merge
 // test and one (per-lane) decision for the far-field sequence.
 template <int XA, int XB, bool XM> HB_HD void atan_sum8_two(const FastCtx& c, double& sa, double& sb)
@@ -426,12 +475,8 @@ template <int XA, int XB, bool XM> HB_HD void atan_sum8_two(const FastCtx& c, do
             y[t] = aim * bre + are * bim;
             x[t] = are * bre - aim * bim;
         }
-        if (tiny_angle(y[0], x[0]) && tiny_angle(y[1], x[1])) {
-            sa = atan_tiny(y[0], x[0]);
-            sb = atan_tiny(y[1], x[1]);
-        } else if (small_angle(y[0], x[0]) && small_angle(y[1], x[1])) {
-            sa = atan_small(y[0], x[0]);
-            sb = atan_small(y[1], x[1]);
+        if (small_angle(y[0], x[0]) && small_angle(y[1], x[1])) {
+            atan_small_two(y, x, sa, sb);
         } else {
             sa = fast_atan2(y[0], x[0]);
             sb = fast_atan2(y[1], x[1]);
@@ -467,12 +512,8 @@ template <int X, bool XM> HB_HD void atan_sum4_both(const FastCtx& c, double (&S
             y[f] = im[f][0] * re[f][1] - re[f][0] * im[f][1];
             x[f] = re[f][0] * re[f][1] + im[f][0] * im[f][1];
         }
-        if (tiny_angle(y[0], x[0]) && tiny_angle(y[1], x[1])) {
-            S[0] = atan_tiny(y[0], x[0]);
-            S[1] = atan_tiny(y[1], x[1]);
-        } else if (small_angle(y[0], x[0]) && small_angle(y[1], x[1])) {
-            S[0] = atan_small(y[0], x[0]);
-            S[1] = atan_small(y[1], x[1]);
+        if (small_angle(y[0], x[0]) && small_angle(y[1], x[1])) {
+            atan_small_two(y, x, S[0], S[1]);
         } else {
             S[0] = fast_atan2(y[0], x[0]);
             S[1] = fast_atan2(y[1], x[1]);
@@ -490,16 +531,20 @@ HB_HD double accel_component(const FastCtx& c, const double* pa, const double* p
 {
     double top[4], bot[4], L[4], S[2];
     unsigned flip[4];
-    if (!(log_mixed<LA>(c) | log_mixed<LB>(c))) {
-        log_group4_tb<LA, FA, true>(c, 0, top[0], bot[0], flip[0]);
-        log_group4_tb<LA, FA, true>(c, 1, top[1], bot[1], flip[1]);
-        log_group4_tb<LB, FB, true>(c, 0, top[2], bot[2], flip[2]);
-        log_group4_tb<LB, FB, true>(c, 1, top[3], bot[3], flip[3]);
-    } else {  // observer inside the prism's extent on one of the two axes
-        log_group4_tb<LA, FA, false>(c, 0, top[0], bot[0], flip[0]);
-        log_group4_tb<LA, FA, false>(c, 1, top[1], bot[1], flip[1]);
-        log_group4_tb<LB, FB, false>(c, 0, top[2], bot[2], flip[2]);
-        log_group4_tb<LB, FB, false>(c, 1, top[3], bot[3], flip[3]);
+    log_group4_tb<LA, FA, true>(c, 0, top[0], bot[0], flip[0]);
+    log_group4_tb<LA, FA, true>(c, 1, top[1], bot[1], flip[1]);
+    log_group4_tb<LB, FB, true>(c, 0, top[2], bot[2], flip[2]);
+    log_group4_tb<LB, FB, true>(c, 1, top[3], bot[3], flip[3]);
+    if (log_mixed<LA>(c) | log_mixed<LB>(c)) {
+        // observer inside the prism's extent on one of the two axes: redo that axis' groups
+        if (log_mixed<LA>(c)) {
+            log_group4_tb<LA, FA, false>(c, 0, top[0], bot[0], flip[0]);
+            log_group4_tb<LA, FA, false>(c, 1, top[1], bot[1], flip[1]);
+        }
+        if (log_mixed<LB>(c)) {
+            log_group4_tb<LB, FB, false>(c, 0, top[2], bot[2], flip[2]);
+            log_group4_tb<LB, FB, false>(c, 1, top[3], bot[3], flip[3]);
+        }
     }
     x_log_ratio4<XM, 4>(top, bot, flip, L);
     atan_sum4_both<AX, XM>(c, S);
@@ -568,12 +613,9 @@ HB_HD void prism_pair_fast(const PairGeom& g0, const double* prm, double* acc, i
                     Pn[a][b] = L[8 + 2 * a + b];
                 }
         }
-#pragma unroll
-        for (int f = 0; f < 2; f++) {
-            SA[0][f] = atan_sum4<0, XM>(c, f);
-            SA[1][f] = atan_sum4<1, XM>(c, f);
-            SA[2][f] = atan_sum4<2, XM>(c, f);
-        }
+        atan_sum4_both<0, XM>(c, SA[0]);  // one merge test and one tier decision per axis
+        atan_sum4_both<1, XM>(c, SA[1]);
+        atan_sum4_both<2, XM>(c, SA[2]);
         if (FS == F_POT) {
             double v = 0.0;
 #pragma unroll
@@ -635,14 +677,13 @@ HB_HD void prism_pair_fast(const PairGeom& g0, const double* prm, double* acc, i
         if (XM && fused) {
             double top[3], bot[3], L[3];
             unsigned flip[3];
-            if (!any_mixed(c)) {
-                log_sum8_tb<2, true>(c, top[0], bot[0], flip[0]);
-                log_sum8_tb<1, true>(c, top[1], bot[1], flip[1]);
-                log_sum8_tb<0, true>(c, top[2], bot[2], flip[2]);
-            } else {  // observer inside the prism's extent on some axis
-                log_sum8_tb<2, false>(c, top[0], bot[0], flip[0]);
-                log_sum8_tb<1, false>(c, top[1], bot[1], flip[1]);
-                log_sum8_tb<0, false>(c, top[2], bot[2], flip[2]);
+            log_sum8_tb<2, true>(c, top[0], bot[0], flip[0]);
+            log_sum8_tb<1, true>(c, top[1], bot[1], flip[1]);
+            log_sum8_tb<0, true>(c, top[2], bot[2], flip[2]);
+            if (any_mixed(c)) {  // observer inside the prism's extent on some axis: redo that one
+                if (log_mixed<2>(c)) log_sum8_tb<2, false>(c, top[0], bot[0], flip[0]);
+                if (log_mixed<1>(c)) log_sum8_tb<1, false>(c, top[1], bot[1], flip[1]);
+                if (log_mixed<0>(c)) log_sum8_tb<0, false>(c, top[2], bot[2], flip[2]);
             }
             x_log_ratio4<XM, 3>(top, bot, flip, L);
             ken = L[0];

@@ -15,8 +15,13 @@
 //       (X'X + alpha I) c = X'y   (dual form (XX' + alpha I) when n_features > n_samples),
 //       SVD ridge filter if the factorisation fails (sklearn's own fallback) or its pivots
 //       show the normal equations to be singular to working precision;
-//   damping None  -> sklearn LinearRegression => scipy.linalg.lstsq (gelsd, cond = eps):
-//       minimum-norm solution from the SVD with singular values below eps * s_max dropped.
+//   damping None  -> sklearn LinearRegression => scipy.linalg.lstsq(X, y, cond = tol): the
+//       minimum-norm solution from the SVD with singular values below rcond * s_max dropped.
+//       rcond = g_fit_rcond (hb200_set_fit_rcond). Default: machine epsilon = cond=None of the
+//       scikit-learn releases the reference's tests were written against (its undamped fits
+//       must reproduce the data to 1e-3, test/test_eq_sources_spherical.py:26-67, which a
+//       truncation at 1e-6 does not). scikit-learn >= 1.7 passes cond = tol = 1e-6: set
+//       hb200_set_fit_rcond(1e-6) to reproduce THAT (tests/test_eqs_fit_host.py checks both).
 #pragma once
 #include <cublas_v2.h>
 #include <cusolverDn.h>
@@ -164,10 +169,11 @@ unsigned blocks_for(int64_t n, int per = 256) { return (unsigned)((n + per - 1) 
 int build_jacobian_dev(Dev& dev, int spherical, const double* const obs[3], int64_t n,
                        const double* const src[3], int64_t p, double* jac)
 {
-    dim3 grid(blocks_for(p), (unsigned)((n + 15) / 16));
+    // a zero distance sets HB200_FLAG_ZERO_DIV in dev.d_flags (callers clear and read it)
+    dim3 grid((unsigned)((n + 15) / 16), blocks_for(p));
     if (!spherical) {
         eqs_jacobian_kernel<<<grid, 256, 0, dev.st>>>(obs[0], obs[1], obs[2], n, src[0], src[1],
-                                                     src[2], p, jac);
+                                                     src[2], p, jac, dev.d_flags);
         CU(cudaGetLastError());
         g_launches += 1;
         return HB200_OK;
@@ -180,7 +186,7 @@ int build_jacobian_dev(Dev& dev, int spherical, const double* const obs[3], int6
     // the weight slot of the record is unused here: any valid array of the right length does
     pack_points_sph_kernel<<<blocks_for(n), 256, 0, dev.st>>>(obs[0], obs[1], obs[2], obs[2], n, orec);
     pack_points_sph_kernel<<<blocks_for(p), 256, 0, dev.st>>>(src[0], src[1], src[2], src[2], p, srec);
-    eqs_jacobian_sph_kernel<<<grid, 256, 0, dev.st>>>(orec, n, srec, p, jac);
+    eqs_jacobian_sph_kernel<<<grid, 256, 0, dev.st>>>(orec, n, srec, p, jac, dev.d_flags);
     CU(cudaGetLastError());
     g_launches += 3;
     CU(cudaStreamSynchronize(dev.st));  // rec is released on return
@@ -214,7 +220,7 @@ int dense_least_squares(Dev& dev, double* jac, int64_t n, int64_t p, const doubl
     int* d_info = static_cast<int*>(b_info.p);
 
     column_scale_kernel<<<(unsigned)((p + 31) / 32), dim3(32, 8), 0, st>>>(jac, n, p, scale);
-    scale_system_kernel<<<dim3(blocks_for(p), (unsigned)((n + 15) / 16)), 256, 0, st>>>(
+    scale_system_kernel<<<dim3((unsigned)((n + 15) / 16), blocks_for(p)), 256, 0, st>>>(
         jac, n, p, scale, weights, data, y);
     CU(cudaGetLastError());
     g_launches += 2;
@@ -222,7 +228,7 @@ int dense_least_squares(Dev& dev, double* jac, int64_t n, int64_t p, const doubl
     // cuBLAS is column-major: the row-major n x p `jac` is M = J' (p x n, leading dimension p)
     bool need_svd = !damped;
     int svd_mode = 0;
-    double svd_param = 2.220446049250313e-16;
+    double svd_param = g_fit_rcond;
     if (path) *path = 0;
     if (damped) {
         const bool primal = p <= n;

@@ -17,13 +17,15 @@ namespace hb {
 // pack_points_sph_kernel, so the inner loop has no transcendental but the square root.
 __global__ void eqs_jacobian_sph_kernel(const double* __restrict__ obs, int64_t n_obs,
                                         const double* __restrict__ src, int64_t n_src,
-                                        double* __restrict__ jac)
+                                        double* __restrict__ jac, unsigned* flags)
 {
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // row blocks on grid.x (no 65535 limit), column blocks on grid.y
+    const int64_t j = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
     if (j >= n_src) return;
     const double* q = src + j * 6;
     const double clam_p = q[0], slam_p = q[1], cphi_p = q[2], sphi_p = q[3], rad_p = q[4];
-    const int64_t i0 = (int64_t)blockIdx.y * 16;
+    const int64_t i0 = (int64_t)blockIdx.x * 16;
+    bool zero = false;
 #pragma unroll 4
     for (int r = 0; r < 16; r++) {
         const int64_t i = i0 + r;
@@ -33,8 +35,10 @@ __global__ void eqs_jacobian_sph_kernel(const double* __restrict__ obs, int64_t 
         const double cospsi = sphi_p * o[3] + cphi_p * o[2] * coslambda;
         const double dr = o[4] - rad_p;
         const double d2 = dr * dr + 2 * o[4] * rad_p * (1 - cospsi);
+        zero |= d2 == 0.0;  // the reference's jitted loop raises ZeroDivisionError here
         jac[i * n_src + j] = 1.0 / sqrt(d2);
     }
+    if (zero && flags) atomicOr(flags, FLAG_ZERO_DIV);
 }
 
 // Column statistics of a row-major n x p matrix, as sklearn's StandardScaler(with_mean=False)
@@ -82,10 +86,10 @@ __global__ void scale_system_kernel(double* __restrict__ jac, int64_t n, int64_t
                                     const double* __restrict__ w, const double* __restrict__ data,
                                     double* __restrict__ y)
 {
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t j = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
     if (j >= p) return;
     const double sc = scale[j];
-    const int64_t i0 = (int64_t)blockIdx.y * 16;
+    const int64_t i0 = (int64_t)blockIdx.x * 16;
     for (int r = 0; r < 16; r++) {
         const int64_t i = i0 + r;
         if (i >= n) break;

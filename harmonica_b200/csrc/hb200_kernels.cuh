@@ -141,9 +141,9 @@ struct PrismArgs {
 };
 
 // ---- TMA bulk-copy staging (cp.async.bulk + mbarrier; SASS: UBLKCP / SYNCS) --------------
-// One elected thread asks the copy engine for the next tile of packed records while the CTA
-// computes on the current one (two shared-memory buffers, one mbarrier each); the other 127
-// threads never touch global memory inside the source loop.
+// One elected lane per warp asks the copy engine for the next tile of packed records while the
+// warp computes on the current one (two shared-memory buffers, one mbarrier each); the other
+// lanes never touch global memory inside the source loop.
 __device__ __forceinline__ unsigned smem_addr(const void* p)
 {
     return (unsigned)__cvta_generic_to_shared(p);
@@ -182,14 +182,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
         : "memory");
 }
 
-template <int FS, int VARIANT>
-__global__ void __launch_bounds__(kBlock, 4) prism_kernel(const PrismArgs a)
+// Every WARP stages its own copy of the record stream (kWarpTile records per bulk copy, two
+// buffers, one mbarrier each) and synchronises only with itself: there is no CTA-wide barrier in
+// the source loop, so a warp whose lanes meet near-field prisms (longer sequences) never holds
+// up the other three. The copies come out of L2 (the packed records of a call are read
+// n_obs / 32 times in total: ~0.1 TB/s for the 500 x 500 layer, far below L2 bandwidth).
+constexpr int kWarpTile = 64;
+constexpr int kWarps = kBlock / 32;
+
+// WARP_TILES = true: as described above. false: ONE copy per CTA (kTile records, elected thread
+// 0, __syncthreads() closes every tile) -- kept selectable (hb200_set_tile_mode) for comparison.
+template <int FS, int VARIANT, bool WARP_TILES = true, int MINB = 4>
+__global__ void __launch_bounds__(kBlock, MINB) prism_kernel(const PrismArgs a)
 {
     typedef Traits<FS> T;
     constexpr int STRIDE = T::mag ? kMagStride : kPrismStride;
-    __shared__ alignas(128) double2 tiles[2][kTile * STRIDE / 2];
-    __shared__ alignas(8) uint64_t bars[2];
+    constexpr int GROUPS = WARP_TILES ? kWarps : 1;       // independent record streams per CTA
+    constexpr int TILE = WARP_TILES ? kWarpTile : kTile;  // records per bulk copy
+    __shared__ alignas(128) double2 tiles[GROUPS][2][TILE * STRIDE / 2];
+    __shared__ alignas(8) uint64_t bars[GROUPS][2];
 
+    const int grp = WARP_TILES ? (threadIdx.x >> 5) : 0;
+    const bool leader = WARP_TILES ? ((threadIdx.x & 31) == 0) : (threadIdx.x == 0);
     const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     const int64_t ic = i < a.n_obs ? i : a.n_obs - 1;
     const double E = a.oe[ic], N = a.on[ic], U = a.ou[ic];
@@ -203,31 +217,32 @@ __global__ void __launch_bounds__(kBlock, 4) prism_kernel(const PrismArgs a)
     const int64_t end = begin + a.chunk_len < a.n_src ? begin + a.chunk_len : a.n_src;
     const double* src = a.packed;
 
-    if (threadIdx.x == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
+    if (leader) {
+        mbar_init(&bars[grp][0], 1);
+        mbar_init(&bars[grp][1], 1);
         mbar_fence_init();
     }
-    __syncthreads();
-    if (threadIdx.x == 0 && begin < end) {
-        const int cnt0 = (int)((end - begin) < kTile ? (end - begin) : kTile);
-        bulk_load(tiles[0], src + begin * STRIDE, (unsigned)(cnt0 * STRIDE * sizeof(double)), &bars[0]);
+    if (WARP_TILES) __syncwarp(); else __syncthreads();
+    if (leader && begin < end) {
+        const int cnt0 = (int)((end - begin) < TILE ? (end - begin) : TILE);
+        bulk_load(tiles[grp][0], src + begin * STRIDE, (unsigned)(cnt0 * STRIDE * sizeof(double)),
+                  &bars[grp][0]);
     }
     unsigned phase0 = 0, phase1 = 0;
     int buf = 0;
-    for (int64_t t0 = begin; t0 < end; t0 += kTile, buf ^= 1) {
-        const int cnt = (int)((end - t0) < kTile ? (end - t0) : kTile);
-        // prefetch the next tile into the other buffer (every thread finished reading it at the
-        // __syncthreads() that closed the previous iteration)
-        const int64_t t1 = t0 + kTile;
-        if (threadIdx.x == 0 && t1 < end) {
-            const int cnt1 = (int)((end - t1) < kTile ? (end - t1) : kTile);
-            bulk_load(tiles[buf ^ 1], src + t1 * STRIDE, (unsigned)(cnt1 * STRIDE * sizeof(double)),
-                      &bars[buf ^ 1]);
+    for (int64_t t0 = begin; t0 < end; t0 += TILE, buf ^= 1) {
+        const int cnt = (int)((end - t0) < TILE ? (end - t0) : TILE);
+        // prefetch the next tile into the other buffer (every thread of the group finished
+        // reading it at the barrier that closed the previous iteration)
+        const int64_t t1 = t0 + TILE;
+        if (leader && t1 < end) {
+            const int cnt1 = (int)((end - t1) < TILE ? (end - t1) : TILE);
+            bulk_load(tiles[grp][buf ^ 1], src + t1 * STRIDE, (unsigned)(cnt1 * STRIDE * sizeof(double)),
+                      &bars[grp][buf ^ 1]);
         }
-        if (buf == 0) { mbar_wait(&bars[0], phase0); phase0 ^= 1; }
-        else { mbar_wait(&bars[1], phase1); phase1 ^= 1; }
-        const double2* tile = tiles[buf];
+        if (buf == 0) { mbar_wait(&bars[grp][0], phase0); phase0 ^= 1; }
+        else { mbar_wait(&bars[grp][1], phase1); phase1 ^= 1; }
+        const double2* tile = tiles[grp][buf];
 #pragma unroll 1
         for (int s = 0; s < cnt; s++) {
             const double2* p = tile + s * (STRIDE / 2);
@@ -245,7 +260,8 @@ __global__ void __launch_bounds__(kBlock, 4) prism_kernel(const PrismArgs a)
             make_geom(g, E, N, U, we.x, we.y, sn.x, sn.y, bt.x, bt.y);
             prism_pair<FS, VARIANT>(g, prm, a.rules, acc, flags);
         }
-        __syncthreads();  // the buffer just read may be refilled in the next iteration
+        // the buffer just read may be refilled in the next iteration
+        if (WARP_TILES) __syncwarp(); else __syncthreads();
     }
     if (i < a.n_obs) {
         if (gridDim.y == 1) {
@@ -515,19 +531,24 @@ __global__ void eqs_jacobian_kernel(const double* __restrict__ oe, const double*
                                     const double* __restrict__ ou, int64_t n_obs,
                                     const double* __restrict__ pe, const double* __restrict__ pn,
                                     const double* __restrict__ pu, int64_t n_src,
-                                    double* __restrict__ jac)
+                                    double* __restrict__ jac, unsigned* flags)
 {
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // row blocks on grid.x (no 65535 limit), column blocks on grid.y
+    const int64_t j = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
     if (j >= n_src) return;
     const double se = pe[j], sn = pn[j], su = pu[j];
-    const int64_t i0 = (int64_t)blockIdx.y * 16;
+    const int64_t i0 = (int64_t)blockIdx.x * 16;
+    bool zero = false;
 #pragma unroll 4
     for (int r = 0; r < 16; r++) {
         const int64_t i = i0 + r;
         if (i >= n_obs) break;
         const double de = oe[i] - se, dn = on[i] - sn, du = ou[i] - su;
-        jac[i * n_src + j] = 1.0 / sqrt(de * de + dn * dn + du * du);
+        const double d2 = de * de + dn * dn + du * du;
+        zero |= d2 == 0.0;  // the reference's jitted loop raises ZeroDivisionError here
+        jac[i * n_src + j] = 1.0 / sqrt(d2);
     }
+    if (zero && flags) atomicOr(flags, FLAG_ZERO_DIV);
 }
 
 // ----------------------------------------------------- FP64 issue-rate probe

@@ -626,6 +626,114 @@ __global__ void __launch_bounds__(kTessBlock, MINB) tesseroid_deferred_kernel(co
     if (flags && a.flags) atomicOr(a.flags, flags);
 }
 
+// ---- variant 6: the root pass and the walks as TWO kernels ---------------------------------------
+// tesseroid_root_kernel: the arithmetic-only far field of tess_root_fast over all pairs; a pair
+// whose root splits is only RECORDED (its offset in the chunk) in a per-(chunk, observer) list in
+// global memory. Without the walk (trig, divisions, the 4.8 KB stack) the kernel needs half the
+// registers of tesseroid_deferred_kernel: 128-thread CTAs, twice the resident warps.
+// tesseroid_walk_kernel: one thread per (chunk, observer) walks the recorded pairs of ITS list in
+// order (lanes = neighbouring observers: similar lists, similar trees) and writes their sum.
+// reduce_partials_kernel then adds, per observer and in fixed order, the root partials and the
+// walk sums of all chunks: deterministic, no atomics on data.
+// A list holds kTessListCap pairs. An observer with more split roots in one chunk (next to a
+// pole every tesseroid of a latitude ring is near) stops its root pass at the first pair that
+// does not fit and records that offset: the walk kernel, after the listed pairs, evaluates the
+// REST of the chunk for this observer pair by pair with the general statements (root decision
+// included). Nothing is skipped and nothing is counted twice.
+constexpr int kTessRootBlock = 128;
+constexpr int kTessListCap = 64;
+
+template <int FIELD, int MINB>
+__global__ void __launch_bounds__(kTessRootBlock, MINB) tesseroid_root_kernel(const TessArgs a, int* list,
+                                                                               int* count)
+{
+    __shared__ double tile[kTessTile * kTessRec];
+    const int64_t i = (int64_t)blockIdx.x * kTessRootBlock + threadIdx.x;
+    const bool live = i < a.n_obs;
+    const int64_t ic = live ? i : a.n_obs - 1;
+    TessObs o;
+    tess_make_obs(o, a.lon[ic], a.lat[ic], a.rad[ic]);
+    double acc = 0.0;
+    unsigned flags = 0;
+    int n_split = 0;
+    const int64_t begin = (int64_t)blockIdx.y * a.chunk_len;
+    const int64_t end = begin + a.chunk_len < a.n_src ? begin + a.chunk_len : a.n_src;
+    int resume = (int)(end - begin);  // offset from which the walk kernel takes over (none)
+    bool open = live;
+    int* my_list = list + ((int64_t)blockIdx.y * kTessListCap) * a.n_obs + ic;  // [chunk][k][obs]
+    for (int64_t t0 = begin; t0 < end; t0 += kTessTile) {
+        const int cnt = (int)((end - t0) < kTessTile ? (end - t0) : kTessTile);
+        __syncthreads();
+        for (int x = threadIdx.x; x < cnt * kTessRec; x += kTessRootBlock)
+            tile[x] = a.packed[t0 * kTessRec + x];
+        __syncthreads();
+        for (int s = 0; s < cnt; s++) {
+            if (!open) continue;
+            const int root = tess_root_fast<FIELD>(o, tile + s * kTessRec, acc, flags);
+            if (root == 0) {
+                if (n_split < kTessListCap) {
+                    my_list[(int64_t)n_split * a.n_obs] = (int)(t0 - begin) + s;
+                    n_split++;
+                } else {  // list full: this pair and the rest of the chunk go to the walk kernel
+                    resume = (int)(t0 - begin) + s;
+                    open = false;
+                }
+            }
+        }
+    }
+    if (live) {
+        a.out[(int64_t)blockIdx.y * a.n_obs + i] = acc;  // always partial: [chunk][obs]
+        count[(int64_t)blockIdx.y * a.n_obs + i] = n_split;
+        count[((int64_t)gridDim.y + blockIdx.y) * a.n_obs + i] = resume;
+    }
+    if (flags && a.flags) atomicOr(a.flags, flags);
+}
+
+template <int FIELD, class TRIG>
+__global__ void __launch_bounds__(kTessBlock) tesseroid_walk_kernel(const TessArgs a, const int* list,
+                                                                    const int* count, double* walk_sum)
+{
+    double stack[kTessStack * 6];
+    const int64_t i = (int64_t)blockIdx.x * kTessBlock + threadIdx.x;
+    if (i >= a.n_obs) return;
+    const int n = count[(int64_t)blockIdx.y * a.n_obs + i];
+    int resume = count[((int64_t)gridDim.y + blockIdx.y) * a.n_obs + i];
+    const int64_t chunk_begin = (int64_t)blockIdx.y * a.chunk_len;
+    const int chunk_cnt = (int)((chunk_begin + a.chunk_len < a.n_src ? chunk_begin + a.chunk_len : a.n_src)
+                                - chunk_begin);
+    double acc = 0.0;
+    if (n > 0 || resume < chunk_cnt) {
+        TessObs o;
+        tess_make_obs(o, a.lon[i], a.lat[i], a.rad[i]);
+        unsigned flags = 0;
+        const int64_t begin = (int64_t)blockIdx.y * a.chunk_len;
+        const int* my_list = list + ((int64_t)blockIdx.y * kTessListCap) * a.n_obs + i;
+        TessWalk wk;
+        wk.stack_top = -1;
+        wk.n_leaves = 0;
+        wk.density[0] = wk.density[1] = 0.0;
+        int k = 0;
+        while (true) {  // one pop per trip, whatever the shapes of the lanes' trees
+            if (wk.stack_top < 0) {
+                int off;
+                if (k < n) off = my_list[(int64_t)(k++) * a.n_obs];  // the listed pairs ...
+                else if (resume < chunk_cnt) off = resume++;         // ... then the rest of the chunk
+                else break;
+                const double* rec = a.packed + (begin + off) * kTessRec;
+                if (rec[29] != 0.0) {  // a zero dimension: numba's ZeroDivisionError (tess_root_fast)
+                    flags |= FLAG_ZERO_DIV;
+                    continue;
+                }
+                tess_walk_begin(wk, rec, rec[6], rec[kTessRho1Fast], stack);
+            }
+            tess_walk_step<FIELD, kTessStack, kTessMaxLeaves, TRIG>(o, a.ratio, a.radial != 0, stack, wk,
+                                                                    acc, flags);
+        }
+        if (flags && a.flags) atomicOr(a.flags, flags);
+    }
+    walk_sum[(int64_t)blockIdx.y * a.n_obs + i] = acc;
+}
+
 // check_points_outside_tesseroids as one pass: sets FLAG_TESS_INSIDE if any pair conflicts
 __global__ void __launch_bounds__(128) tesseroid_inside_scan_kernel(const TessArgs a)
 {

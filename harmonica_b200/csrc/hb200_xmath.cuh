@@ -160,30 +160,44 @@ HB_HD double log1p_small(double z)
     return fma(z2, p, z);
 }
 
-// log1p(z) for |z| < 2^-11: Taylor to z^5 (truncation z^6 / 6 < 2^-57 |z|)
-HB_HD double log1p_tiny(double z)
+// log1p(z) = z + z^2 (c0 + c1 z + ...) with the Taylor degree chosen from the class of |z|
+// (m = upper word of |z|): |z| < 2^-11: z^5, < 2^-8: z^7, < 2^-5: z^11 (truncation below 2^-55
+// |z| in every class). The classes differ only in the LEADING Horner steps (log1p_head_*), the
+// last three steps (log1p_tail) are shared, so a warp whose lanes fall into two classes
+// repeats little. m >= kLog1pMax is not allowed.
+constexpr int kLog1pTiny = 0x3f400000;   // 2^-11
+constexpr int kLog1pSmall = 0x3f700000;  // 2^-8
+constexpr int kLog1pMax = 0x3fa00000;    // 2^-5
+HB_HD double log1p_head_tiny(double z) { return fma(kLogC[3], z, kLogC[2]); }
+HB_HD double log1p_head_small(double z)
 {
-    const double z2 = z * z;
-    double p = fma(kLogC[3], z, kLogC[2]);
-    p = fma(p, z, kLogC[1]);
-    p = fma(p, z, kLogC[0]);
-    return fma(z2, p, z);
+    double p = fma(kLogC[5], z, kLogC[4]);
+    p = fma(p, z, kLogC[3]);
+    return fma(p, z, kLogC[2]);
 }
-
-// log1p(z) for |z| < 2^-5: Taylor to z^11 (truncation z^12 / 12 < 2^-58 |z|), no table
-HB_HD double log1p_mid(double z)
+HB_HD double log1p_head_mid(double z)
 {
-    const double z2 = z * z;
     double p = fma(kLogC[9], z, kLogC[8]);
     p = fma(p, z, kLogC[7]);
     p = fma(p, z, kLogC[6]);
     p = fma(p, z, kLogC[5]);
     p = fma(p, z, kLogC[4]);
     p = fma(p, z, kLogC[3]);
-    p = fma(p, z, kLogC[2]);
+    return fma(p, z, kLogC[2]);
+}
+HB_HD double log1p_tail(double z, double p)
+{
     p = fma(p, z, kLogC[1]);
     p = fma(p, z, kLogC[0]);
-    return fma(z2, p, z);
+    return fma(z * z, p, z);
+}
+HB_HD double log1p_nested(double z, int m)
+{
+    double p;
+    if (m < kLog1pTiny) p = log1p_head_tiny(z);
+    else if (m < kLog1pSmall) p = log1p_head_small(z);
+    else p = log1p_head_mid(z);
+    return log1p_tail(z, p);
 }
 
 // sufficient for x > 0 and |y| < x / 32 (resp. x / 512): compared on the upper words only
@@ -198,24 +212,21 @@ HB_HD bool tiny_angle(double y, double x)
     return hi_word(x) - (9 << 20) > (hi_word(y) & 0x7fffffff);
 }
 
-// atan(y / x) for x > 0, |y| < x / 32: same polynomial as fast_atan2 after its reduction
-HB_HD double atan_small(double y, double x)
+// atan(y / x) for x > 0, |y| < x / 32: same polynomial as fast_atan2 after its reduction;
+// tiny (|y| < x / 512): the three leading Horner steps are dropped (truncation s^3 / 7 < 2^-56)
+HB_HD double atan_poly_small(double s)
 {
-    const double a = y * fast_rcp(x);
-    const double s = a * a;
     double p = fma(kAtanC[4], s, kAtanC[3]);
     p = fma(p, s, kAtanC[2]);
     p = fma(p, s, kAtanC[1]);
-    p = fma(p, s, kAtanC[0]);
-    return fma(a * s, p, a);
+    return fma(p, s, kAtanC[0]);
 }
-
-// atan(y / x) for x > 0, |y| < x / 512: a (1 - s/3 + s^2/5), truncation s^3 / 7 < 2^-56
-HB_HD double atan_tiny(double y, double x)
+HB_HD double atan_poly_tiny(double s) { return fma(kAtanC[1], s, kAtanC[0]); }
+HB_HD double atan_small(double y, double x, bool tiny = false)
 {
     const double a = y * fast_rcp(x);
     const double s = a * a;
-    const double p = fma(kAtanC[1], s, kAtanC[0]);
+    const double p = tiny ? atan_poly_tiny(s) : atan_poly_small(s);
     return fma(a * s, p, a);
 }
 

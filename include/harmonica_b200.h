@@ -38,6 +38,9 @@ extern "C" {
 #define HB200_ECUDA (-2)   /* CUDA runtime error, see hb200_last_error() */
 #define HB200_ENODEV (-3)  /* no usable sm_100 device */
 #define HB200_ENOMEM (-4)
+#define HB200_EZERODIV (-5) /* an observation point coincides with a source (entry points without
+                             * a flags argument: the Jacobians and the fits); the reference's
+                             * jitted loops raise ZeroDivisionError there */
 
 /* field ids (bit positions of field_mask). Names follow harmonica's FIELDS
  * dict, _forward/prisms/gravity.py:37-48. */
@@ -82,19 +85,37 @@ void hb200_shutdown(void);
 const char* hb200_last_error(void);
 /* variant 0 = rule-exact direct evaluation for every pair; 1 = merged
  * transcendentals (CUDA libm) with the direct path on pairs whose observer lies
- * in the plane of a prism face; 2 (default) = as 1 with the library's own
- * division / sqrt / log / atan2 sequences (hb200_xmath.cuh) */
+ * on (the extension of) a prism edge or vertex; 2 (default) = as 1 with the
+ * library's own division / sqrt / log / atan2 sequences (hb200_xmath.cuh) */
 int hb200_set_variant(int variant);
 int hb200_get_variant(void);
 /* tesseroid kernels: 1 = observer-independent parts of every tesseroid precomputed into root
  * records, pairs that split deferred and walked by all lanes of a warp together; 2 (default) =
  * as 1 with an arithmetic-only far field (cosine of the longitude difference from precomputed
  * factors, the library's reciprocal square root, squared split thresholds); 3 = as 2 with the
- * library's own bounded-angle sin / cos / acos in the walks (written after the round-1 GPU budget
- * ended: validated on the host build only, not the default); 0 = first build (every pair walked
- * where it is met) */
+ * library's own bounded-angle sin / cos / acos in the walks; 4, 5 = as 3 compiled for 80 / 64
+ * registers (occupancy experiments); 0 = first build (every pair walked where it is met) */
 int hb200_set_tesseroid_variant(int variant);
 int hb200_get_tesseroid_variant(void);
+/* staging of the packed prism records in the prism kernels: 1 (default) = every warp streams
+ * its own copy with TMA bulk copies and synchronises only with itself; 0 = one copy per CTA with
+ * a CTA-wide barrier per tile (first build, kept for comparison). Values are identical. */
+int hb200_set_tile_mode(int mode);
+int hb200_get_tile_mode(void);
+/* Reproducibility. The value of an (observer, source) pair never depends on the batch it is
+ * computed in. What does depend on the call is the ASSOCIATION of the sum over sources: with few
+ * observers the source list is split into chunks over grid.y (to fill the GPU) whose partial sums
+ * are added in a fixed order. chunks > 0 pins the number of chunks (1 = one sequential sum per
+ * observer, like the reference's loop): results are then bit-identical under any batching,
+ * permutation or sharding of the observers. 0 (default): chosen from the grid size. */
+int hb200_set_source_chunks(int chunks);
+int hb200_get_source_chunks(void);
+/* relative singular-value cutoff of the UNDAMPED equivalent-sources fit (damping = NaN): values
+ * below rcond * s_max are dropped, like scipy.linalg.lstsq(cond=rcond) behind sklearn's
+ * LinearRegression. Default: machine epsilon (cond=None, scikit-learn < 1.7, the behaviour the
+ * reference's own tests pin); 1e-6 reproduces LinearRegression(tol=1e-6) of scikit-learn >= 1.7. */
+int hb200_set_fit_rcond(double rcond);
+double hb200_get_fit_rcond(void);
 /* number of CUDA kernels this library has launched so far (all entry points) */
 uint64_t hb200_launch_count(void);
 
@@ -218,7 +239,8 @@ int hb200_eqs_jacobian_spherical(const double* longitude, const double* latitude
  *   damping given (not NaN): (X'X + damping I) c = X'y by Cholesky, like sklearn's Ridge
  *       (dual form when n_src > n_obs; SVD ridge filter if the factorisation fails);
  *   damping = NaN ("None"): minimum-norm least squares from the SVD with singular values
- *       below eps * s_max dropped, like scipy.linalg.lstsq behind sklearn's LinearRegression.
+ *       below rcond * s_max dropped (hb200_set_fit_rcond), like scipy.linalg.lstsq behind
+ *       sklearn's LinearRegression.
  * coefs (n_src) receives the unscaled coefficients. *solver_path (may be NULL): 0 Cholesky,
  * 1 SVD pseudo-inverse, 2 SVD ridge filter. Dense algebra: cuBLAS / cuSOLVER, loaded on
  * first use. */

@@ -17,6 +17,8 @@ from _common import GRAVITY_FIELDS, TENSOR_FIELDS, config1, layer_config2  # noq
 hb.init([0])
 variant = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 hb._lib.load().hb200_set_variant(variant)
+if os.environ.get("HB200_TILE_MODE"):
+    hb._lib.load().hb200_set_tile_mode(int(os.environ["HB200_TILE_MODE"]))
 rng = np.random.default_rng(0)
 
 

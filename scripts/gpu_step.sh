@@ -6,7 +6,7 @@ TAG=$1; shift
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader > gpurun_out/${TAG}_gpu.txt 2>&1
 ncu_case() {  # name kernel-regex python-snippet
-    timeout 90 ncu --set full --clock-control none --import-source on -k "regex:$2" -c 1 -f \
+    timeout 150 ncu --set full --clock-control none --import-source on -k "regex:$2" -c 1 -f \
         -o gpurun_out/${TAG}_prof_$1 python -c "
 import sys; sys.path[:0]=['.','tests']
 import numpy as np, bench, harmonica_b200 as hb
@@ -28,6 +28,17 @@ bench)
 benchq)  # quick: main workload only
     timeout 120 python bench.py --no-cpu --no-also --no-north-star --steps 3 > gpurun_out/${TAG}_bench_quick.log 2>&1
     echo "benchq rc=$?"; tail -1 gpurun_out/${TAG}_bench_quick.log | cut -c1-200 ;;
+tesstests)
+    timeout 200 python -m pytest tests/test_gpu_tesseroid.py -m gpu -q --timeout=90 -p no:cacheprovider -x > gpurun_out/${TAG}_pytest_tess.log 2>&1
+    echo "pytest rc=$?" >> gpurun_out/${TAG}_pytest_tess.log; tail -4 gpurun_out/${TAG}_pytest_tess.log ;;
+tilecmp)
+    for m in ${TILE_MODES:-0 1}; do
+        timeout 120 python bench.py --no-cpu --no-also --no-north-star --steps 3 --tile-mode $m > gpurun_out/${TAG}_bench_tile$m.log 2>&1
+        echo "tile mode $m:"; tail -1 gpurun_out/${TAG}_bench_tile$m.log | cut -c1-200
+        HB200_TILE_MODE=$m SWEEP_ONLY="prism_gravity g_z" timeout 60 python profiles/field_sweep.py > gpurun_out/${TAG}_sweep_tile$m.jsonl 2>&1
+        HB200_TILE_MODE=$m SWEEP_ONLY="fused" timeout 60 python profiles/field_sweep.py >> gpurun_out/${TAG}_sweep_tile$m.jsonl 2>&1
+        cut -c1-160 gpurun_out/${TAG}_sweep_tile$m.jsonl
+    done ;;
 benchref)
     timeout 200 python bench.py --impl reference --steps 3 --warmup 1 --cpu-seconds 4 > gpurun_out/${TAG}_bench_reference.log 2>&1
     echo "benchref rc=$?"; tail -1 gpurun_out/${TAG}_bench_reference.log | cut -c1-200 ;;
@@ -63,12 +74,12 @@ hb.prism_magnetic(wl['coords'],s['prisms'],s['magnetization'],'b',disable_checks
 ncu_pot)
     ncu_case pot 'prism_kernel' "
 from _common import config1
-c,p,d=config1(100000,37888,seed=1)
+c,p,d=config1(20000,37888,seed=1)
 hb.prism_gravity(c,p,d,'potential',disable_checks=True)" ;;
 ncu_acc3)
     ncu_case acc3 'prism_kernel' "
 from _common import config1
-c,p,d=config1(100000,37888,seed=1)
+c,p,d=config1(20000,37888,seed=1)
 hb.prism_gravity(c,p,d,('g_e','g_n','g_z'),disable_checks=True)" ;;
 ncu_eqs)
     ncu_case eqs 'point_kernel_cart' "
@@ -76,9 +87,16 @@ wl=bench.make_workload('eqs',151552,1000000)
 s=wl['sources']
 hb.eqs_predict(wl['coords'],s['points'],s['coefs'])" ;;
 ncu_tess)
-    ncu_case tess 'tesseroid_' "
+    timeout 200 ncu --set full --clock-control none --import-source on -k "regex:tesseroid_(root|walk|deferred)" -c 2 -f \
+        -o gpurun_out/${TAG}_prof_tess python -c "
+import sys; sys.path[:0]=['.','tests']
+import numpy as np, bench, harmonica_b200 as hb
+hb.init([0])
+hb._lib.load().hb200_set_tesseroid_variant(int('${TESS_VARIANT:-6}'))
 wl=bench.make_workload('tess_gz',65536)
-hb.tesseroid_gravity(wl['coords'],wl['tesseroids'],wl['density'],'g_z',disable_checks=True)" ;;
+hb.tesseroid_gravity(wl['coords'],wl['tesseroids'],wl['density'],'g_z',disable_checks=True)
+" > gpurun_out/${TAG}_ncu_tess.log 2>&1
+    echo "ncu tess rc=$?" ;;
 benchtess)
     timeout 100 python bench.py --workload tess_gz --steps 3 --warmup 3 --cpu-seconds 4 > gpurun_out/${TAG}_bench_tess_gz.log 2>&1
     echo "benchtess rc=$?"; tail -1 gpurun_out/${TAG}_bench_tess_gz.log | cut -c1-200 ;;

@@ -18,6 +18,34 @@ from _common import TENSOR_FIELDS, TOL, config1, max_rel
 pytestmark = pytest.mark.gpu
 
 
+def test_config2_layer_observers_on_the_surface_all_fields(hb):
+    """SURVEY 8d C2 parity variant at FULL size: the 500 x 500 layer observed ON its surface, at
+    cell centres (on top faces) and at cell corners (on the shared vertical edges of four
+    neighbouring prisms), all ten fields, NaN pattern of the tensor components included."""
+    from _common import GRAVITY_FIELDS, layer_config2
+
+    coords, east_c, north_c, bottom, top, density = layer_config2()
+    rng = np.random.default_rng(22)
+    half = (east_c[1] - east_c[0]) / 2
+    cells = rng.permutation(500 * 500)
+    k, j = np.divmod(cells, 500)
+    ok = np.isfinite(top[k, j]) & (k < 499) & (j < 499)
+    k, j = k[ok][:240], j[ok][:240]
+    centres = (east_c[j[:120]], north_c[k[:120]], top[k[:120], j[:120]])
+    corners = (east_c[j[120:]] + half, north_c[k[120:]] + half, top[k[120:], j[120:]])
+    obs = tuple(np.concatenate([a, b]) for a, b in zip(centres, corners))
+    nan_seen = False
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for f in GRAVITY_FIELDS:
+            got = hb.prism_layer_gravity(obs, east_c, north_c, bottom, top, density, f)
+            want = O.prism_layer_gravity(obs, east_c, north_c, bottom, top, density, f)
+            assert max_rel(got, want) <= TOL, f  # compares the NaN patterns as well
+            nan_seen |= bool(np.isnan(want).any())
+            assert np.isfinite(want[:120]).all(), f  # face centres are never singular
+    assert nan_seen  # corners sit on vertical edges: g_ee / g_nn / g_en are NaN there
+
+
 def test_config3_full_tensor_1m_x_1m(hb):
     """prism_gravity, six tensor components fused, 1M prisms x 1M observers"""
     coords, prisms, density = config1(1_000_000, 1_000_000, seed=3, scale=10.0)

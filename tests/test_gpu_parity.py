@@ -228,13 +228,15 @@ def test_layer_vs_oracle_and_flat(hb, variant):
     flat = hb.prism_gravity(sub, prisms[keep], rho[keep], "g_z")
     npt.assert_allclose(quiet(layer.gravity, sub, "g_z"), flat, rtol=1e-9)
     # observers ON the surface: cell centres (top faces) and cell corners (shared vertical edges)
-    e0, n0 = east_c[10], north_c[12]
-    surf = (np.array([e0, e0 + 100.0]), np.array([n0, n0 + 100.0]), np.array([top[12, 10], top[12, 10]]))
-    if np.isfinite(surf[2]).all():
-        for f in ("g_z", "potential", "g_e"):
-            got = quiet(layer.gravity, surf, f)
-            want = O.prism_layer_gravity(surf, east_c, north_c, bottom, top, density, f)
-            assert max_rel(got, want) <= TOL, f
+    ok = np.isfinite(top[:-1, :-1]) & np.isfinite(top[1:, :-1]) & np.isfinite(top[:-1, 1:]) & np.isfinite(top[1:, 1:])
+    kk, jj = np.argwhere(ok)[np.argwhere(ok).shape[0] // 2]  # a cell whose three neighbours exist too
+    e0, n0 = east_c[jj], north_c[kk]
+    surf = (np.array([e0, e0 + 100.0]), np.array([n0, n0 + 100.0]), np.array([top[kk, jj], top[kk, jj]]))
+    assert np.isfinite(surf[2]).all()  # the case must not vanish silently (seed-dependent NaN cells)
+    for f in GRAVITY_FIELDS:
+        got = quiet(layer.gravity, surf, f)
+        want = O.prism_layer_gravity(surf, east_c, north_c, bottom, top, density, f)
+        assert max_rel(got, want) <= TOL, f  # max_rel also compares the NaN patterns
 
 
 # ----------------------------------------------------------------- edge cases
@@ -301,11 +303,43 @@ def test_progressbar_gives_identical_results(hb, medium):
     coords, prisms, density = medium
     a = hb.prism_gravity(coords, prisms[:200], density[:200], "g_z")
     b = hb.prism_gravity(coords, prisms[:200], density[:200], "g_z", progressbar=True)
-    # the reference asserts allclose here too (test/test_prism.py:325-377); the progress bar
-    # splits the observers into chunks, which regroups lanes into warps and source chunks, so
-    # the warp-uniform choice of far-field sequences may differ at rounding level
+    # the reference asserts allclose here too (test/test_prism.py:325-377). The value of a pair
+    # does not depend on the batch (far-field sequences are chosen per lane), but the progress
+    # bar's smaller observer batches split the source list into more chunks (grid.y), i.e. the
+    # partial sums are associated differently
     npt.assert_allclose(a, b, rtol=0, atol=1e-11 * np.max(np.abs(a)))
     npt.assert_array_equal(a, hb.prism_gravity(coords, prisms[:200], density[:200], "g_z"))
+
+
+def test_bit_reproducible_under_any_observer_batching(hb):
+    """With the source chunking pinned (hb200_set_source_chunks) an observer's value is
+    bit-identical whatever batch it is computed in: whole set, progress-bar chunks, a
+    permutation, one observer at a time. (Far-field shortcuts are per-lane decisions; no
+    warp votes.)"""
+    lib = hb._lib.load()
+    coords, prisms, density = config1(3000, 4099, seed=77)
+    # near-field pairs too: some observers just above / next to prisms
+    for t in range(64):
+        coords[0][t] = prisms[t, 1] + 3.0
+        coords[1][t] = 0.5 * (prisms[t, 2] + prisms[t, 3])
+        coords[2][t] = prisms[t, 5] + 0.5
+    try:
+        for n_chunks in (1, 3):
+            hb._lib.check(lib.hb200_set_source_chunks(n_chunks))
+            for field in ("g_z", ("g_ee", "g_nn", "g_zz", "g_en", "g_ez", "g_nz"), "potential"):
+                whole = np.stack(np.atleast_2d(hb.prism_gravity(coords, prisms, density, field)))
+                bar = np.stack(np.atleast_2d(hb.prism_gravity(coords, prisms, density, field, progressbar=True)))
+                npt.assert_array_equal(whole, bar)
+                perm = np.random.default_rng(1).permutation(coords[0].size)
+                shuffled = np.stack(np.atleast_2d(
+                    hb.prism_gravity(tuple(c[perm] for c in coords), prisms, density, field)))
+                npt.assert_array_equal(whole[:, perm], shuffled)
+                for i in (0, 17, 63, 4098):
+                    one = np.stack(np.atleast_2d(
+                        hb.prism_gravity(tuple(c[i:i + 1] for c in coords), prisms, density, field)))
+                    npt.assert_array_equal(whole[:, i:i + 1], one)
+    finally:
+        hb._lib.check(lib.hb200_set_source_chunks(0))
 
 
 def test_few_observers_many_sources_uses_source_chunks(hb, variant):

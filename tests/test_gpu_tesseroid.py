@@ -25,17 +25,16 @@ from test_tesseroid_host import (MEAN_RADIUS, MODES, _cases, _key, _shell, _shel
 pytestmark = pytest.mark.gpu
 
 
-DEFAULT_VARIANT = 2
-
-
-@pytest.fixture(params=[2, 1, 0], ids=["fast", "deferred", "plain"])
+@pytest.fixture(params=[6, 3, 2, 1, 0], ids=["two-kernel", "own-trig", "fast", "deferred", "plain"])
 def tess_variant(request, hb):
-    """the tesseroid kernels: 2 = root records + deferred walks + arithmetic-only far field
-    (default), 1 = without the fast far field, 0 = first build"""
+    """the tesseroid kernels: 6 = root pass and walks as two kernels; 3 = one kernel, root records
+    + deferred walks + arithmetic-only far field + the library's own trig in the walks; 2 = as 3
+    with CUDA's trig; 1 = without the fast far field; 0 = first build"""
     lib = hb._lib.load()
+    default = lib.hb200_get_tesseroid_variant()
     assert lib.hb200_set_tesseroid_variant(request.param) == 0
     yield request.param
-    lib.hb200_set_tesseroid_variant(DEFAULT_VARIANT)
+    lib.hb200_set_tesseroid_variant(default)
 
 
 @pytest.mark.parametrize("field,radial", MODES)
@@ -139,8 +138,7 @@ def test_errors_shapes_and_dtypes(hb):
     before = lib.hb200_launch_count()
     hb.tesseroid_gravity([0, 0, R + 10], tess, 2670.0, "potential")
     assert lib.hb200_launch_count() - before >= 3  # inside scan (pack + scan), pack + kernel
-    assert lib.hb200_get_tesseroid_variant() == DEFAULT_VARIANT
-    assert lib.hb200_set_tesseroid_variant(7) != 0
+    assert lib.hb200_set_tesseroid_variant(99) != 0
 
 
 @pytest.mark.parametrize("field", ["potential", "g_z"])
