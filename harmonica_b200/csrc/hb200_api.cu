@@ -164,8 +164,6 @@ template <int FS> void launch_prism_fs(const PrismArgs& a, dim3 grid, cudaStream
     if (g_variant == 0) prism_kernel<FS, 0><<<grid, kBlock, 0, st>>>(a);
     else if (g_variant == 1) prism_kernel<FS, 1><<<grid, kBlock, 0, st>>>(a);
     else if (g_tile_mode == 0) prism_kernel<FS, 2, false><<<grid, kBlock, 0, st>>>(a);
-    else if (g_tile_mode == 2) prism_kernel<FS, 2, true, 5><<<grid, kBlock, 0, st>>>(a);   // 102 registers
-    else if (g_tile_mode == 3) prism_kernel<FS, 2, false, 5><<<grid, kBlock, 0, st>>>(a);
     else prism_kernel<FS, 2, true><<<grid, kBlock, 0, st>>>(a);
 }
 
@@ -533,14 +531,28 @@ int dipole_magnetic_dev_impl(const double* oe, const double* on, const double* o
 int g_tess_variant = 2;  // 0: first build; 1: root records + deferred walks; 2: 1 + fast far field;
                          // 3: 2 + the library's own sin / cos / acos in the walks (not yet measured)
 
+// chunking of the two-kernel variant (hb200_tess.cuh): short chunks, at most kTessMaxChunks
+int tess_two_kernel_chunks(int64_t n_src, int64_t* chunk_len)
+{
+    int64_t len = kTessChunk;
+    if ((n_src + len - 1) / len > kTessMaxChunks) {
+        len = (n_src + kTessMaxChunks - 1) / kTessMaxChunks;
+        len = (len + kTessTile - 1) / kTessTile * kTessTile;
+    }
+    *chunk_len = len;
+    return (int)std::max<int64_t>(1, (n_src + len - 1) / len);
+}
+
 size_t tesseroid_ws_bytes(int64_t n_obs, int64_t n_src, int sms)
 {
-    // variant 6: [records][root partials + walk sums: 2 chunks n_obs doubles][lists][counts]
+    // two-kernel variant, one observer batch: [records][root partials + walk sums: 2 chunks x
+    // batch doubles][lists: chunks x cap x batch u16][counts + resume offsets: 2 chunks x batch]
     int64_t chunk_len;
-    const int chunks = choose_chunks(n_obs, n_src, kTessRootBlock, sms, &chunk_len);
-    const size_t two_kernel = align_up((size_t)2 * chunks * n_obs * sizeof(double))
-                            + align_up((size_t)chunks * kTessListCap * n_obs * sizeof(int))
-                            + align_up((size_t)2 * chunks * n_obs * sizeof(int));
+    const int chunks = tess_two_kernel_chunks(n_src, &chunk_len);
+    const int64_t batch = std::min<int64_t>(std::max<int64_t>(n_obs, 1), kTessObsBatch);
+    const size_t two_kernel = align_up((size_t)(1 + kTessWalkSlices) * chunks * batch * sizeof(double))
+                            + align_up((size_t)chunks * kTessListCap * batch * sizeof(unsigned short))
+                            + align_up((size_t)2 * chunks * batch * sizeof(int));
     return align_up((size_t)std::max<int64_t>(n_src, 1) * kTessRec * sizeof(double))
          + std::max(partial_bytes_for(n_obs, n_src, 1, kTessBlock, sms), two_kernel) + 256;
 }
@@ -554,7 +566,12 @@ int tesseroid_dev_impl(const double* lon, const double* lat, const double* rad, 
 {
     if (field != F_POT && field != F_U) return fail(HB200_EINVAL, "tesseroids: potential or g_z only");
     Ws ws(wsp, ws_bytes);
-    const int variant = g_tess_variant;
+    int variant = g_tess_variant;
+    if (variant >= 6) {  // 16-bit offsets inside a chunk: absurdly long lists use the one-kernel variant
+        int64_t cl;
+        tess_two_kernel_chunks(n_tess, &cl);
+        if (cl > 65535) variant = 3;
+    }
     double* packed = ws.take((size_t)std::max<int64_t>(n_tess, 1) * kTessRec * sizeof(double));
     if (!packed) return fail(HB200_EINVAL, "workspace too small");
     if (n_obs == 0) return HB200_OK;
@@ -575,41 +592,47 @@ int tesseroid_dev_impl(const double* lon, const double* lat, const double* rad, 
     // tesseroid_gravity.py:222-225: g_z is the downward component in mGal
     const double scale = raw ? 1.0 : (field == F_U ? -1e5 : 1.0);
     if (variant >= 6) {
-        // root pass + walk pass + ordered sum (hb200_tess.cuh)
+        // root pass + walk pass + ordered sum (hb200_tess.cuh), in observer batches
         int64_t chunk_len = 0;
-        const int chunks = choose_chunks(n_obs, n_tess, kTessRootBlock, sms, &chunk_len);
-        double* parts = ws.take((size_t)2 * chunks * n_obs * sizeof(double));
-        int* list = (int*)ws.take((size_t)chunks * kTessListCap * n_obs * sizeof(int));
-        int* count = (int*)ws.take((size_t)2 * chunks * n_obs * sizeof(int));  // counts, resume offsets
+        const int chunks = tess_two_kernel_chunks(n_tess, &chunk_len);
+        const int64_t batch = std::min<int64_t>(n_obs, kTessObsBatch);
+        double* parts = ws.take((size_t)(1 + kTessWalkSlices) * chunks * batch * sizeof(double));
+        unsigned short* list =
+            (unsigned short*)ws.take((size_t)chunks * kTessListCap * batch * sizeof(unsigned short));
+        int* count = (int*)ws.take((size_t)2 * chunks * batch * sizeof(int));  // counts, resume offsets
         if (!parts || !list || !count) return fail(HB200_EINVAL, "workspace too small");
-        TessArgs a;
-        a.lon = lon; a.lat = lat; a.rad = rad; a.n_obs = n_obs;
-        a.packed = packed; a.n_src = n_tess; a.chunk_len = chunk_len;
-        a.out = parts; a.scale = scale;
-        a.ratio = field == F_POT ? 1.0 : 2.5;
-        a.radial = radial; a.flags = d_flags;
-        dim3 grid_r((unsigned)((n_obs + kTessRootBlock - 1) / kTessRootBlock), (unsigned)chunks);
-        dim3 grid_w((unsigned)((n_obs + kTessBlock - 1) / kTessBlock), (unsigned)chunks);
-        double* walk_sum = parts + (size_t)chunks * n_obs;
-        // variants 6 / 7 / 8: the root kernel compiled for 4 / 6 / 8 resident CTAs (128 / 80 / 64 registers)
-        if (field == F_POT) {
-            if (variant == 6) tesseroid_root_kernel<F_POT, 4><<<grid_r, kTessRootBlock, 0, st>>>(a, list, count);
-            else if (variant == 7) tesseroid_root_kernel<F_POT, 6><<<grid_r, kTessRootBlock, 0, st>>>(a, list, count);
-            else tesseroid_root_kernel<F_POT, 8><<<grid_r, kTessRootBlock, 0, st>>>(a, list, count);
-            tesseroid_walk_kernel<F_POT, OwnTrig><<<grid_w, kTessBlock, 0, st>>>(a, list, count, walk_sum);
-        } else {
-            if (variant == 6) tesseroid_root_kernel<F_U, 4><<<grid_r, kTessRootBlock, 0, st>>>(a, list, count);
-            else if (variant == 7) tesseroid_root_kernel<F_U, 6><<<grid_r, kTessRootBlock, 0, st>>>(a, list, count);
-            else tesseroid_root_kernel<F_U, 8><<<grid_r, kTessRootBlock, 0, st>>>(a, list, count);
-            tesseroid_walk_kernel<F_U, OwnTrig><<<grid_w, kTessBlock, 0, st>>>(a, list, count, walk_sum);
+        for (int64_t o0 = 0; o0 < n_obs; o0 += batch) {
+            const int64_t nb = std::min(batch, n_obs - o0);
+            TessArgs a;
+            a.lon = lon + o0; a.lat = lat + o0; a.rad = rad + o0; a.n_obs = nb;
+            a.packed = packed; a.n_src = n_tess; a.chunk_len = chunk_len;
+            a.out = parts; a.scale = scale;
+            a.ratio = field == F_POT ? 1.0 : 2.5;
+            a.radial = radial; a.flags = d_flags;
+            dim3 grid_r((unsigned)((nb + kTessRootBlock - 1) / kTessRootBlock), (unsigned)chunks);
+            dim3 grid_w((unsigned)((nb + kTessBlock - 1) / kTessBlock), (unsigned)chunks, kTessWalkSlices);
+            double* walk_sum = parts + (size_t)chunks * nb;
+            // variants 6 / 7 / 8: the root kernel compiled for 4 / 6 / 8 resident CTAs
+            if (field == F_POT) {
+                if (variant == 6) tesseroid_root_kernel<F_POT, 4><<<grid_r, kTessRootBlock, 0, st>>>(a, list, count);
+                else if (variant == 7) tesseroid_root_kernel<F_POT, 6><<<grid_r, kTessRootBlock, 0, st>>>(a, list, count);
+                else tesseroid_root_kernel<F_POT, 8><<<grid_r, kTessRootBlock, 0, st>>>(a, list, count);
+                tesseroid_walk_kernel<F_POT, OwnTrig><<<grid_w, kTessBlock, 0, st>>>(a, list, count, walk_sum);
+            } else {
+                if (variant == 6) tesseroid_root_kernel<F_U, 4><<<grid_r, kTessRootBlock, 0, st>>>(a, list, count);
+                else if (variant == 7) tesseroid_root_kernel<F_U, 6><<<grid_r, kTessRootBlock, 0, st>>>(a, list, count);
+                else tesseroid_root_kernel<F_U, 8><<<grid_r, kTessRootBlock, 0, st>>>(a, list, count);
+                tesseroid_walk_kernel<F_U, OwnTrig><<<grid_w, kTessBlock, 0, st>>>(a, list, count, walk_sum);
+            }
+            CU(cudaGetLastError());
+            Scales sc;
+            sc.s[0] = scale;
+            reduce_partials_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(
+                parts, (1 + kTessWalkSlices) * chunks, 1, nb, sc, out + o0);
+            CU(cudaGetLastError());
+            g_launches += 3;
         }
-        CU(cudaGetLastError());
-        Scales sc;
-        sc.s[0] = scale;
-        reduce_partials_kernel<<<(unsigned)((n_obs + 255) / 256), 256, 0, st>>>(parts, 2 * chunks, 1,
-                                                                               n_obs, sc, out);
-        CU(cudaGetLastError());
-        g_launches += 4;
+        g_launches += 1;  // the pack kernel
         return HB200_OK;
     }
     double* partial = (double*)(ws.base + ws.used);
@@ -925,7 +948,7 @@ int hb200_set_tesseroid_variant(int variant)
 int hb200_get_tesseroid_variant(void) { return g_tess_variant; }
 int hb200_set_tile_mode(int mode)
 {
-    if (mode < 0 || mode > 3) return fail(HB200_EINVAL, "tile mode must be 0 (per CTA) or 1 (per warp)");
+    if (mode != 0 && mode != 1) return fail(HB200_EINVAL, "tile mode must be 0 (per CTA) or 1 (per warp)");
     g_tile_mode = mode;
     return HB200_OK;
 }

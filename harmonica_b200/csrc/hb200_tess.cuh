@@ -642,12 +642,34 @@ __global__ void __launch_bounds__(kTessBlock, MINB) tesseroid_deferred_kernel(co
 // included). Nothing is skipped and nothing is counted twice.
 constexpr int kTessRootBlock = 128;
 constexpr int kTessListCap = 64;
+// Chunks of the tesseroid list are SHORT (128 tesseroids while the list has <= 32768 of them):
+// the walks of one observer are then spread over n / 128 threads of the walk kernel, which is
+// what bounds its tail (an observer next to a pole has hundreds of near tesseroids, all others
+// ~20; with 32 long chunks the walk kernel kept the SMs busy 40 % of its run time, profiles/).
+// Offsets inside a chunk fit 16 bits.
+constexpr int kTessChunk = 128;
+constexpr int kTessMaxChunks = 256;
+constexpr int kTessObsBatch = 32768;  // observers per pass: bounds the list workspace (~0.6 GB)
 
+// TMA bulk copy + mbarrier helpers (defined in hb200_kernels.cuh, included first by hb200_api.cu)
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count);
+__device__ __forceinline__ void mbar_fence_init();
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, uint64_t* bar);
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity);
+
+constexpr int kTessWarpTile = 16;  // root records per bulk copy (4 KB), two buffers per warp
+constexpr int kTessWalkSlices = 4; // threads that share the walks of one (chunk, observer) list
+
+// Every warp streams its own copy of the chunk's root records (TMA bulk copies, two buffers, one
+// mbarrier each) and synchronises only with itself, like prism_kernel.
 template <int FIELD, int MINB>
-__global__ void __launch_bounds__(kTessRootBlock, MINB) tesseroid_root_kernel(const TessArgs a, int* list,
-                                                                               int* count)
+__global__ void __launch_bounds__(kTessRootBlock, MINB) tesseroid_root_kernel(const TessArgs a,
+                                                                               unsigned short* list, int* count)
 {
-    __shared__ double tile[kTessTile * kTessRec];
+    constexpr int WARPS = kTessRootBlock / 32;
+    __shared__ alignas(128) double tiles[WARPS][2][kTessWarpTile * kTessRec];
+    __shared__ alignas(8) uint64_t bars[WARPS][2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t i = (int64_t)blockIdx.x * kTessRootBlock + threadIdx.x;
     const bool live = i < a.n_obs;
     const int64_t ic = live ? i : a.n_obs - 1;
@@ -660,19 +682,37 @@ __global__ void __launch_bounds__(kTessRootBlock, MINB) tesseroid_root_kernel(co
     const int64_t end = begin + a.chunk_len < a.n_src ? begin + a.chunk_len : a.n_src;
     int resume = (int)(end - begin);  // offset from which the walk kernel takes over (none)
     bool open = live;
-    int* my_list = list + ((int64_t)blockIdx.y * kTessListCap) * a.n_obs + ic;  // [chunk][k][obs]
-    for (int64_t t0 = begin; t0 < end; t0 += kTessTile) {
-        const int cnt = (int)((end - t0) < kTessTile ? (end - t0) : kTessTile);
-        __syncthreads();
-        for (int x = threadIdx.x; x < cnt * kTessRec; x += kTessRootBlock)
-            tile[x] = a.packed[t0 * kTessRec + x];
-        __syncthreads();
+    unsigned short* my_list = list + ((int64_t)blockIdx.y * kTessListCap) * a.n_obs + ic;  // [chunk][k][obs]
+    if (lane == 0) {
+        mbar_init(&bars[warp][0], 1);
+        mbar_init(&bars[warp][1], 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    if (lane == 0 && begin < end) {
+        const int cnt0 = (int)((end - begin) < kTessWarpTile ? (end - begin) : kTessWarpTile);
+        bulk_load(tiles[warp][0], a.packed + begin * kTessRec, (unsigned)(cnt0 * kTessRec * sizeof(double)),
+                  &bars[warp][0]);
+    }
+    unsigned phase0 = 0, phase1 = 0;
+    int buf = 0;
+    for (int64_t t0 = begin; t0 < end; t0 += kTessWarpTile, buf ^= 1) {
+        const int cnt = (int)((end - t0) < kTessWarpTile ? (end - t0) : kTessWarpTile);
+        const int64_t t1 = t0 + kTessWarpTile;
+        if (lane == 0 && t1 < end) {
+            const int cnt1 = (int)((end - t1) < kTessWarpTile ? (end - t1) : kTessWarpTile);
+            bulk_load(tiles[warp][buf ^ 1], a.packed + t1 * kTessRec,
+                      (unsigned)(cnt1 * kTessRec * sizeof(double)), &bars[warp][buf ^ 1]);
+        }
+        if (buf == 0) { mbar_wait(&bars[warp][0], phase0); phase0 ^= 1; }
+        else { mbar_wait(&bars[warp][1], phase1); phase1 ^= 1; }
+        const double* tile = tiles[warp][buf];
         for (int s = 0; s < cnt; s++) {
             if (!open) continue;
             const int root = tess_root_fast<FIELD>(o, tile + s * kTessRec, acc, flags);
             if (root == 0) {
                 if (n_split < kTessListCap) {
-                    my_list[(int64_t)n_split * a.n_obs] = (int)(t0 - begin) + s;
+                    my_list[(int64_t)n_split * a.n_obs] = (unsigned short)((int)(t0 - begin) + s);
                     n_split++;
                 } else {  // list full: this pair and the rest of the chunk go to the walk kernel
                     resume = (int)(t0 - begin) + s;
@@ -680,6 +720,7 @@ __global__ void __launch_bounds__(kTessRootBlock, MINB) tesseroid_root_kernel(co
                 }
             }
         }
+        __syncwarp();  // the buffer just read may be refilled in the next iteration
     }
     if (live) {
         a.out[(int64_t)blockIdx.y * a.n_obs + i] = acc;  // always partial: [chunk][obs]
@@ -689,36 +730,45 @@ __global__ void __launch_bounds__(kTessRootBlock, MINB) tesseroid_root_kernel(co
     if (flags && a.flags) atomicOr(a.flags, flags);
 }
 
+// grid = (observer blocks, chunks, kTessWalkSlices): slice z of a (chunk, observer) list takes
+// every kTessWalkSlices-th listed pair and every kTessWalkSlices-th pair of the remainder, so
+// the few heavy observers (next to a pole) are shared by more threads. walk_sum is
+// [chunk][slice][obs]; the final reduce adds the slices in fixed order.
 template <int FIELD, class TRIG>
-__global__ void __launch_bounds__(kTessBlock) tesseroid_walk_kernel(const TessArgs a, const int* list,
+__global__ void __launch_bounds__(kTessBlock) tesseroid_walk_kernel(const TessArgs a,
+                                                                    const unsigned short* list,
                                                                     const int* count, double* walk_sum)
 {
     double stack[kTessStack * 6];
     const int64_t i = (int64_t)blockIdx.x * kTessBlock + threadIdx.x;
     if (i >= a.n_obs) return;
     const int n = count[(int64_t)blockIdx.y * a.n_obs + i];
-    int resume = count[((int64_t)gridDim.y + blockIdx.y) * a.n_obs + i];
-    const int64_t chunk_begin = (int64_t)blockIdx.y * a.chunk_len;
-    const int chunk_cnt = (int)((chunk_begin + a.chunk_len < a.n_src ? chunk_begin + a.chunk_len : a.n_src)
-                                - chunk_begin);
+    int resume = count[((int64_t)gridDim.y + blockIdx.y) * a.n_obs + i] + (int)blockIdx.z;
+    const int64_t begin = (int64_t)blockIdx.y * a.chunk_len;
+    const int chunk_cnt = (int)((begin + a.chunk_len < a.n_src ? begin + a.chunk_len : a.n_src) - begin);
+    int k = (int)blockIdx.z;
     double acc = 0.0;
-    if (n > 0 || resume < chunk_cnt) {
+    if (k < n || resume < chunk_cnt) {
         TessObs o;
         tess_make_obs(o, a.lon[i], a.lat[i], a.rad[i]);
         unsigned flags = 0;
-        const int64_t begin = (int64_t)blockIdx.y * a.chunk_len;
-        const int* my_list = list + ((int64_t)blockIdx.y * kTessListCap) * a.n_obs + i;
+        const unsigned short* my_list = list + ((int64_t)blockIdx.y * kTessListCap) * a.n_obs + i;
         TessWalk wk;
         wk.stack_top = -1;
         wk.n_leaves = 0;
         wk.density[0] = wk.density[1] = 0.0;
-        int k = 0;
         while (true) {  // one pop per trip, whatever the shapes of the lanes' trees
             if (wk.stack_top < 0) {
                 int off;
-                if (k < n) off = my_list[(int64_t)(k++) * a.n_obs];  // the listed pairs ...
-                else if (resume < chunk_cnt) off = resume++;         // ... then the rest of the chunk
-                else break;
+                if (k < n) {  // the listed pairs of this slice ...
+                    off = my_list[(int64_t)k * a.n_obs];
+                    k += kTessWalkSlices;
+                } else if (resume < chunk_cnt) {  // ... then its share of the rest of the chunk
+                    off = resume;
+                    resume += kTessWalkSlices;
+                } else {
+                    break;
+                }
                 const double* rec = a.packed + (begin + off) * kTessRec;
                 if (rec[29] != 0.0) {  // a zero dimension: numba's ZeroDivisionError (tess_root_fast)
                     flags |= FLAG_ZERO_DIV;
@@ -731,7 +781,7 @@ __global__ void __launch_bounds__(kTessBlock) tesseroid_walk_kernel(const TessAr
         }
         if (flags && a.flags) atomicOr(a.flags, flags);
     }
-    walk_sum[(int64_t)blockIdx.y * a.n_obs + i] = acc;
+    walk_sum[((int64_t)blockIdx.y * kTessWalkSlices + blockIdx.z) * a.n_obs + i] = acc;
 }
 
 // check_points_outside_tesseroids as one pass: sets FLAG_TESS_INSIDE if any pair conflicts

@@ -6,12 +6,14 @@ import collections
 import csv
 import io
 import subprocess
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.abspath(__file__)))
+import _ncu_pages  # noqa: E402
 import sys
 
 rep, pairs = sys.argv[1], float(sys.argv[2])
 top_n = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"],
-                     capture_output=True, text=True).stdout
+raw = _ncu_pages.page(rep, "srcsass")
 FP64 = ("DFMA", "DMUL", "DADD", "DSETP", "DMNMX")
 lines = collections.defaultdict(lambda: [0, 0, collections.Counter(), ""])
 cur_file, cur_line, cur_text = "", "", ""

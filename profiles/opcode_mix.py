@@ -5,10 +5,13 @@ import collections
 import csv
 import io
 import subprocess
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.abspath(__file__)))
+import _ncu_pages  # noqa: E402
 import sys
 
 rep, pairs = sys.argv[1], float(sys.argv[2])
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+raw = _ncu_pages.page(rep, "source")
 rows = list(csv.reader(io.StringIO(raw)))
 hdr = rows[1]
 iS, iE = hdr.index("Source"), hdr.index("Instructions Executed")

@@ -4,6 +4,9 @@
 import csv
 import io
 import subprocess
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.abspath(__file__)))
+import _ncu_pages  # noqa: E402
 import sys
 
 KEYS = [
@@ -38,8 +41,7 @@ KEYS = [
 def main():
     rep = sys.argv[1]
     pairs = float(sys.argv[2]) if len(sys.argv) > 2 else None
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True,
-                         text=True).stdout
+    raw = _ncu_pages.page(rep, "raw")
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     for vals in rows[2:]:

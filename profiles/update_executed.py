@@ -14,6 +14,9 @@ import io
 import json
 import os
 import subprocess
+import os as _os, sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.abspath(__file__)))
+import _ncu_pages  # noqa: E402
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -27,7 +30,7 @@ FILES = {"layer_gz": PRISM_FILES, "c1_gz": PRISM_FILES, "tensor": PRISM_FILES, "
 
 workload, rep, pairs, source = sys.argv[1], sys.argv[2], float(sys.argv[3]), sys.argv[4]
 dram = int(sys.argv[5]) if len(sys.argv) > 5 else None
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+raw = _ncu_pages.page(rep, "source")
 rows = list(csv.reader(io.StringIO(raw)))
 hdr = rows[1]
 iS, iE = hdr.index("Source"), hdr.index("Instructions Executed")

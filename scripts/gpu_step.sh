@@ -5,6 +5,12 @@
 TAG=$1; shift
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader > gpurun_out/${TAG}_gpu.txt 2>&1
+export_pages() {  # base (without .ncu-rep): CSV pages stay, the 20-40 MB report does not travel
+    ncu -i $1.ncu-rep --page raw --csv > $1.raw.csv 2>/dev/null
+    ncu -i $1.ncu-rep --page source --csv 2>/dev/null | gzip > $1.source.csv.gz
+    ncu -i $1.ncu-rep --page source --csv --print-source cuda,sass 2>/dev/null | gzip > $1.srcsass.csv.gz
+    [ -n "$KEEP_REP" ] || rm -f $1.ncu-rep
+}
 ncu_case() {  # name kernel-regex python-snippet
     timeout 150 ncu --set full --clock-control none --import-source on -k "regex:$2" -c 1 -f \
         -o gpurun_out/${TAG}_prof_$1 python -c "
@@ -14,6 +20,7 @@ hb.init([0])
 $3
 " > gpurun_out/${TAG}_ncu_$1.log 2>&1
     echo "ncu $1 rc=$?"
+    export_pages gpurun_out/${TAG}_prof_$1
 }
 for what in "$@"; do
 case $what in
@@ -96,7 +103,8 @@ hb._lib.load().hb200_set_tesseroid_variant(int('${TESS_VARIANT:-6}'))
 wl=bench.make_workload('tess_gz',65536)
 hb.tesseroid_gravity(wl['coords'],wl['tesseroids'],wl['density'],'g_z',disable_checks=True)
 " > gpurun_out/${TAG}_ncu_tess.log 2>&1
-    echo "ncu tess rc=$?" ;;
+    echo "ncu tess rc=$?"
+    export_pages gpurun_out/${TAG}_prof_tess ;;
 benchtess)
     timeout 100 python bench.py --workload tess_gz --steps 3 --warmup 3 --cpu-seconds 4 > gpurun_out/${TAG}_bench_tess_gz.log 2>&1
     echo "benchtess rc=$?"; tail -1 gpurun_out/${TAG}_bench_tess_gz.log | cut -c1-200 ;;

@@ -217,3 +217,40 @@ def test_density_function_rules(hb):
                             hb.tesseroid_gravity(grid, tesseroid, 2900.0, field))  # fmt: skip
     with pytest.raises(NotImplementedError, match="radial_adaptive_discretization"):
         hb.tesseroid_gravity(grid, tesseroid, lambda radius: 2900.0, "g_z", radial_adaptive_discretization=True)
+
+
+@pytest.mark.parametrize("variant", [6, 3])
+def test_polar_observers_fill_the_split_lists(hb, variant):
+    """Next to a pole EVERY tesseroid of the nearest latitude rings is near (hundreds of split
+    roots for one observer, against ~20 elsewhere): in the two-kernel variant the per-chunk lists
+    of split pairs overflow and the walk kernel takes over the rest of the chunk; more than
+    32 768 observers are processed in several batches. Against the oracle."""
+    lib = hb._lib.load()
+    R = MEAN_RADIUS
+    lon_c, lat_c = np.meshgrid(np.arange(-179.0, 180.0, 2.0), np.arange(-89.0, 90.0, 2.0))
+    tess = np.stack([lon_c.ravel() - 1, lon_c.ravel() + 1, lat_c.ravel() - 1, lat_c.ravel() + 1,
+                     np.full(lon_c.size, R - 30e3), np.full(lon_c.size, R - 1e3)], axis=1)
+    rng = np.random.default_rng(12)
+    density = rng.uniform(2500, 3300, lon_c.size)
+    lon = np.array([0.0, 33.0, -120.0, 77.7, 10.0, -45.0, 179.0, 5.0])
+    lat = np.array([89.9, 89.0, -89.5, 88.0, -87.0, 0.0, 45.0, 90.0])
+    coords = (lon, lat, np.full(lon.size, R + 10e3))
+    default = lib.hb200_get_tesseroid_variant()
+    try:
+        assert lib.hb200_set_tesseroid_variant(variant) == 0
+        for field in ("g_z", "potential"):
+            want = O.tesseroid_gravity(coords, tess, density, field)
+            got = hb.tesseroid_gravity(coords, tess, density, field, disable_checks=True)
+            assert max_rel(got, want) <= 2e-8, field
+        # several observer batches, polar observers in the last one
+        n = 40_000
+        many = (np.concatenate([rng.uniform(-180, 180, n), lon]),
+                np.concatenate([rng.uniform(-60, 60, n), lat]), np.full(n + lon.size, R + 10e3))
+        got = hb.tesseroid_gravity(many, tess, density, "g_z", disable_checks=True)
+        want = O.tesseroid_gravity(coords, tess, density, "g_z")
+        assert max_rel(got[n:], want) <= 2e-8
+        idx = np.arange(0, n, 1600)
+        sub = tuple(c[idx] for c in many)
+        assert max_rel(got[idx], O.tesseroid_gravity(sub, tess, density, "g_z")) <= 2e-8
+    finally:
+        lib.hb200_set_tesseroid_variant(default)
