@@ -528,8 +528,10 @@ int dipole_magnetic_dev_impl(const double* oe, const double* on, const double* o
 }
 
 // tesseroid_gravity: one field per pass (potential or g_z); workspace = [packed][partials]
-int g_tess_variant = 2;  // 0: first build; 1: root records + deferred walks; 2: 1 + fast far field;
-                         // 3: 2 + the library's own sin / cos / acos in the walks (not yet measured)
+int g_tess_variant = 9;  // 0: first build; 1: root records + deferred walks; 2: 1 + fast far field;
+                         // 3: 2 + the library's own sin / cos / acos in the walks; 4, 5: register
+                         // experiments; 6 (7, 8): root pass and walks as two kernels; 9: as 6 with the
+                         // walks done by groups of 8 lanes from a work list (default)
 
 // chunking of the two-kernel variant (hb200_tess.cuh): short chunks, at most kTessMaxChunks
 int tess_two_kernel_chunks(int64_t n_src, int64_t* chunk_len)
@@ -552,7 +554,9 @@ size_t tesseroid_ws_bytes(int64_t n_obs, int64_t n_src, int sms)
     const int64_t batch = std::min<int64_t>(std::max<int64_t>(n_obs, 1), kTessObsBatch);
     const size_t two_kernel = align_up((size_t)(1 + kTessWalkSlices) * chunks * batch * sizeof(double))
                             + align_up((size_t)chunks * kTessListCap * batch * sizeof(unsigned short))
-                            + align_up((size_t)2 * chunks * batch * sizeof(int));
+                            + align_up((size_t)2 * chunks * batch * sizeof(int))
+                            // work list and redo list of the cooperative walks, their counters
+                            + 2 * align_up((size_t)chunks * batch * sizeof(int)) + align_up(4 * sizeof(int));
     return align_up((size_t)std::max<int64_t>(n_src, 1) * kTessRec * sizeof(double))
          + std::max(partial_bytes_for(n_obs, n_src, 1, kTessBlock, sms), two_kernel) + 256;
 }
@@ -600,7 +604,11 @@ int tesseroid_dev_impl(const double* lon, const double* lat, const double* rad, 
         unsigned short* list =
             (unsigned short*)ws.take((size_t)chunks * kTessListCap * batch * sizeof(unsigned short));
         int* count = (int*)ws.take((size_t)2 * chunks * batch * sizeof(int));  // counts, resume offsets
-        if (!parts || !list || !count) return fail(HB200_EINVAL, "workspace too small");
+        int* items = (int*)ws.take((size_t)chunks * batch * sizeof(int));
+        int* redo_items = (int*)ws.take((size_t)chunks * batch * sizeof(int));
+        int* counters = (int*)ws.take(4 * sizeof(int));
+        if (!parts || !list || !count || !items || !redo_items || !counters)
+            return fail(HB200_EINVAL, "workspace too small");
         for (int64_t o0 = 0; o0 < n_obs; o0 += batch) {
             const int64_t nb = std::min(batch, n_obs - o0);
             TessArgs a;
@@ -610,27 +618,47 @@ int tesseroid_dev_impl(const double* lon, const double* lat, const double* rad, 
             a.ratio = field == F_POT ? 1.0 : 2.5;
             a.radial = radial; a.flags = d_flags;
             dim3 grid_r((unsigned)((nb + kTessRootBlock - 1) / kTessRootBlock), (unsigned)chunks);
+            const bool coop = variant >= 9;  // walks by groups of 8 lanes (tesseroid_coop_walk_kernel)
+            const int slices = coop ? 1 : kTessWalkSlices;
             dim3 grid_w((unsigned)((nb + kTessBlock - 1) / kTessBlock), (unsigned)chunks, kTessWalkSlices);
+            const unsigned grid_c = (unsigned)(sms * kCoopCtasPerSm);  // persistent: one CTA per slot
             double* walk_sum = parts + (size_t)chunks * nb;
+            if (coop) {  // only the lists on the work list are written
+                CU(cudaMemsetAsync(counters, 0, 4 * sizeof(int), st));
+                CU(cudaMemsetAsync(walk_sum, 0, (size_t)chunks * nb * sizeof(double), st));
+            }
+            int* items_arg = coop ? items : nullptr;
             // variants 6 / 7 / 8: the root kernel compiled for 4 / 6 / 8 resident CTAs
             if (field == F_POT) {
-                if (variant == 6) tesseroid_root_kernel<F_POT, 4><<<grid_r, kTessRootBlock, 0, st>>>(a, list, count);
-                else if (variant == 7) tesseroid_root_kernel<F_POT, 6><<<grid_r, kTessRootBlock, 0, st>>>(a, list, count);
-                else tesseroid_root_kernel<F_POT, 8><<<grid_r, kTessRootBlock, 0, st>>>(a, list, count);
-                tesseroid_walk_kernel<F_POT, OwnTrig><<<grid_w, kTessBlock, 0, st>>>(a, list, count, walk_sum);
+                if (variant == 7) tesseroid_root_kernel<F_POT, 6><<<grid_r, kTessRootBlock, 0, st>>>(a, list, count, items_arg, counters);
+                else if (variant == 8) tesseroid_root_kernel<F_POT, 8><<<grid_r, kTessRootBlock, 0, st>>>(a, list, count, items_arg, counters);
+                else tesseroid_root_kernel<F_POT, 4><<<grid_r, kTessRootBlock, 0, st>>>(a, list, count, items_arg, counters);
+                if (coop) {
+                    tesseroid_coop_walk_kernel<F_POT, OwnTrig><<<grid_c, kCoopBlock, 0, st>>>(
+                        a, chunks, list, count, items, counters, redo_items, walk_sum);
+                    tesseroid_redo_kernel<F_POT, OwnTrig><<<(unsigned)sms, kTessBlock, 0, st>>>(
+                        a, chunks, list, count, counters, redo_items, walk_sum);
+                }
+                else tesseroid_walk_kernel<F_POT, OwnTrig><<<grid_w, kTessBlock, 0, st>>>(a, list, count, walk_sum);
             } else {
-                if (variant == 6) tesseroid_root_kernel<F_U, 4><<<grid_r, kTessRootBlock, 0, st>>>(a, list, count);
-                else if (variant == 7) tesseroid_root_kernel<F_U, 6><<<grid_r, kTessRootBlock, 0, st>>>(a, list, count);
-                else tesseroid_root_kernel<F_U, 8><<<grid_r, kTessRootBlock, 0, st>>>(a, list, count);
-                tesseroid_walk_kernel<F_U, OwnTrig><<<grid_w, kTessBlock, 0, st>>>(a, list, count, walk_sum);
+                if (variant == 7) tesseroid_root_kernel<F_U, 6><<<grid_r, kTessRootBlock, 0, st>>>(a, list, count, items_arg, counters);
+                else if (variant == 8) tesseroid_root_kernel<F_U, 8><<<grid_r, kTessRootBlock, 0, st>>>(a, list, count, items_arg, counters);
+                else tesseroid_root_kernel<F_U, 4><<<grid_r, kTessRootBlock, 0, st>>>(a, list, count, items_arg, counters);
+                if (coop) {
+                    tesseroid_coop_walk_kernel<F_U, OwnTrig><<<grid_c, kCoopBlock, 0, st>>>(
+                        a, chunks, list, count, items, counters, redo_items, walk_sum);
+                    tesseroid_redo_kernel<F_U, OwnTrig><<<(unsigned)sms, kTessBlock, 0, st>>>(
+                        a, chunks, list, count, counters, redo_items, walk_sum);
+                }
+                else tesseroid_walk_kernel<F_U, OwnTrig><<<grid_w, kTessBlock, 0, st>>>(a, list, count, walk_sum);
             }
             CU(cudaGetLastError());
             Scales sc;
             sc.s[0] = scale;
             reduce_partials_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(
-                parts, (1 + kTessWalkSlices) * chunks, 1, nb, sc, out + o0);
+                parts, (1 + slices) * chunks, 1, nb, sc, out + o0);
             CU(cudaGetLastError());
-            g_launches += 3;
+            g_launches += coop ? 4 : 3;
         }
         g_launches += 1;  // the pack kernel
         return HB200_OK;
@@ -941,7 +969,7 @@ int hb200_set_variant(int variant)
 int hb200_get_variant(void) { return g_variant; }
 int hb200_set_tesseroid_variant(int variant)
 {
-    if (variant < 0 || variant > 8) return fail(HB200_EINVAL, "tesseroid variant must be 0 .. 8");
+    if (variant < 0 || variant > 9) return fail(HB200_EINVAL, "tesseroid variant must be 0 .. 9");
     g_tess_variant = variant;
     return HB200_OK;
 }

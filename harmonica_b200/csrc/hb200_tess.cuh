@@ -218,6 +218,20 @@ HB_HD double tess_glq_nodes(const TessObs& o, const TessNodes& q, unsigned& flag
     return result;
 }
 
+// The decision of one pop of _adaptive_discretization (:178-191): dimensions, distance to the
+// centre, split counts. Returns false where numba raises ZeroDivisionError.
+template <class TRIG = LibmTrig>
+HB_HD bool tess_classify(const TessObs& o, double ratio, bool radial, double w, double e, double s,
+                         double n, double bottom, double top, int& n_lon, int& n_lat, int& n_rad)
+{
+    TessDims dims;
+    tess_dims<TRIG>(dims, w, e, s, n, bottom, top);
+    TessCentre centre;
+    tess_centre<TRIG>(centre, w, e, s, n, bottom, top);
+    const double distance = tess_distance<TRIG>(o, centre);
+    return tess_split_counts(distance, dims, ratio, radial, n_lon, n_lat, n_rad);
+}
+
 // ---- the walk over the adaptive discretisation of one pair --------------------------------------
 struct TessWalk {
     int stack_top;   // < 0: no pair in progress
@@ -248,13 +262,8 @@ HB_HD void tess_walk_step(const TessObs& o, double ratio, bool radial, double* s
     const double* q = stack + 6 * wk.stack_top;
     const double w = q[0], e = q[1], s = q[2], n = q[3], bottom = q[4], top = q[5];
     wk.stack_top -= 1;
-    TessDims dims;
-    tess_dims<TRIG>(dims, w, e, s, n, bottom, top);
-    TessCentre centre;
-    tess_centre<TRIG>(centre, w, e, s, n, bottom, top);
-    const double distance = tess_distance<TRIG>(o, centre);
     int n_lon, n_lat, n_rad;
-    if (!tess_split_counts(distance, dims, ratio, radial, n_lon, n_lat, n_rad)) {
+    if (!tess_classify<TRIG>(o, ratio, radial, w, e, s, n, bottom, top, n_lon, n_lat, n_rad)) {
         flags |= FLAG_ZERO_DIV;
         wk.stack_top = -1;
         return;
@@ -664,7 +673,9 @@ constexpr int kTessWalkSlices = 4; // threads that share the walks of one (chunk
 // mbarrier each) and synchronises only with itself, like prism_kernel.
 template <int FIELD, int MINB>
 __global__ void __launch_bounds__(kTessRootBlock, MINB) tesseroid_root_kernel(const TessArgs a,
-                                                                               unsigned short* list, int* count)
+                                                                               unsigned short* list, int* count,
+                                                                               int* items = nullptr,
+                                                                               int* n_items = nullptr)
 {
     constexpr int WARPS = kTessRootBlock / 32;
     __shared__ alignas(128) double tiles[WARPS][2][kTessWarpTile * kTessRec];
@@ -727,7 +738,57 @@ __global__ void __launch_bounds__(kTessRootBlock, MINB) tesseroid_root_kernel(co
         count[(int64_t)blockIdx.y * a.n_obs + i] = n_split;
         count[((int64_t)gridDim.y + blockIdx.y) * a.n_obs + i] = resume;
     }
+    if (items) {
+        // the (chunk, observer) lists that hold work, compacted for tesseroid_coop_walk_kernel:
+        // one atomic per warp; the order of the items has no influence on any result
+        const bool has = live && (n_split > 0 || resume < (int)(end - begin));
+        const unsigned m = __ballot_sync(0xffffffffu, has);
+        if (m) {
+            const int leader = __ffs(m) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(n_items, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (has) items[base + __popc(m & ((1u << lane) - 1u))] = (int)blockIdx.y * kTessObsBatch + (int)i;
+        }
+    }
     if (flags && a.flags) atomicOr(a.flags, flags);
+}
+
+// The listed pairs k, k + stride, ... of one (chunk, observer) list and then the pairs resume,
+// resume + stride, ... of the rest of the chunk, each walked depth-first with the caller's private
+// stack exactly like the reference does (one pop per trip of a single loop).
+template <int FIELD, class TRIG>
+__device__ __forceinline__ void tess_walk_list_exact(const TessArgs& a, const TessObs& o,
+                                                     const unsigned short* my_list, int n, int k, int resume,
+                                                     int chunk_cnt, int64_t begin, int stride, double* stack,
+                                                     double& acc, unsigned& flags)
+{
+    TessWalk wk;
+    wk.stack_top = -1;
+    wk.n_leaves = 0;
+    wk.density[0] = wk.density[1] = 0.0;
+    while (true) {  // one pop per trip, whatever the shapes of the lanes' trees
+        if (wk.stack_top < 0) {
+            int off;
+            if (k < n) {  // the listed pairs of this slice ...
+                off = my_list[(int64_t)k * a.n_obs];
+                k += stride;
+            } else if (resume < chunk_cnt) {  // ... then its share of the rest of the chunk
+                off = resume;
+                resume += stride;
+            } else {
+                break;
+            }
+            const double* rec = a.packed + (begin + off) * kTessRec;
+            if (rec[29] != 0.0) {  // a zero dimension: numba's ZeroDivisionError (tess_root_fast)
+                flags |= FLAG_ZERO_DIV;
+                continue;
+            }
+            tess_walk_begin(wk, rec, rec[6], rec[kTessRho1Fast], stack);
+        }
+        tess_walk_step<FIELD, kTessStack, kTessMaxLeaves, TRIG>(o, a.ratio, a.radial != 0, stack, wk, acc,
+                                                                flags);
+    }
 }
 
 // grid = (observer blocks, chunks, kTessWalkSlices): slice z of a (chunk, observer) list takes
@@ -753,35 +814,233 @@ __global__ void __launch_bounds__(kTessBlock) tesseroid_walk_kernel(const TessAr
         tess_make_obs(o, a.lon[i], a.lat[i], a.rad[i]);
         unsigned flags = 0;
         const unsigned short* my_list = list + ((int64_t)blockIdx.y * kTessListCap) * a.n_obs + i;
-        TessWalk wk;
-        wk.stack_top = -1;
-        wk.n_leaves = 0;
-        wk.density[0] = wk.density[1] = 0.0;
-        while (true) {  // one pop per trip, whatever the shapes of the lanes' trees
-            if (wk.stack_top < 0) {
-                int off;
-                if (k < n) {  // the listed pairs of this slice ...
-                    off = my_list[(int64_t)k * a.n_obs];
-                    k += kTessWalkSlices;
-                } else if (resume < chunk_cnt) {  // ... then its share of the rest of the chunk
-                    off = resume;
-                    resume += kTessWalkSlices;
-                } else {
-                    break;
-                }
-                const double* rec = a.packed + (begin + off) * kTessRec;
-                if (rec[29] != 0.0) {  // a zero dimension: numba's ZeroDivisionError (tess_root_fast)
-                    flags |= FLAG_ZERO_DIV;
-                    continue;
-                }
-                tess_walk_begin(wk, rec, rec[6], rec[kTessRho1Fast], stack);
-            }
-            tess_walk_step<FIELD, kTessStack, kTessMaxLeaves, TRIG>(o, a.ratio, a.radial != 0, stack, wk,
-                                                                    acc, flags);
-        }
+        tess_walk_list_exact<FIELD, TRIG>(a, o, my_list, n, k, resume, chunk_cnt, begin, kTessWalkSlices,
+                                          stack, acc, flags);
         if (flags && a.flags) atomicOr(a.flags, flags);
     }
     walk_sum[((int64_t)blockIdx.y * kTessWalkSlices + blockIdx.z) * a.n_obs + i] = acc;
+}
+
+// ---- cooperative walks (kernel variant 9) --------------------------------------------------------
+// tesseroid_walk_kernel gives every (chunk, observer) list to one thread: the 32 lists of a warp
+// have very different lengths and tree shapes, and ncu counted 8 of 32 active lanes on its
+// instructions (profiles/r2_ncu_tesseroid_gz_two_kernel.txt). Here a GROUP of kCoopG = 8 lanes
+// walks one list together: the group keeps a stack of nodes (bounds + the pair they belong to)
+// in shared memory, every trip each lane pops one node, decides on it with the reference's
+// statements, and either pushes its children back (positions from a prefix sum over the group) or
+// integrates the leaf into its own accumulator; the lanes' accumulators are added in fixed order
+// when the list is done. The lists that hold work are compacted by the root kernel into a work
+// list; the kernel is persistent (one CTA per resident slot) and every group draws its next list
+// from a global cursor, so the few long lists (observers next to a pole) do not leave the rest of
+// the machine idle. The four groups of a warp run the same trip loop in lockstep. What changes
+// against the reference is only the ORDER in which the leaves of a list are added; that order
+// depends on nothing but the list itself (bit-reproducible under any batching of the observers).
+//
+// Where the reference raises (OverflowError): its depth-first stack of kTessStack nodes cannot
+// overflow before depth (kTessStack - 8) / 7 = 13, and no pair can exceed kTessMaxLeaves leaves
+// unless the whole list does. A list that reaches either bound (or that would overflow the
+// group's stack) is thrown away and noted; tesseroid_redo_kernel walks it with ONE thread and the
+// exact depth-first walk of tesseroid_walk_kernel, which reports the reference's errors.
+constexpr int kCoopG = 8;        // lanes per group
+constexpr int kCoopCap = 56;     // nodes per group stack
+constexpr int kCoopDeep = 13;    // a node at this depth that wants to split sends the list to the exact walk
+constexpr int kCoopBlock = 128;  // 4 warps = 16 groups
+constexpr int kCoopCtasPerSm = 4;
+
+struct CoopStack {
+    double b[6][kCoopCap];  // w e s n bottom top, one row per bound: lanes read neighbouring words
+    int tag[kCoopCap];      // offset of the pair's root record in the chunk | depth << 16; -1: void
+};
+
+// counters[0]: number of items; [1]: cursor of the walk kernel; [2]: number of redo items
+template <int FIELD, class TRIG>
+__global__ void __launch_bounds__(kCoopBlock, kCoopCtasPerSm) tesseroid_coop_walk_kernel(
+    const TessArgs a, int n_chunks, const unsigned short* list, const int* count, const int* items,
+    int* counters, int* redo_items, double* walk_sum)
+{
+    __shared__ CoopStack stacks[kCoopBlock / kCoopG];
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int g = lane / kCoopG, l = lane % kCoopG;
+    CoopStack& S = stacks[threadIdx.x / kCoopG];
+    const int n_items = counters[0];
+    const bool radial = a.radial != 0;
+    const int spread = radial ? 7 : 3;  // net growth of the stack per node that splits, at most
+
+    // group state (the same in the 8 lanes of a group, except acc / leaves / flags)
+    int phase = 0;  // 0: draw the next list; 1: walking; 2: the work list is exhausted
+    int item = 0, n = 0, k = 0, resume = 0, cnt = 0, leaves = 0, chunk_cnt = 0;
+    int64_t begin = 0, obs = 0;
+    const unsigned short* my_list = list;
+    TessObs o;
+    tess_make_obs(o, 0.0, 0.0, 1.0);
+    double acc = 0.0;
+    unsigned flags = 0;
+
+    while (true) {
+        {
+            int drawn = 0;
+            if (phase == 0 && l == 0) drawn = atomicAdd(&counters[1], 1);
+            drawn = __shfl_sync(FULL, drawn, 0, kCoopG);
+            if (phase == 0) {
+                if (drawn < n_items) {
+                    item = items[drawn];
+                    const int chunk = item / kTessObsBatch;
+                    obs = item % kTessObsBatch;
+                    begin = (int64_t)chunk * a.chunk_len;
+                    chunk_cnt = (int)((begin + a.chunk_len < a.n_src ? begin + a.chunk_len : a.n_src) - begin);
+                    n = count[(int64_t)chunk * a.n_obs + obs];
+                    resume = count[((int64_t)n_chunks + chunk) * a.n_obs + obs];
+                    tess_make_obs(o, a.lon[obs], a.lat[obs], a.rad[obs]);
+                    my_list = list + ((int64_t)chunk * kTessListCap) * a.n_obs + obs;
+                    k = 0; cnt = 0; leaves = 0; acc = 0.0;
+                    phase = 1;
+                } else {
+                    phase = 2;
+                }
+            }
+        }
+        if (!__any_sync(FULL, phase == 1)) break;
+
+        // feed: the next pairs of the list (then of the rest of the chunk) become root nodes
+        if (phase == 1 && cnt < kCoopG) {
+            const int rest = chunk_cnt - resume;
+            const int roots = (n - k) + (rest > 0 ? rest : 0);
+            const int m = roots < kCoopG ? roots : kCoopG;
+            const int from_list = (n - k) < m ? (n - k) : m;
+            if (l < m) {
+                const int off = l < from_list ? (int)my_list[(int64_t)(k + l) * a.n_obs] : resume + (l - from_list);
+                const double* rec = a.packed + (begin + off) * kTessRec;
+                int tag = off;
+                if (rec[29] != 0.0) {  // a zero dimension: numba's ZeroDivisionError (tess_root_fast)
+                    flags |= FLAG_ZERO_DIV;
+                    tag = -1;
+                }
+#pragma unroll
+                for (int c = 0; c < 6; c++) S.b[c][cnt + l] = rec[c];
+                S.tag[cnt + l] = tag;
+            }
+            k += from_list;
+            resume += m - from_list;
+            cnt += m;
+        }
+        __syncwarp();
+
+        // pop: as many nodes as there are lanes, fewer while the stack is nearly full
+        int take = 0;
+        bool stuck = false;
+        if (phase == 1) {
+            take = cnt < kCoopG ? cnt : kCoopG;
+            const int room = (kCoopCap - cnt) / spread;
+            if (room < take) take = room;
+            stuck = take == 0 && cnt > 0;
+        }
+        double w = 0, e = 0, s = 0, nn = 0, bottom = 0, top = 0;
+        int tag = -1;
+        if (l < take) {
+            const int at = cnt - 1 - l;
+            w = S.b[0][at]; e = S.b[1][at]; s = S.b[2][at]; nn = S.b[3][at]; bottom = S.b[4][at]; top = S.b[5][at];
+            tag = S.tag[at];
+        }
+        cnt -= take;
+        __syncwarp();  // every pop has been read before a child is pushed over it
+
+        int n_lon = 1, n_lat = 1, n_rad = 1, kids = 0;
+        bool leaf = false;
+        if (tag >= 0) {
+            if (!tess_classify<TRIG>(o, a.ratio, radial, w, e, s, nn, bottom, top, n_lon, n_lat, n_rad)) {
+                flags |= FLAG_ZERO_DIV;
+            } else {
+                kids = n_lon * n_lat * n_rad;
+                leaf = kids == 1;
+                if (leaf) kids = 0;
+            }
+        }
+        const bool too_deep = kids > 0 && (tag >> 16) + 1 >= kCoopDeep;
+        // where the children go: prefix sum over the lanes of the group
+        int incl = kids;
+#pragma unroll
+        for (int d = 1; d < kCoopG; d <<= 1) {
+            const int v = __shfl_up_sync(FULL, incl, d, kCoopG);
+            if (l >= d) incl += v;
+        }
+        const int pushed = __shfl_sync(FULL, incl, kCoopG - 1, kCoopG);
+        const unsigned bad_lanes = __ballot_sync(FULL, too_deep || stuck);
+        const bool bad = ((bad_lanes >> (kCoopG * g)) & ((1u << kCoopG) - 1u)) != 0u;
+        if (kids > 0 && !bad) {  // _split_tesseroid
+            int at = cnt + incl - kids;
+            const double d_lon = (e - w) / n_lon, d_lat = (nn - s) / n_lat, d_rad = (top - bottom) / n_rad;
+            const int child_tag = tag + (1 << 16);
+            for (int i = 0; i < n_lon; i++)
+                for (int j = 0; j < n_lat; j++)
+                    for (int r = 0; r < n_rad; r++, at++) {
+                        S.b[0][at] = w + d_lon * i;
+                        S.b[1][at] = w + d_lon * (i + 1);
+                        S.b[2][at] = s + d_lat * j;
+                        S.b[3][at] = s + d_lat * (j + 1);
+                        S.b[4][at] = bottom + d_rad * r;
+                        S.b[5][at] = bottom + d_rad * (r + 1);
+                        S.tag[at] = child_tag;
+                    }
+        }
+        cnt += pushed;
+        if (leaf) {
+            const double* rec = a.packed + (begin + (tag & 0xffff)) * kTessRec;
+            const double density[2] = {rec[6], rec[kTessRho1Fast]};
+            TessNodes nodes;
+            tess_nodes<TRIG>(nodes, w, e, s, nn, bottom, top, density);
+            acc += tess_glq_nodes<FIELD, TRIG>(o, nodes, flags);
+            leaves += 1;
+        }
+
+        // a list is done (or given up): add the lanes' sums in fixed order
+        const bool done = phase == 1 && (bad || (cnt == 0 && k >= n && resume >= chunk_cnt));
+        if (__any_sync(FULL, done)) {
+            double total = acc;
+            int total_leaves = leaves;
+#pragma unroll
+            for (int d = 1; d < kCoopG; d <<= 1) {
+                total += __shfl_xor_sync(FULL, total, d, kCoopG);
+                total_leaves += __shfl_xor_sync(FULL, total_leaves, d, kCoopG);
+            }
+            if (done) {
+                if (l == 0) {
+                    if (bad || total_leaves > kTessMaxLeaves) redo_items[atomicAdd(&counters[2], 1)] = item;
+                    else walk_sum[(int64_t)(item / kTessObsBatch) * a.n_obs + obs] = total;
+                }
+                phase = 0;
+            }
+        }
+    }
+    if (flags && a.flags) atomicOr(a.flags, flags);
+}
+
+// the lists the cooperative walk gave up (rare): one thread each, the exact depth-first walk
+template <int FIELD, class TRIG>
+__global__ void __launch_bounds__(kTessBlock) tesseroid_redo_kernel(const TessArgs a, int n_chunks,
+                                                                    const unsigned short* list, const int* count,
+                                                                    const int* counters, const int* redo_items,
+                                                                    double* walk_sum)
+{
+    const int n_redo = counters[2];
+    double stack[kTessStack * 6];
+    for (int r = blockIdx.x * kTessBlock + threadIdx.x; r < n_redo; r += gridDim.x * kTessBlock) {
+        const int item = redo_items[r];
+        const int chunk = item / kTessObsBatch;
+        const int64_t obs = item % kTessObsBatch;
+        const int64_t begin = (int64_t)chunk * a.chunk_len;
+        const int chunk_cnt = (int)((begin + a.chunk_len < a.n_src ? begin + a.chunk_len : a.n_src) - begin);
+        TessObs o;
+        tess_make_obs(o, a.lon[obs], a.lat[obs], a.rad[obs]);
+        double acc = 0.0;
+        unsigned flags = 0;
+        tess_walk_list_exact<FIELD, TRIG>(a, o, list + ((int64_t)chunk * kTessListCap) * a.n_obs + obs,
+                                          count[(int64_t)chunk * a.n_obs + obs], 0,
+                                          count[((int64_t)n_chunks + chunk) * a.n_obs + obs], chunk_cnt, begin, 1,
+                                          stack, acc, flags);
+        walk_sum[(int64_t)chunk * a.n_obs + obs] = acc;
+        if (flags && a.flags) atomicOr(a.flags, flags);
+    }
 }
 
 // check_points_outside_tesseroids as one pass: sets FLAG_TESS_INSIDE if any pair conflicts

@@ -90,11 +90,15 @@ const char* hb200_last_error(void);
 int hb200_set_variant(int variant);
 int hb200_get_variant(void);
 /* tesseroid kernels: 1 = observer-independent parts of every tesseroid precomputed into root
- * records, pairs that split deferred and walked by all lanes of a warp together; 2 (default) =
- * as 1 with an arithmetic-only far field (cosine of the longitude difference from precomputed
- * factors, the library's reciprocal square root, squared split thresholds); 3 = as 2 with the
- * library's own bounded-angle sin / cos / acos in the walks; 4, 5 = as 3 compiled for 80 / 64
- * registers (occupancy experiments); 0 = first build (every pair walked where it is met) */
+ * records, pairs that split deferred and walked by all lanes of a warp together; 2 = as 1 with an
+ * arithmetic-only far field (cosine of the longitude difference from precomputed factors, the
+ * library's reciprocal square root, squared split thresholds); 3 = as 2 with the library's own
+ * bounded-angle sin / cos / acos in the walks; 4, 5 = as 3 compiled for 80 / 64 registers
+ * (occupancy experiments); 6 (7, 8: other register budgets) = the far field of all pairs in one
+ * kernel that lists the pairs that split, their walks in a second kernel (one thread per list);
+ * 9 (default) = as 6 with the walks done by groups of 8 lanes on a shared stack, lists drawn
+ * from a compacted work list by a persistent kernel; 0 = first build (every pair walked where
+ * it is met) */
 int hb200_set_tesseroid_variant(int variant);
 int hb200_get_tesseroid_variant(void);
 /* staging of the packed prism records in the prism kernels: 1 (default) = every warp streams

@@ -19,3 +19,50 @@ def page(rep, name):
             with opener(path, "rt") as fh:
                 return fh.read()
     raise FileNotFoundError(f"no ncu report or exported '{name}' page for {rep}")
+
+
+def opcode_sections(rep):
+    """[(kernel name, Counter opcode -> warp instructions executed, avg active threads)] of the
+    source page, one entry per captured launch (ncu prints every launch of a multi-kernel report
+    twice: identical sections are dropped)."""
+    import collections
+    import csv
+    import hashlib
+    import io
+
+    rows = list(csv.reader(io.StringIO(page(rep, "source"))))
+    sections, cur = [], None
+    for r in rows:
+        if r and r[0] == "Kernel Name":
+            cur = {"name": r[1], "rows": []}
+            sections.append(cur)
+        elif cur is not None:
+            cur["rows"].append(r)
+    out, seen = [], set()
+    for sec in sections:
+        digest = hashlib.sha256(repr(sec["rows"]).encode()).hexdigest()
+        if digest in seen or not sec["rows"]:
+            continue
+        seen.add(digest)
+        hdr = sec["rows"][0]
+        iS, iE, iT = hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed")
+        ops, threads = collections.Counter(), 0
+        for r in sec["rows"][1:]:
+            if len(r) <= iT:
+                continue
+            try:
+                n = int(r[iE])
+                threads += int(r[iT])
+            except ValueError:
+                continue
+            toks = r[iS].strip().split()
+            if not toks:
+                continue
+            op = (toks[1] if toks[0].startswith("@") and len(toks) > 1 else toks[0]).split(".")[0]
+            ops[op] += n
+        total = sum(ops.values())
+        out.append((sec["name"], ops, threads / total if total else 0.0))
+    return out
+
+
+FP64_OPS = ("DFMA", "DMUL", "DADD", "DSETP", "DMNMX")

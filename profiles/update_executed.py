@@ -30,26 +30,16 @@ FILES = {"layer_gz": PRISM_FILES, "c1_gz": PRISM_FILES, "tensor": PRISM_FILES, "
 
 workload, rep, pairs, source = sys.argv[1], sys.argv[2], float(sys.argv[3]), sys.argv[4]
 dram = int(sys.argv[5]) if len(sys.argv) > 5 else None
-raw = _ncu_pages.page(rep, "source")
-rows = list(csv.reader(io.StringIO(raw)))
-hdr = rows[1]
-iS, iE = hdr.index("Source"), hdr.index("Instructions Executed")
-ops, tot = collections.Counter(), 0
-for r in rows[2:]:
-    if len(r) <= iE:
-        continue
-    try:
-        n = int(r[iE])
-    except ValueError:
-        continue
-    toks = r[iS].strip().split()
-    op = (toks[1] if toks[0].startswith("@") else toks[0]).split(".")[0]
-    ops[op] += n
-    tot += n
-fp64 = sum(n for op, n in ops.items() if op in ("DFMA", "DMUL", "DADD", "DSETP", "DMNMX"))
+sections = _ncu_pages.opcode_sections(rep)  # several kernels (tesseroids: root pass + walks): their sum
+ops = collections.Counter()
+for _name, sec_ops, _lanes in sections:
+    ops.update(sec_ops)
+tot = sum(ops.values())
+fp64 = sum(n for op, n in ops.items() if op in _ncu_pages.FP64_OPS)
+kernel_name = " + ".join(name for name, _o, _l in sections)
 path = bench.EXECUTED_FILE
 table = json.load(open(path)) if os.path.exists(path) else {}
-entry = {"kernel": rows[0][1], "fp64": round(fp64 * 32 / pairs, 2), "other": round((tot - fp64) * 32 / pairs, 2),
+entry = {"kernel": kernel_name, "fp64": round(fp64 * 32 / pairs, 2), "other": round((tot - fp64) * 32 / pairs, 2),
          "pairs_per_launch": pairs, "files": FILES[workload], "sha16": bench.csrc_sha16(FILES[workload]),
          "source": source}
 if dram is not None:

@@ -94,12 +94,12 @@ wl=bench.make_workload('eqs',151552,1000000)
 s=wl['sources']
 hb.eqs_predict(wl['coords'],s['points'],s['coefs'])" ;;
 ncu_tess)
-    timeout 200 ncu --set full --clock-control none --import-source on -k "regex:tesseroid_(root|walk|deferred)" -c 2 -f \
+    timeout 200 ncu --set full --clock-control none --import-source on -k "regex:tesseroid_(root|walk|deferred|coop)" -c 2 -f \
         -o gpurun_out/${TAG}_prof_tess python -c "
 import sys; sys.path[:0]=['.','tests']
 import numpy as np, bench, harmonica_b200 as hb
 hb.init([0])
-hb._lib.load().hb200_set_tesseroid_variant(int('${TESS_VARIANT:-6}'))
+hb._lib.load().hb200_set_tesseroid_variant(int('${TESS_VARIANT:-9}'))
 wl=bench.make_workload('tess_gz',65536)
 hb.tesseroid_gravity(wl['coords'],wl['tesseroids'],wl['density'],'g_z',disable_checks=True)
 " > gpurun_out/${TAG}_ncu_tess.log 2>&1

@@ -25,9 +25,10 @@ from test_tesseroid_host import (MEAN_RADIUS, MODES, _cases, _key, _shell, _shel
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=[6, 3, 2, 1, 0], ids=["two-kernel", "own-trig", "fast", "deferred", "plain"])
+@pytest.fixture(params=[9, 6, 3, 2, 1, 0], ids=["group-walks", "two-kernel", "own-trig", "fast", "deferred", "plain"])
 def tess_variant(request, hb):
-    """the tesseroid kernels: 6 = root pass and walks as two kernels; 3 = one kernel, root records
+    """the tesseroid kernels: 9 = as 6 with the walks done by groups of 8 lanes on a shared stack;
+    6 = root pass and walks as two kernels; 3 = one kernel, root records
     + deferred walks + arithmetic-only far field + the library's own trig in the walks; 2 = as 3
     with CUDA's trig; 1 = without the fast far field; 0 = first build"""
     lib = hb._lib.load()
@@ -219,7 +220,7 @@ def test_density_function_rules(hb):
         hb.tesseroid_gravity(grid, tesseroid, lambda radius: 2900.0, "g_z", radial_adaptive_discretization=True)
 
 
-@pytest.mark.parametrize("variant", [6, 3])
+@pytest.mark.parametrize("variant", [9, 6, 3])
 def test_polar_observers_fill_the_split_lists(hb, variant):
     """Next to a pole EVERY tesseroid of the nearest latitude rings is near (hundreds of split
     roots for one observer, against ~20 elsewhere): in the two-kernel variant the per-chunk lists
@@ -252,5 +253,27 @@ def test_polar_observers_fill_the_split_lists(hb, variant):
         idx = np.arange(0, n, 1600)
         sub = tuple(c[idx] for c in many)
         assert max_rel(got[idx], O.tesseroid_gravity(sub, tess, density, "g_z")) <= 2e-8
+    finally:
+        lib.hb200_set_tesseroid_variant(default)
+
+
+@pytest.mark.parametrize("variant", [9, 6])
+def test_deep_trees(hb, variant):
+    """Continental tesseroids seen from 2 km above: the discretisation goes 14 levels deep, beyond
+    what the groups of the cooperative walk keep on their shared stacks; such lists are handed to
+    the exact depth-first walk inside the same kernel. Against the oracle."""
+    lib = hb._lib.load()
+    R = MEAN_RADIUS
+    tess = np.array([[-60, 60, -60, 60, R - 1000.0, R], [60, 180, -60, 60, R - 1500.0, R - 100]])
+    density = np.array([2670.0, 2900.0])
+    coords = (np.array([0.1, 13.0, 59.0, 100.0, -70.0]), np.array([0.2, -33.0, 59.5, 10.0, 61.0]),
+              np.array([R + 2000, R + 2500.0, R + 3000.0, R + 2000.0, R + 5000.0]))
+    default = lib.hb200_get_tesseroid_variant()
+    try:
+        assert lib.hb200_set_tesseroid_variant(variant) == 0
+        for field in ("g_z", "potential"):
+            want = O.tesseroid_gravity(coords, tess, density, field)
+            got = hb.tesseroid_gravity(coords, tess, density, field)
+            assert max_rel(got, want) <= TOL, field
     finally:
         lib.hb200_set_tesseroid_variant(default)

@@ -177,3 +177,22 @@ def test_dipole_errors():
     assert list(inspect.signature(hb.dipole_magnetic).parameters)[:8] == [
         "coordinates", "dipoles", "magnetic_moments", "field", "parallel", "dtype", "progressbar",
         "disable_checks"]
+
+
+def test_locality_order_of_tesseroid_observers():
+    """the Morton ordering handed to the device: a permutation, NaN-safe, and local (consecutive
+    points are neighbours on the sphere)"""
+    from harmonica_b200 import _tesseroid as T
+
+    rng = np.random.default_rng(5)
+    lon = rng.uniform(-180, 360, 20_000)
+    lat = np.degrees(np.arcsin(rng.uniform(-1, 1, 20_000)))
+    lon[7], lat[11] = np.nan, np.nan
+    order = T._locality_order(lon, lat)
+    assert np.array_equal(np.sort(order), np.arange(lon.size))
+    lo, la = np.mod(lon[order], 360.0), lat[order]
+    dlon = np.abs(np.diff(lo))
+    jump = np.abs(np.diff(la)) + np.minimum(dlon, 360.0 - dlon)
+    assert np.nanmedian(jump) < 3.0  # random order: ~100 degrees
+    assert not T._already_local(lon, lat)
+    assert T._already_local(lon[order], lat[order])
