@@ -29,7 +29,8 @@ namespace {
 thread_local std::string g_err;
 std::mutex g_mu;
 int g_variant = 2;
-int g_tile_mode = 1;         // 1: one record stream per warp; 0: per CTA (hb200_set_tile_mode)
+int g_tile_mode = 1;         // 1: one record stream per warp, vertex reuse along layer columns;
+                             // 2: without the reuse; 0: one stream per CTA (hb200_set_tile_mode)
 int g_source_chunks = 0;     // 0: chosen from the grid size (choose_chunks)
 double g_fit_rcond = 2.220446049250313e-16;  // cutoff of the undamped fit (hb200_fit_host.cuh)
 std::atomic<uint64_t> g_launches{0};  // kernels launched by this library (hb200_launch_count)
@@ -159,11 +160,19 @@ int choose_chunks(int64_t n_obs, int64_t n_src, int obs_per_block, int sms, int6
     return (int)std::max<int64_t>(1, chunks);
 }
 
+// set by prism_layer_dev_impl around its passes: the records come from pack_layer_kernel, which
+// marks the ones that share vertices with their predecessor (one host thread per device)
+thread_local bool t_layer_records = false;
+
 template <int FS> void launch_prism_fs(const PrismArgs& a, dim3 grid, cudaStream_t st)
 {
+    // the fields of prism_layer.gravity; the potential kernel is at its register limit (the carry spills)
+    constexpr bool gravity = FS <= F_NU && FS != F_POT;
     if (g_variant == 0) prism_kernel<FS, 0><<<grid, kBlock, 0, st>>>(a);
     else if (g_variant == 1) prism_kernel<FS, 1><<<grid, kBlock, 0, st>>>(a);
     else if (g_tile_mode == 0) prism_kernel<FS, 2, false><<<grid, kBlock, 0, st>>>(a);
+    else if (gravity && g_tile_mode == 1 && t_layer_records)
+        prism_kernel<FS, 2, true, 4, gravity><<<grid, kBlock, 0, st>>>(a);  // vertex reuse along layer columns
     else prism_kernel<FS, 2, true><<<grid, kBlock, 0, st>>>(a);
 }
 
@@ -367,7 +376,10 @@ int prism_layer_dev_impl(const double* oe, const double* on, const double* ou, i
         CU(cudaGetLastError());
         g_launches += 1;
     }
-    return gravity_passes(oe, on, ou, n_obs, packed, n_src, mask, raw, out, d_flags, ws, sms, st);
+    t_layer_records = true;
+    const int rc = gravity_passes(oe, on, ou, n_obs, packed, n_src, mask, raw, out, d_flags, ws, sms, st);
+    t_layer_records = false;
+    return rc;
 }
 
 int prism_magnetic_dev_impl(const double* oe, const double* on, const double* ou, int64_t n_obs,
@@ -976,7 +988,8 @@ int hb200_set_tesseroid_variant(int variant)
 int hb200_get_tesseroid_variant(void) { return g_tess_variant; }
 int hb200_set_tile_mode(int mode)
 {
-    if (mode != 0 && mode != 1) return fail(HB200_EINVAL, "tile mode must be 0 (per CTA) or 1 (per warp)");
+    if (mode < 0 || mode > 2)
+        return fail(HB200_EINVAL, "tile mode must be 0 (per CTA), 1 (per warp; layers reuse vertices) or 2 (per warp, no reuse)");
     g_tile_mode = mode;
     return HB200_OK;
 }

@@ -76,7 +76,21 @@ struct FastCtx {
     double r[2][2][2];
 };
 
-template <int FS, bool XM> HB_HD void make_fast_ctx(FastCtx& c, const PairGeom& g)
+// Vertex distances carried from one record of a prism layer to the next (records are emitted
+// easting-outer / northing-inner, layer.py:591-594): where the next prism has the same west /
+// east bounds and bottom and its south bound IS the previous north bound (pack_layer_kernel marks
+// such records), its two bottom-south vertices are the previous bottom-north ones: the same
+// inputs, hence bit-identical distances, and two of the eight square roots are not redone.
+// (Carrying the whole context -- shifts, squares, all shared distances -- was measured too: the
+// loop-carried registers cost more moves than the 22 FP64 instructions they save, 70.8 against
+// 73.4 G pair/s; these two doubles give 75.0 G.)
+struct LayerCarry {
+    double r[2];  // r[i][north][bottom] of the previous record, i = east / west
+    bool valid;   // the previous record of this lane went through the merged path
+};
+
+template <int FS, bool XM>
+HB_HD void make_fast_ctx(FastCtx& c, const PairGeom& g, const LayerCarry* carry = nullptr, bool reuse = false)
 {
 #pragma unroll
     for (int i = 0; i < 2; i++) {
@@ -92,7 +106,19 @@ template <int FS, bool XM> HB_HD void make_fast_ctx(FastCtx& c, const PairGeom& 
 #pragma unroll
         for (int j = 0; j < 2; j++)
 #pragma unroll
-            for (int k = 0; k < 2; k++) c.r[i][j][k] = x_sqrt<XM>(add_rn(c.en2[i][j], g.su2[k]));
+            for (int k = 0; k < 2; k++) {
+                if (carry && j == 1 && k == 1) continue;  // below
+                c.r[i][j][k] = x_sqrt<XM>(add_rn(c.en2[i][j], g.su2[k]));
+            }
+    if (carry) {
+        if (reuse) {
+            c.r[0][1][1] = carry->r[0];
+            c.r[1][1][1] = carry->r[1];
+        } else {
+            c.r[0][1][1] = x_sqrt<XM>(add_rn(c.en2[0][1], g.su2[1]));
+            c.r[1][1][1] = x_sqrt<XM>(add_rn(c.en2[1][1], g.su2[1]));
+        }
+    }
 }
 
 // safe_log type X (0: x = e, 1: x = n, 2: x = u) at vertex ijk:
@@ -557,7 +583,8 @@ HB_HD double plus_zero(double x) { return x == 0.0 ? 0.0 : x; }
 
 template <int FS, bool XM>
 HB_HD void prism_pair_fast(const PairGeom& g0, const double* prm, double* acc, int cls = PAIR_FAST,
-                           unsigned mag_rules = 0u, unsigned* flags = nullptr)
+                           unsigned mag_rules = 0u, unsigned* flags = nullptr, LayerCarry* carry = nullptr,
+                           bool reuse = false)
 {
     typedef Traits<FS> T;
     PairGeom g = g0;
@@ -568,7 +595,11 @@ HB_HD void prism_pair_fast(const PairGeom& g0, const double* prm, double* acc, i
         }
     }
     FastCtx c;
-    make_fast_ctx<FS, XM>(c, g);
+    make_fast_ctx<FS, XM>(c, g, carry, reuse);
+    if (carry) {
+        carry->r[0] = c.r[0][0][1];
+        carry->r[1] = c.r[1][0][1];
+    }
     const double* e = c.se;
     const double* n = c.sn;
     const double* u = c.su;
@@ -729,15 +760,20 @@ HB_HD void prism_pair_fast(const PairGeom& g0, const double* prm, double* acc, i
 // pair (libm); 1 = merged path on CUDA libm; 2 = merged path on the library's own sequences.
 template <int FS, int VARIANT>
 HB_HD void prism_pair(const PairGeom& g, const double* prm, unsigned mag_rules, double* acc,
-                      unsigned& flags)
+                      unsigned& flags, LayerCarry* carry = nullptr, bool reuse = false)
 {
     if (VARIANT == 0) {
         prism_pair_direct<FS>(g, prm, mag_rules, acc, flags);
         return;
     }
     const int cls = classify_pair<FS>(g);
-    if (cls == PAIR_EXACT) prism_pair_direct<FS, (VARIANT == 2)>(g, prm, mag_rules, acc, flags);
-    else prism_pair_fast<FS, (VARIANT == 2)>(g, prm, acc, cls, mag_rules, &flags);
+    if (cls == PAIR_EXACT) {
+        prism_pair_direct<FS, (VARIANT == 2)>(g, prm, mag_rules, acc, flags);
+        if (carry) carry->valid = false;
+    } else {
+        prism_pair_fast<FS, (VARIANT == 2)>(g, prm, acc, cls, mag_rules, &flags, carry, reuse);
+        if (carry) carry->valid = true;
+    }
 }
 
 }  // namespace hb

@@ -87,7 +87,19 @@ __global__ void pack_layer_kernel(const double* __restrict__ east_c,
     q[4] = b;
     q[5] = t;
     q[6] = kG * rho;
-    q[7] = skip ? 1.0 : 0.0;
+    // 2: evaluated, in the same column as the previous record, which is evaluated too, with the
+    // same bottom, and its south bound IS that record's north bound (bit for bit):
+    // prism_kernel<.., REUSE> then keeps two vertex distances (LayerCarry, hb200_fast.cuh)
+    double mark = skip ? 1.0 : 0.0;
+    if (!skip && k > 0) {
+        const double rho_p = density[(k - 1) * n_east + j];
+        const double b_p = bottom[(k - 1) * n_east + j], t_p = top[(k - 1) * n_east + j];
+        bool skip_p = (rho_p == 0.0) || isnan(rho_p);
+        skip_p = skip_p || (t_p - b_p < thickness_threshold);
+        skip_p = skip_p || isnan(t_p) || isnan(b_p);
+        if (!skip_p && b_p == b && north_c[k - 1] + half_n == q[2]) mark = 2.0;
+    }
+    q[7] = mark;
 }
 
 // point sources: weight = G*mass (choclo.point: G * mass * kernel) or the EQS
@@ -192,7 +204,9 @@ constexpr int kWarps = kBlock / 32;
 
 // WARP_TILES = true: as described above. false: ONE copy per CTA (kTile records, elected thread
 // 0, __syncthreads() closes every tile) -- kept selectable (hb200_set_tile_mode) for comparison.
-template <int FS, int VARIANT, bool WARP_TILES = true, int MINB = 4>
+// REUSE = true: records marked 2 by pack_layer_kernel take two vertex distances from the previous
+// record (LayerCarry, hb200_fast.cuh); results are bit-identical to REUSE = false.
+template <int FS, int VARIANT, bool WARP_TILES = true, int MINB = 4, bool REUSE = false>
 __global__ void __launch_bounds__(kBlock, MINB) prism_kernel(const PrismArgs a)
 {
     typedef Traits<FS> T;
@@ -212,6 +226,9 @@ __global__ void __launch_bounds__(kBlock, MINB) prism_kernel(const PrismArgs a)
 #pragma unroll
     for (int c = 0; c < T::nout; c++) acc[c] = 0.0;
     unsigned flags = 0;
+    LayerCarry carry;
+    carry.r[0] = carry.r[1] = 0.0;
+    carry.valid = false;
 
     const int64_t begin = (int64_t)blockIdx.y * a.chunk_len;
     const int64_t end = begin + a.chunk_len < a.n_src ? begin + a.chunk_len : a.n_src;
@@ -248,17 +265,23 @@ __global__ void __launch_bounds__(kBlock, MINB) prism_kernel(const PrismArgs a)
             const double2* p = tile + s * (STRIDE / 2);
             const double2 we = p[0], sn = p[1], bt = p[2], q3 = p[3];
             double prm[3];
+            double mark;
             if (T::mag) {
                 const double2 q4 = p[4];
-                if (q4.y != 0.0) continue;  // warp-uniform
+                mark = q4.y;
                 prm[0] = q3.x; prm[1] = q3.y; prm[2] = q4.x;
             } else {
-                if (q3.y != 0.0) continue;  // warp-uniform
+                mark = q3.y;
                 prm[0] = q3.x; prm[1] = 0.0; prm[2] = 0.0;
+            }
+            if (mark == 1.0) {  // warp-uniform
+                if (REUSE) carry.valid = false;
+                continue;
             }
             PairGeom g;
             make_geom(g, E, N, U, we.x, we.y, sn.x, sn.y, bt.x, bt.y);
-            prism_pair<FS, VARIANT>(g, prm, a.rules, acc, flags);
+            if (REUSE) prism_pair<FS, VARIANT>(g, prm, a.rules, acc, flags, &carry, carry.valid && mark == 2.0);
+            else prism_pair<FS, VARIANT>(g, prm, a.rules, acc, flags);
         }
         // the buffer just read may be refilled in the next iteration
         if (WARP_TILES) __syncwarp(); else __syncthreads();

@@ -102,8 +102,10 @@ int hb200_get_variant(void);
 int hb200_set_tesseroid_variant(int variant);
 int hb200_get_tesseroid_variant(void);
 /* staging of the packed prism records in the prism kernels: 1 (default) = every warp streams
- * its own copy with TMA bulk copies and synchronises only with itself; 0 = one copy per CTA with
- * a CTA-wide barrier per tile (first build, kept for comparison). Values are identical. */
+ * its own copy with TMA bulk copies and synchronises only with itself, and in prism_layer_gravity
+ * neighbouring prisms of a layer column share two vertex distances; 2 = as 1 without that reuse;
+ * 0 = one copy per CTA with a CTA-wide barrier per tile (first build, kept for comparison).
+ * Values are identical. */
 int hb200_set_tile_mode(int mode);
 int hb200_get_tile_mode(void);
 /* Reproducibility. The value of an (observer, source) pair never depends on the batch it is

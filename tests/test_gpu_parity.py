@@ -492,3 +492,32 @@ def test_equivalent_sources_fit_predict_round_trip(hb):
     npt.assert_array_equal(fixed.points_[2], np.full(36, -1e3))
     # 36 sources with the 1/r kernel cannot reproduce 64 g_z values exactly: least-squares misfit
     assert np.max(np.abs(fixed.predict(coords) - data)) < 0.1 * np.max(np.abs(data))
+
+
+def test_layer_vertex_reuse_is_bit_identical(hb):
+    """tile mode 1 (default) against 2: neighbouring prisms of a layer column share two vertex distances
+    (LayerCarry); same inputs to the same operations, so every field is bit-identical to the
+    generic kernel — NaN / zero-density cells (broken chains), unequal bottoms, observers above,
+    on top faces and on cell corners (exact-path pairs invalidate a lane's carry) included."""
+    lib = hb._lib.load()
+    coords, east_c, north_c, bottom, top, density = layer_config2(n=60, seed=7)
+    rng = np.random.default_rng(3)
+    bottom = bottom.copy()
+    bottom[rng.integers(0, 60, 40), rng.integers(0, 60, 40)] -= 25.0  # unequal bottoms break the reuse
+    ee, nn = np.meshgrid(east_c, north_c)
+    ok = np.isfinite(top)
+    on_top = (ee[ok][::7], nn[ok][::7], top[ok][::7])
+    corners = (ee[ok][::11] + 100.0, nn[ok][::11] + 100.0, top[ok][::11])
+    obs = tuple(np.concatenate([a[::5], b, c]) for a, b, c in zip(coords, on_top, corners))
+    default = lib.hb200_get_tile_mode()
+    try:
+        for field in ("g_z", "potential", "g_e", "g_zz", "g_en"):
+            results = []
+            for mode in (2, 1):
+                assert lib.hb200_set_tile_mode(mode) == 0
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    results.append(hb.prism_layer_gravity(obs, east_c, north_c, bottom, top, density, field))
+            assert np.array_equal(results[0], results[1], equal_nan=True), field
+    finally:
+        lib.hb200_set_tile_mode(default)
