@@ -30,6 +30,8 @@ Prints ONE JSON line (rank 0):
   also         short runs of the other BASELINE configs (tensor, mag_b, eqs)
   north_star   BASELINE configs[2]: the six tensor components of 1M prisms on 1M
                observers, end to end through the (sharded) public API, 1 step
+  source_sharded (N > 1) BASELINE configs[4]: EQS predict with the 4M sources
+               sharded over the ranks and an NCCL float64 reduce-sum, short run
   cpu_baseline the reference's CPU path on the host cores: the Numba
                parallel=True restatement (oracle/numba_loops.py) and the
                C/OpenMP port (oracle/choclo_port.c), both reported
@@ -621,6 +623,22 @@ def run_b200(args):
         del st3, w3
         torch.cuda.empty_cache()
 
+    source_sharded = None
+    if world > 1 and not args.no_also and args.workload == "layer_gz" and not args.n_obs:
+        # BASELINE configs[4] (262 144 of its 4M observers): sources sharded over the ranks, every rank
+        # a full-length partial field, ONE float64 reduce-sum to rank 0 over NCCL; short run
+        w5 = make_workload("eqs")
+        st5 = Stepper(w5, rank, world, "strong", "sources")
+        m5 = measure(st5, 3, 3, rank, world, local, False, e2e_steps=2)
+        source_sharded = {"workload": w5["desc"], "scaling": "strong", "n_gpus": world, "steps": 3,
+                          "warmup": 3, "value": m5["value"], "unit": "pair/s",
+                          "ms_per_step": m5["ms_per_step"], "e2e": m5["e2e_value"],
+                          "gpu_launches": m5["gpu_launches"],
+                          "sharding": f"sources over {world} ranks, torch.distributed NCCL reduce(sum, f64) "
+                                      "to rank 0 inside the timed region"}
+        del st5, w5
+        torch.cuda.empty_cache()
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
         nthreads = host_cores()
@@ -667,6 +685,7 @@ def run_b200(args):
             "cpu_baseline": cpu_baseline,
             "also": also,
             "north_star": north_star,
+            "source_sharded": source_sharded,
         }  # fmt: skip
         print(json.dumps(line), flush=True)
     if world > 1:

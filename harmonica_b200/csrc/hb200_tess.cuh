@@ -842,15 +842,19 @@ __global__ void __launch_bounds__(kTessBlock) tesseroid_walk_kernel(const TessAr
 // group's stack) is thrown away and noted; tesseroid_redo_kernel walks it with ONE thread and the
 // exact depth-first walk of tesseroid_walk_kernel, which reports the reference's errors.
 constexpr int kCoopG = 8;        // lanes per group
-constexpr int kCoopCap = 56;     // nodes per group stack
+constexpr int kCoopCap = 80;     // nodes per group stack (56 with the 3-D discretisation: 6 bounds per node)
+constexpr int kCoopCapRadial = 56;
 constexpr int kCoopDeep = 13;    // a node at this depth that wants to split sends the list to the exact walk
 constexpr int kCoopBlock = 128;  // 4 warps = 16 groups
 constexpr int kCoopCtasPerSm = 4;
 
+// One row per bound (lanes read neighbouring words): w e s n, and bottom top only when the radial
+// direction is discretised too (otherwise they follow from the root's, read from the record).
 struct CoopStack {
-    double b[6][kCoopCap];  // w e s n bottom top, one row per bound: lanes read neighbouring words
-    int tag[kCoopCap];      // offset of the pair's root record in the chunk | depth << 16; -1: void
+    double b[6 * kCoopCapRadial];  // >= 4 * kCoopCap
+    int tag[kCoopCap];             // offset of the pair's root record in the chunk | depth << 16; -1: void
 };
+static_assert(6 * kCoopCapRadial >= 4 * kCoopCap, "CoopStack rows");
 
 // counters[0]: number of items; [1]: cursor of the walk kernel; [2]: number of redo items
 template <int FIELD, class TRIG>
@@ -866,6 +870,12 @@ __global__ void __launch_bounds__(kCoopBlock, kCoopCtasPerSm) tesseroid_coop_wal
     const int n_items = counters[0];
     const bool radial = a.radial != 0;
     const int spread = radial ? 7 : 3;  // net growth of the stack per node that splits, at most
+    const int cap = radial ? kCoopCapRadial : kCoopCap;
+    // Eight lanes popping the top of the stack need eight times the memory of a depth-first walk
+    // (24 nodes per level). While the stack is nearly full only ONE lane pops -- a plain
+    // depth-first descent, 3 nodes per level, for which `narrow` slots are kept free -- until
+    // the top of the stack has drained.
+    const int narrow = radial ? 14 : 18;
 
     // group state (the same in the 8 lanes of a group, except acc / leaves / flags)
     int phase = 0;  // 0: draw the next list; 1: walking; 2: the work list is exhausted
@@ -917,7 +927,11 @@ __global__ void __launch_bounds__(kCoopBlock, kCoopCtasPerSm) tesseroid_coop_wal
                     tag = -1;
                 }
 #pragma unroll
-                for (int c = 0; c < 6; c++) S.b[c][cnt + l] = rec[c];
+                for (int c = 0; c < 4; c++) S.b[c * cap + cnt + l] = rec[c];
+                if (radial) {
+                    S.b[4 * cap + cnt + l] = rec[4];
+                    S.b[5 * cap + cnt + l] = rec[5];
+                }
                 S.tag[cnt + l] = tag;
             }
             k += from_list;
@@ -931,16 +945,35 @@ __global__ void __launch_bounds__(kCoopBlock, kCoopCtasPerSm) tesseroid_coop_wal
         bool stuck = false;
         if (phase == 1) {
             take = cnt < kCoopG ? cnt : kCoopG;
-            const int room = (kCoopCap - cnt) / spread;
-            if (room < take) take = room;
+            int wide = (cap - narrow - cnt) / spread;
+            if (wide < 1) wide = 1;
+            if (take > wide) take = wide;
+            if (cnt + spread > cap) take = 0;  // even one pop could overflow: give the list up
             stuck = take == 0 && cnt > 0;
         }
         double w = 0, e = 0, s = 0, nn = 0, bottom = 0, top = 0;
         int tag = -1;
         if (l < take) {
             const int at = cnt - 1 - l;
-            w = S.b[0][at]; e = S.b[1][at]; s = S.b[2][at]; nn = S.b[3][at]; bottom = S.b[4][at]; top = S.b[5][at];
+            w = S.b[at]; e = S.b[cap + at]; s = S.b[2 * cap + at]; nn = S.b[3 * cap + at];
             tag = S.tag[at];
+            if (radial) {
+                bottom = S.b[4 * cap + at];
+                top = S.b[5 * cap + at];
+            } else if (tag >= 0) {
+                // _split_tesseroid with n_rad = 1 hands every child bottom + 0 (exact) and
+                // bottom + (top - bottom) / 1, which need not be the parent's top bit for bit:
+                // the node's top is the root's after `depth` such steps (a fixed point after one
+                // or two)
+                const double* rec = a.packed + (begin + (tag & 0xffff)) * kTessRec;
+                bottom = rec[4];
+                top = rec[5];
+                for (int d = tag >> 16; d > 0; d--) {
+                    const double next = bottom + (top - bottom);
+                    if (next == top) break;
+                    top = next;
+                }
+            }
         }
         cnt -= take;
         __syncwarp();  // every pop has been read before a child is pushed over it
@@ -974,12 +1007,14 @@ __global__ void __launch_bounds__(kCoopBlock, kCoopCtasPerSm) tesseroid_coop_wal
             for (int i = 0; i < n_lon; i++)
                 for (int j = 0; j < n_lat; j++)
                     for (int r = 0; r < n_rad; r++, at++) {
-                        S.b[0][at] = w + d_lon * i;
-                        S.b[1][at] = w + d_lon * (i + 1);
-                        S.b[2][at] = s + d_lat * j;
-                        S.b[3][at] = s + d_lat * (j + 1);
-                        S.b[4][at] = bottom + d_rad * r;
-                        S.b[5][at] = bottom + d_rad * (r + 1);
+                        S.b[at] = w + d_lon * i;
+                        S.b[cap + at] = w + d_lon * (i + 1);
+                        S.b[2 * cap + at] = s + d_lat * j;
+                        S.b[3 * cap + at] = s + d_lat * (j + 1);
+                        if (radial) {
+                            S.b[4 * cap + at] = bottom + d_rad * r;
+                            S.b[5 * cap + at] = bottom + d_rad * (r + 1);
+                        }
                         S.tag[at] = child_tag;
                     }
         }

@@ -53,6 +53,10 @@ launches)
     timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
         --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu --no-also --no-north-star \
         > gpurun_out/${TAG}_launches_bench.log 2>&1; echo "launches rc=$?" ;;
+launches_tess)
+    timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv \
+        --log-file gpurun_out/${TAG}_launches_tess.csv python bench.py --workload tess_gz --steps 2 --warmup 1 --no-cpu \
+        > gpurun_out/${TAG}_launches_tess_bench.log 2>&1; echo "launches_tess rc=$?" ;;
 ncu_gz)
     ncu_case gz 'prism_kernel' "
 wl=bench.make_workload('layer_gz',37888)

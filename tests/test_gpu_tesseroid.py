@@ -277,3 +277,28 @@ def test_deep_trees(hb, variant):
             assert max_rel(got, want) <= TOL, field
     finally:
         lib.hb200_set_tesseroid_variant(default)
+
+
+@pytest.mark.parametrize("variant", [9, 6])
+def test_many_tesseroids_long_chunks(hb, variant):
+    """more than 32 768 tesseroids: the chunks of the two-kernel variants grow beyond 128 records
+    (at most 256 chunks), the lists of polar observers overflow into long remainders"""
+    lib = hb._lib.load()
+    R = MEAN_RADIUS
+    lon_c, lat_c = np.meshgrid(np.arange(-179.5, 180.0, 1.0), np.arange(-89.5, 90.0, 1.0))
+    tess = np.stack([lon_c.ravel() - 0.5, lon_c.ravel() + 0.5, lat_c.ravel() - 0.5, lat_c.ravel() + 0.5,
+                     np.full(lon_c.size, R - 20e3), np.full(lon_c.size, R - 2e3)], axis=1)
+    rng = np.random.default_rng(21)
+    density = rng.uniform(2500, 3300, lon_c.size)
+    lon = np.concatenate([rng.uniform(-180, 180, 12), [0.0, 77.0, -100.0]])
+    lat = np.concatenate([rng.uniform(-80, 80, 12), [89.8, -89.9, 89.2]])
+    coords = (lon, lat, np.full(lon.size, R + 5e3))
+    default = lib.hb200_get_tesseroid_variant()
+    try:
+        assert lib.hb200_set_tesseroid_variant(variant) == 0
+        for field in ("g_z", "potential"):
+            want = O.tesseroid_gravity(coords, tess, density, field)
+            got = hb.tesseroid_gravity(coords, tess, density, field, disable_checks=True)
+            assert max_rel(got, want) <= 2e-8, field
+    finally:
+        lib.hb200_set_tesseroid_variant(default)
