@@ -31,7 +31,13 @@
  * face rules of the magnetic kernels, the digits of choclo's mu_0. The
  * absolute values / units / signs of prism_magnetic (which the reference only
  * compares with choclo) are pinned formula-independently by a Gauss-Legendre
- * quadrature of the dipole field over the prism volume (test_oracle_pins.py).
+ * quadrature of the dipole field over the prism volume (test_oracle_pins.py);
+ * the dipole field itself has a REFERENCE-HELD pin that does not go through
+ * choclo: the reference's own ellipsoid_magnetic (numpy + scipy) for
+ * uniformly magnetised spheres, which are exactly dipoles outside
+ * (oracle/make_golden_ellipsoid.py, tests/golden/ellipsoid_sphere_magnetic.npz):
+ * agreement to 1.35e-10, all of it the digits of mu_0 (scipy's CODATA 2022
+ * value there, 4 pi 1e-7 here).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline/reference
  * arm may load this library.

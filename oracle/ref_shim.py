@@ -24,6 +24,11 @@ Modules loaded (reference file):
   harmonica._forward._tesseroid_utils src/harmonica/_forward/_tesseroid_utils.py
   harmonica._forward.tesseroid_gravity src/harmonica/_forward/tesseroid_gravity.py
       (which also pulls in _tesseroid_variable_density.py)
+  load_ellipsoids(): harmonica._forward.ellipsoids.{ellipsoids,magnetic,utils}
+      src/harmonica/_forward/ellipsoids/*.py -- NOT on the hot path and free of choclo (numpy +
+      scipy, Clark 1986 / Takahashi 2018): the external field of a uniformly magnetised SPHERE is
+      exactly a dipole's, which makes the reference's own ellipsoid code an independent check of
+      the absolute values, units and signs of dipole_magnetic (oracle/make_golden_ellipsoid.py)
 """
 
 import importlib
@@ -99,6 +104,17 @@ def load():
         "harmonica._forward._tesseroid_variable_density"
     )
     return types.SimpleNamespace(**_loaded)
+
+
+def load_ellipsoids():
+    """The reference's unmodified ellipsoid modules (ellipsoids.py, magnetic.py, utils.py)."""
+    load()
+    if "harmonica._forward.ellipsoids" not in sys.modules:
+        _pkg("harmonica._forward.ellipsoids", os.path.join(REFERENCE_SRC, "_forward", "ellipsoids"))
+    return types.SimpleNamespace(
+        ellipsoids=importlib.import_module("harmonica._forward.ellipsoids.ellipsoids"),
+        magnetic=importlib.import_module("harmonica._forward.ellipsoids.magnetic"),
+    )
 
 
 def greens_func_cartesian():

@@ -521,3 +521,19 @@ def test_layer_vertex_reuse_is_bit_identical(hb):
             assert np.array_equal(results[0], results[1], equal_nan=True), field
     finally:
         lib.hb200_set_tile_mode(default)
+
+
+def test_dipole_against_the_references_ellipsoid_code(hb):
+    """the reference's own ellipsoid_magnetic for magnetised spheres (exactly dipoles outside;
+    tests/golden/ellipsoid_sphere_magnetic.npz): a choclo-free pin of the absolute values, units
+    and signs of dipole_magnetic; mu_0 digits account for 1.35e-10"""
+    from test_oracle_pins import _sphere_moments
+
+    g = golden("ellipsoid_sphere_magnetic")
+    coords = tuple(np.ascontiguousarray(c) for c in g["coordinates"])
+    centre = tuple(np.array([c]) for c in g["centre"])
+    ratio = float(g["mu_0"]) / (4 * np.pi * 1e-7)
+    for key, moment in _sphere_moments(g).items():
+        got = np.array(hb.dipole_magnetic(coords, centre, tuple(np.array([m]) for m in moment), "b"))
+        assert max_rel(got, g[key]) < TOL
+        assert max_rel(got * ratio, g[key]) < 1e-12

@@ -9,7 +9,7 @@ import numpy.testing as npt
 import pytest
 
 import oracle as O
-from _common import GRAVITY_FIELDS, golden
+from _common import GRAVITY_FIELDS, golden, max_rel
 
 G = 6.6743e-11
 
@@ -276,3 +276,33 @@ def test_dipole_magnetic_against_prism_limit():
     moments = tuple(np.array([c * volume]) for c in magnetization)
     got = O.dipole_magnetic(obs, (np.array([0.0]), np.array([0.0]), np.array([0.0])), moments, "b")
     npt.assert_allclose([float(np.ravel(c)[0]) for c in got], want, rtol=1e-5)
+
+
+def _sphere_moments(g):
+    """dipole moments equivalent to the two magnetised spheres of the ellipsoid golden file"""
+    volume = 4.0 / 3.0 * np.pi * float(g["radius"]) ** 3
+    h0 = g["inducing_field"] * 1e-9 / float(g["mu_0"])
+    chi = float(g["susceptibility"])
+    return {"b_remanent": volume * g["remanent_mag"], "b_induced": volume * chi * h0 / (1 + chi / 3)}
+
+
+def test_dipole_against_the_references_ellipsoid_code():
+    """REFERENCE-HELD pin of dipole_magnetic that does not go through choclo: the reference's own
+    ellipsoid_magnetic (numpy + scipy; golden made by oracle/make_golden_ellipsoid.py from the
+    unmodified module) for uniformly magnetised spheres, whose external field is exactly a
+    dipole's (the reference compares the two at 5e-4, test/ellipsoids/test_magnetic.py:560-581).
+    Absolute values, nT and the signs of all three components agree to 1.4e-10; the whole
+    difference is the digits of mu_0 (scipy's CODATA-2022 value in the ellipsoid code against
+    4 pi 1e-7 here): rescaled by that ratio the two agree to rounding."""
+    g = golden("ellipsoid_sphere_magnetic")
+    coords = tuple(np.ascontiguousarray(c) for c in g["coordinates"])
+    centre = tuple(np.array([c]) for c in g["centre"])
+    ratio = float(g["mu_0"]) / (4 * np.pi * 1e-7)
+    assert abs(ratio - 1) < 2e-10
+    for key, moment in _sphere_moments(g).items():
+        got = np.array(O.dipole_magnetic(coords, centre, tuple(np.array([m]) for m in moment), "b"))
+        assert max_rel(got, g[key]) < 2e-10
+        assert max_rel(got * ratio, g[key]) < 1e-13
+        for k, field in enumerate(("b_e", "b_n", "b_u")):
+            one = O.dipole_magnetic(coords, centre, tuple(np.array([m]) for m in moment), field)
+            assert max_rel(np.asarray(one) * ratio, g[key][k]) < 1e-13
