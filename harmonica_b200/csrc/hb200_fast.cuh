@@ -41,6 +41,7 @@ template <bool XM> HB_HD double x_sqrt(double x) { return XM ? fast_sqrt_1ulp(x)
 HB_HD double log_from_z(double z, double top, double y, int m)
 {
     if (m < kLog1pMax) return log1p_nested(z, m);
+    if (m < kLogAtanhMax) return log1p_atanh(z);
     return fast_log(top * y);
 }
 
@@ -308,6 +309,9 @@ HB_HD void x_log_ratio4(const double (&top)[NQ], const double (&bot)[NQ], const 
         }
 #pragma unroll
         for (int q = 0; q < NQ; q++) out[q] = flip_by(log1p_tail(z[q], p[q]), flip[q]);
+    } else if (worst < kLogAtanhMax) {  // ratios within 1/4 of 1: no table either
+#pragma unroll
+        for (int q = 0; q < NQ; q++) out[q] = flip_by(log1p_atanh(z[q]), flip[q]);
     } else {
 #pragma unroll
         for (int q = 0; q < NQ; q++) out[q] = flip_by(fast_log(top[q] * y[q]), flip[q]);
@@ -577,6 +581,16 @@ HB_HD double accel_component(const FastCtx& c, const double* pa, const double* p
     return pa[0] * L[0] - pa[1] * L[1] + pb[0] * L[2] - pb[1] * L[3] - (px[0] * S[0] - px[1] * S[1]);
 }
 
+// build switches of two restructurings (kept to measure them against the one-batch forms)
+#ifndef HB_ACC3_BY_COMPONENT
+#define HB_ACC3_BY_COMPONENT 0  // measured: 28.8 (by component) against 31.0 G pair/s (twelve logs at once)
+#endif
+#ifndef HB_POT_BY_AXIS
+#define HB_POT_BY_AXIS 1
+#endif
+constexpr bool kAcc3ByComponent = HB_ACC3_BY_COMPONENT != 0;
+constexpr bool kPotByAxis = HB_POT_BY_AXIS != 0;
+
 // +0.0 for x == -0.0 (a shift bound - observer is -0 when the bound is -0 and the coordinate +0):
 // the sign-bit tests of the merged path must see a zero shift as non-negative
 HB_HD double plus_zero(double x) { return x == 0.0 ? 0.0 : x; }
@@ -609,6 +623,65 @@ HB_HD void prism_pair_fast(const PairGeom& g0, const double* prm, double* acc, i
         acc[0] += prm[0] * -accel_component<2, 1, 1, 2, 0, XM>(c, n, u, e);
     } else if (FS == F_N) {
         acc[0] += prm[0] * -accel_component<0, 2, 2, 0, 1, XM>(c, u, e, n);
+    } else if (FS == FS_ACC3 && XM && kAcc3ByComponent) {
+        // the three single-component evaluations on ONE shared context (shifts, squares, the
+        // eight vertex distances): four logs and one class decision at a time keep the kernel
+        // inside its registers (twelve at once: 128 registers and spills)
+        const double ve = accel_component<2, 1, 1, 2, 0, XM>(c, n, u, e);
+        const double vn = accel_component<0, 2, 2, 0, 1, XM>(c, u, e, n);
+        const double vu = accel_component<1, 0, 0, 1, 2, XM>(c, e, n, u);
+        acc[0] += prm[0] * -ve;
+        acc[1] += prm[0] * -vn;
+        acc[2] += prm[0] * -vu;
+    } else if (FS == F_POT && XM && kPotByAxis) {
+        // the potential's twelve vertex-pair logs in three batches of four (one per log type):
+        // a class decision per batch and a third of the live registers (all twelve at once
+        // spilled 100 bytes per thread)
+        double v = 0.0;
+        {
+            double top[4], bot[4], L[4];
+            unsigned flip[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) log_pair_tb<2, true>(c, q >> 1, q & 1, top[q], bot[q], flip[q]);
+            if (log_mixed<2>(c)) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) log_pair_tb<2, false>(c, q >> 1, q & 1, top[q], bot[q], flip[q]);
+            }
+            x_log_ratio4<XM, 4>(top, bot, flip, L);
+            v += e[0] * (n[0] * L[0] - n[1] * L[1]) - e[1] * (n[0] * L[2] - n[1] * L[3]);
+        }
+        {
+            double top[4], bot[4], L[4];
+            unsigned flip[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) log_pair_tb<0, true>(c, q >> 1, q & 1, top[q], bot[q], flip[q]);
+            if (log_mixed<0>(c)) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) log_pair_tb<0, false>(c, q >> 1, q & 1, top[q], bot[q], flip[q]);
+            }
+            x_log_ratio4<XM, 4>(top, bot, flip, L);
+            v += n[0] * (u[0] * L[0] - u[1] * L[1]) - n[1] * (u[0] * L[2] - u[1] * L[3]);
+        }
+        {
+            double top[4], bot[4], L[4];
+            unsigned flip[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) log_pair_tb<1, true>(c, q >> 1, q & 1, top[q], bot[q], flip[q]);
+            if (log_mixed<1>(c)) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) log_pair_tb<1, false>(c, q >> 1, q & 1, top[q], bot[q], flip[q]);
+            }
+            x_log_ratio4<XM, 4>(top, bot, flip, L);
+            v += e[0] * (u[0] * L[0] - u[1] * L[1]) - e[1] * (u[0] * L[2] - u[1] * L[3]);
+        }
+        double S[2];
+        atan_sum4_both<0, XM>(c, S);
+        v -= 0.5 * (c.se2[0] * S[0] - c.se2[1] * S[1]);
+        atan_sum4_both<1, XM>(c, S);
+        v -= 0.5 * (c.sn2[0] * S[0] - c.sn2[1] * S[1]);
+        atan_sum4_both<2, XM>(c, S);
+        v -= 0.5 * (c.su2[0] * S[0] - c.su2[1] * S[1]);
+        acc[0] += prm[0] * v;
     } else if (FS == FS_ACC3 && XM) {
         // the three single-component formulas on one shared context: second differences
         // (4-vertex groups), so the far-field log1p shortcut applies; one vote for all 12 logs

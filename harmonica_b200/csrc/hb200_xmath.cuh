@@ -200,6 +200,29 @@ HB_HD double log1p_nested(double z, int m)
     return log1p_tail(z, p);
 }
 
+// log(1 + z) for |z| < 1/4 without a table: log(1 + z) = 2 atanh(w), w = z / (2 + z), |w| < 1/7;
+// with t = 2 w:  t + t^3 (1/12 + t^2 / 80 + ...), coefficients 1 / ((2k + 1) 4^k), k = 1 .. 9
+// (the next term is below 2^-59 of the result). One division and a polynomial in t^2: no
+// exponent extraction, no table loads, no integer-to-double conversion -- the ratios of the
+// potential's vertex pairs (first differences along an axis) mostly fall in this class.
+constexpr int kLogAtanhMax = 0x3fd00000;  // 2^-2
+HB_COEF double kAtanhC[9] = {1.0 / 12.0, 1.0 / 80.0, 1.0 / 448.0, 1.0 / 2304.0, 1.0 / 11264.0,
+                             1.0 / 53248.0, 1.0 / 245760.0, 1.0 / 1114112.0, 1.0 / 4980736.0};
+HB_HD double log1p_atanh(double z)
+{
+    const double t = (z + z) * fast_rcp(2.0 + z);
+    const double u = t * t;
+    double p = fma(kAtanhC[8], u, kAtanhC[7]);
+    p = fma(p, u, kAtanhC[6]);
+    p = fma(p, u, kAtanhC[5]);
+    p = fma(p, u, kAtanhC[4]);
+    p = fma(p, u, kAtanhC[3]);
+    p = fma(p, u, kAtanhC[2]);
+    p = fma(p, u, kAtanhC[1]);
+    p = fma(p, u, kAtanhC[0]);
+    return fma(t * u, p, t);
+}
+
 // sufficient for x > 0 and |y| < x / 32 (resp. x / 512): compared on the upper words only
 // (positive doubles order like integers; subtracting 5 (9) from the exponent field divides by 32
 // (512)). Pairs that fail take the general sequence, which is valid everywhere.

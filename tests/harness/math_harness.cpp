@@ -40,7 +40,7 @@ static void pair_any(int fs, int variant, const double* o, const double* p, cons
 extern "C" {
 
 // element-wise checks of the xmath sequences: op 0 rcp, 1 sqrt, 2 log, 3 atan2(a, b),
-// 4 sqrt (1 ulp), 5 rsqrt
+// 4 sqrt (1 ulp), 5 rsqrt, 6 log1p for |a| < 1/4 (atanh form)
 void hbt_xmath(int op, int64_t n, const double* a, const double* b, double* out)
 {
     for (int64_t i = 0; i < n; i++) {
@@ -49,6 +49,7 @@ void hbt_xmath(int op, int64_t n, const double* a, const double* b, double* out)
         else if (op == 2) out[i] = fast_log(a[i]);
         else if (op == 3) out[i] = fast_atan2(a[i], b[i]);
         else if (op == 4) out[i] = fast_sqrt_1ulp(a[i]);
+        else if (op == 6) out[i] = log1p_atanh(a[i]);
         else out[i] = fast_rsqrt(a[i]);
     }
 }

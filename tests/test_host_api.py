@@ -196,3 +196,22 @@ def test_locality_order_of_tesseroid_observers():
     assert np.nanmedian(jump) < 3.0  # random order: ~100 degrees
     assert not T._already_local(lon, lat)
     assert T._already_local(lon[order], lat[order])
+
+
+def test_cartesian_locality_order():
+    """the observer ordering of the prism wrappers: None for small jobs and grids, else a
+    NaN-safe permutation that makes consecutive points neighbours"""
+    from harmonica_b200._utils import cartesian_locality_order as order_of
+
+    rng = np.random.default_rng(8)
+    e, n = rng.uniform(-5e4, 5e4, 50_000), rng.uniform(0, 2e4, 50_000)
+    assert order_of(e[:1000], n[:1000], 10**6) is None  # few observers
+    assert order_of(e, n, 100) is None  # few pairs
+    ge, gn = np.meshgrid(np.linspace(0, 1e4, 250), np.linspace(0, 1e4, 200))
+    assert order_of(ge.ravel(), gn.ravel(), 10**6) is None  # a grid is local already
+    e[3], n[5] = np.nan, np.nan
+    perm = order_of(e, n, 10**6)
+    assert np.array_equal(np.sort(perm), np.arange(e.size))
+    jump = np.abs(np.diff(e[perm])) + np.abs(np.diff(n[perm]))
+    assert np.nanmedian(jump) < 0.02 * 1.2e5
+    assert order_of(e[perm], n[perm], 10**6) is None

@@ -224,6 +224,9 @@ def test_xmath_sequences_accuracy():
     assert np.max(np.abs(lg - np.log(x)) / np.maximum(np.abs(np.log(x)), 1.0)) <= 4e-16
     near = 1 + rng.uniform(-2e-2, 2e-2, 400_000)
     assert np.max(np.abs(xm(2, near) - np.log(near))) <= 4e-18
+    quarter = rng.uniform(-0.25, 0.25, 400_000)  # the table-free mid range (atanh form)
+    want = np.log1p(quarter)
+    assert np.max(np.abs(xm(6, quarter) - want) / np.abs(want)) <= 4.5e-16
     y, x2 = rng.normal(size=400_000) * 1e8, rng.normal(size=400_000) * 1e8
     assert np.max(np.abs(xm(3, y, x2) - np.arctan2(y, x2))) <= 5e-16
     small = rng.uniform(-1e-3, 1e-3, 400_000)  # far-field regime: tiny angles keep RELATIVE accuracy
