@@ -711,7 +711,8 @@ def main():
     ap.add_argument("--tile-mode", type=int, default=-1, help="experiments: 0 per-CTA, 1 per-warp tiles")
     args = ap.parse_args()
     if args.impl == "reference":
-        args.cpu_seconds = min(args.cpu_seconds, 6.0)
+        # a bounded sample per step: the whole --steps K --warmup W run stays within ~2 minutes
+        args.cpu_seconds = max(0.5, min(args.cpu_seconds, 6.0, 120.0 / max(1, args.steps + args.warmup)))
         run_reference(args)
     else:
         run_b200(args)
