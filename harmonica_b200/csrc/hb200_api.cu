@@ -543,7 +543,7 @@ int dipole_magnetic_dev_impl(const double* oe, const double* on, const double* o
 int g_tess_variant = 9;  // 0: first build; 1: root records + deferred walks; 2: 1 + fast far field;
                          // 3: 2 + the library's own sin / cos / acos in the walks; 4, 5: register
                          // experiments; 6 (7, 8): root pass and walks as two kernels; 9: as 6 with the
-                         // walks done by groups of 8 lanes from a work list (default)
+                         // walks done by groups of 16 lanes from a work list (default)
 
 // chunking of the two-kernel variant (hb200_tess.cuh): short chunks, at most kTessMaxChunks
 int tess_two_kernel_chunks(int64_t n_src, int64_t* chunk_len)
@@ -630,7 +630,7 @@ int tesseroid_dev_impl(const double* lon, const double* lat, const double* rad, 
             a.ratio = field == F_POT ? 1.0 : 2.5;
             a.radial = radial; a.flags = d_flags;
             dim3 grid_r((unsigned)((nb + kTessRootBlock - 1) / kTessRootBlock), (unsigned)chunks);
-            const bool coop = variant >= 9;  // walks by groups of 8 lanes (tesseroid_coop_walk_kernel)
+            const bool coop = variant >= 9;  // walks by groups of 16 lanes (tesseroid_coop_walk_kernel)
             const int slices = coop ? 1 : kTessWalkSlices;
             dim3 grid_w((unsigned)((nb + kTessBlock - 1) / kTessBlock), (unsigned)chunks, kTessWalkSlices);
             const unsigned grid_c = (unsigned)(sms * kCoopCtasPerSm);  // persistent: one CTA per slot

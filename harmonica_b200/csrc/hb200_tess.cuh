@@ -824,7 +824,7 @@ __global__ void __launch_bounds__(kTessBlock) tesseroid_walk_kernel(const TessAr
 // ---- cooperative walks (kernel variant 9) --------------------------------------------------------
 // tesseroid_walk_kernel gives every (chunk, observer) list to one thread: the 32 lists of a warp
 // have very different lengths and tree shapes, and ncu counted 8 of 32 active lanes on its
-// instructions (profiles/r2_ncu_tesseroid_gz_two_kernel.txt). Here a GROUP of kCoopG = 8 lanes
+// instructions (profiles/r2_ncu_tesseroid_gz_two_kernel.txt). Here a GROUP of kCoopG = 16 lanes
 // walks one list together: the group keeps a stack of nodes (bounds + the pair they belong to)
 // in shared memory, every trip each lane pops one node, decides on it with the reference's
 // statements, and either pushes its children back (positions from a prefix sum over the group) or
@@ -832,7 +832,7 @@ __global__ void __launch_bounds__(kTessBlock) tesseroid_walk_kernel(const TessAr
 // when the list is done. The lists that hold work are compacted by the root kernel into a work
 // list; the kernel is persistent (one CTA per resident slot) and every group draws its next list
 // from a global cursor, so the few long lists (observers next to a pole) do not leave the rest of
-// the machine idle. The four groups of a warp run the same trip loop in lockstep. What changes
+// the machine idle. The two groups of a warp run the same trip loop in lockstep. What changes
 // against the reference is only the ORDER in which the leaves of a list are added; that order
 // depends on nothing but the list itself (bit-reproducible under any batching of the observers).
 //
@@ -841,11 +841,11 @@ __global__ void __launch_bounds__(kTessBlock) tesseroid_walk_kernel(const TessAr
 // unless the whole list does. A list that reaches either bound (or that would overflow the
 // group's stack) is thrown away and noted; tesseroid_redo_kernel walks it with ONE thread and the
 // exact depth-first walk of tesseroid_walk_kernel, which reports the reference's errors.
-constexpr int kCoopG = 8;        // lanes per group
-constexpr int kCoopCap = 80;     // nodes per group stack (56 with the 3-D discretisation: 6 bounds per node)
-constexpr int kCoopCapRadial = 56;
+constexpr int kCoopG = 16;       // lanes per group (measured: 4 lanes 2.4 ms, 8: 1.46, 16: 1.39, 32: 1.73 ms per batch)
+constexpr int kCoopCap = 160;    // nodes per group stack (107 with the 3-D discretisation: 6 bounds per node)
+constexpr int kCoopCapRadial = 107;
 constexpr int kCoopDeep = 13;    // a node at this depth that wants to split sends the list to the exact walk
-constexpr int kCoopBlock = 128;  // 4 warps = 16 groups
+constexpr int kCoopBlock = 128;  // 4 warps = 8 groups
 constexpr int kCoopCtasPerSm = 4;
 
 // One row per bound (lanes read neighbouring words): w e s n, and bottom top only when the radial
@@ -871,13 +871,13 @@ __global__ void __launch_bounds__(kCoopBlock, kCoopCtasPerSm) tesseroid_coop_wal
     const bool radial = a.radial != 0;
     const int spread = radial ? 7 : 3;  // net growth of the stack per node that splits, at most
     const int cap = radial ? kCoopCapRadial : kCoopCap;
-    // Eight lanes popping the top of the stack need eight times the memory of a depth-first walk
-    // (24 nodes per level). While the stack is nearly full only ONE lane pops -- a plain
+    // Sixteen lanes popping the top of the stack need sixteen times the memory of a depth-first
+    // walk (48 nodes per level). While the stack is nearly full only ONE lane pops -- a plain
     // depth-first descent, 3 nodes per level, for which `narrow` slots are kept free -- until
     // the top of the stack has drained.
     const int narrow = radial ? 14 : 18;
 
-    // group state (the same in the 8 lanes of a group, except acc / leaves / flags)
+    // group state (the same in all lanes of a group, except acc / leaves / flags)
     int phase = 0;  // 0: draw the next list; 1: walking; 2: the work list is exhausted
     int item = 0, n = 0, k = 0, resume = 0, cnt = 0, leaves = 0, chunk_cnt = 0;
     int64_t begin = 0, obs = 0;
@@ -999,7 +999,8 @@ __global__ void __launch_bounds__(kCoopBlock, kCoopCtasPerSm) tesseroid_coop_wal
         }
         const int pushed = __shfl_sync(FULL, incl, kCoopG - 1, kCoopG);
         const unsigned bad_lanes = __ballot_sync(FULL, too_deep || stuck);
-        const bool bad = ((bad_lanes >> (kCoopG * g)) & ((1u << kCoopG) - 1u)) != 0u;
+        constexpr unsigned group_mask = kCoopG == 32 ? 0xffffffffu : ((1u << (kCoopG % 32)) - 1u);
+        const bool bad = ((bad_lanes >> ((kCoopG * g) % 32)) & group_mask) != 0u;
         if (kids > 0 && !bad) {  // _split_tesseroid
             int at = cnt + incl - kids;
             const double d_lon = (e - w) / n_lon, d_lat = (nn - s) / n_lat, d_rad = (top - bottom) / n_rad;

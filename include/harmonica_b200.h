@@ -96,7 +96,7 @@ int hb200_get_variant(void);
  * bounded-angle sin / cos / acos in the walks; 4, 5 = as 3 compiled for 80 / 64 registers
  * (occupancy experiments); 6 (7, 8: other register budgets) = the far field of all pairs in one
  * kernel that lists the pairs that split, their walks in a second kernel (one thread per list);
- * 9 (default) = as 6 with the walks done by groups of 8 lanes on a shared stack, lists drawn
+ * 9 (default) = as 6 with the walks done by groups of 16 lanes on a shared stack, lists drawn
  * from a compacted work list by a persistent kernel; 0 = first build (every pair walked where
  * it is met) */
 int hb200_set_tesseroid_variant(int variant);

@@ -27,7 +27,7 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(params=[9, 6, 3, 2, 1, 0], ids=["group-walks", "two-kernel", "own-trig", "fast", "deferred", "plain"])
 def tess_variant(request, hb):
-    """the tesseroid kernels: 9 = as 6 with the walks done by groups of 8 lanes on a shared stack;
+    """the tesseroid kernels: 9 = as 6 with the walks done by groups of 16 lanes on a shared stack;
     6 = root pass and walks as two kernels; 3 = one kernel, root records
     + deferred walks + arithmetic-only far field + the library's own trig in the walks; 2 = as 3
     with CUDA's trig; 1 = without the fast far field; 0 = first build"""
