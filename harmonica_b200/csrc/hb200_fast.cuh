@@ -1,9 +1,10 @@
 // hb200_fast.cuh -- merged-transcendental evaluation of the 8-vertex prism sum.
 //
-// Valid for the pairs needs_exact_path<FS>() lets through (roughly: observer not in
-// the plane of a prism face; potential/accelerations tolerate one such axis); every
-// other pair takes prism_pair_direct, which carries the reference's singular-point
-// rules verbatim.
+// Valid for the pairs classify_pair<FS>() lets through: every pair whose observer is not
+// on (the extension of) an edge or a vertex of the prism -- ONE axis may hold a zero shift
+// (observer in the plane of a face), the reference's face rule is then applied after the
+// merged evaluation (PAIR_FAST_CHECK). Every other pair takes prism_pair_direct, which
+// carries the reference's singular-point rules verbatim.
 //
 // The reference (choclo kernels behind gravity.py:526-537 / magnetic.py:319)
 // evaluates per vertex 1-3 safe_log and 1-3 safe_atan2 and forms an
