@@ -265,22 +265,22 @@ __global__ void __launch_bounds__(kBlock, MINB) prism_kernel(const PrismArgs a)
             const double2* p = tile + s * (STRIDE / 2);
             const double2 we = p[0], sn = p[1], bt = p[2], q3 = p[3];
             double prm[3];
-            double mark;
+            int mark;  // upper word of the record's last double: 0.0, 1.0 (skip) or 2.0 (reuse)
             if (T::mag) {
                 const double2 q4 = p[4];
-                mark = q4.y;
+                mark = __double2hiint(q4.y);
                 prm[0] = q3.x; prm[1] = q3.y; prm[2] = q4.x;
             } else {
-                mark = q3.y;
+                mark = __double2hiint(q3.y);
                 prm[0] = q3.x; prm[1] = 0.0; prm[2] = 0.0;
             }
-            if (mark == 1.0) {  // warp-uniform
+            if (mark == 0x3ff00000) {  // 1.0: skip (warp-uniform)
                 if (REUSE) carry.valid = false;
                 continue;
             }
             PairGeom g;
             make_geom(g, E, N, U, we.x, we.y, sn.x, sn.y, bt.x, bt.y);
-            if (REUSE) prism_pair<FS, VARIANT>(g, prm, a.rules, acc, flags, &carry, carry.valid && mark == 2.0);
+            if (REUSE) prism_pair<FS, VARIANT>(g, prm, a.rules, acc, flags, &carry, carry.valid && mark == 0x40000000);
             else prism_pair<FS, VARIANT>(g, prm, a.rules, acc, flags);
         }
         // the buffer just read may be refilled in the next iteration
