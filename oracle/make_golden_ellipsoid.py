@@ -9,6 +9,9 @@ magnetisation M = chi H0 / (1 + chi / 3) (demagnetisation factor 1/3). The refer
 compares the two at 5e-4 (test/ellipsoids/test_magnetic.py:560-581, without the
 demagnetisation term); here the exact relation is stored.
 
+Also writes tests/golden/ellipsoid_sphere_gravity.npz (g_e, g_n, g_z of a homogeneous sphere in
+mGal from the reference's ellipsoid_gravity: a point mass outside).
+
 Writes tests/golden/ellipsoid_sphere_magnetic.npz:
   coordinates (3, n), centre (3,), radius, remanent_mag (3,), b_remanent (3, n) [nT],
   susceptibility, inducing_field (3,) [nT], b_induced (3, n) [nT], mu_0 (scipy's, which the
@@ -44,8 +47,17 @@ def main():
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         b_induced = np.array(ref.magnetic.ellipsoid_magnetic(tuple(coordinates), sphere, tuple(inducing)))
-    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden",
-                       "ellipsoid_sphere_magnetic.npz")
+    # ellipsoid_gravity (gravity.py:30-135) of a homogeneous sphere: exactly a point mass outside.
+    # Its only link to choclo is the constant G (choclo.constants.GRAVITATIONAL_CONST, here the
+    # value of oracle/choclo_numba.py), so it pins the SIGNS (g_z downward) and the mGal scaling of
+    # point_gravity's accelerations, not G.
+    density = 2670.0
+    sphere = ref.ellipsoids.Ellipsoid(radius, radius, radius, center=centre, density=density)
+    g_sphere = np.array(ref.gravity.ellipsoid_gravity(tuple(coordinates), sphere))
+    golden_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+    np.savez(os.path.join(golden_dir, "ellipsoid_sphere_gravity.npz"), coordinates=coordinates,
+             centre=np.array(centre), radius=radius, density=density, g_sphere=g_sphere)
+    out = os.path.join(golden_dir, "ellipsoid_sphere_magnetic.npz")
     np.savez(out, coordinates=coordinates, centre=np.array(centre), radius=radius, remanent_mag=remanent,
              b_remanent=b_remanent, susceptibility=chi, inducing_field=inducing, b_induced=b_induced,
              mu_0=mu_0)

@@ -114,6 +114,7 @@ def load_ellipsoids():
     return types.SimpleNamespace(
         ellipsoids=importlib.import_module("harmonica._forward.ellipsoids.ellipsoids"),
         magnetic=importlib.import_module("harmonica._forward.ellipsoids.magnetic"),
+        gravity=importlib.import_module("harmonica._forward.ellipsoids.gravity"),
     )
 
 

@@ -537,3 +537,15 @@ def test_dipole_against_the_references_ellipsoid_code(hb):
         got = np.array(hb.dipole_magnetic(coords, centre, tuple(np.array([m]) for m in moment), "b"))
         assert max_rel(got, g[key]) < TOL
         assert max_rel(got * ratio, g[key]) < 1e-12
+
+
+def test_point_accelerations_against_the_references_ellipsoid_code(hb):
+    """the reference's own ellipsoid_gravity for a homogeneous sphere (a point mass outside):
+    signs and mGal scaling of point_gravity's accelerations (tests/golden/ellipsoid_sphere_gravity.npz)"""
+    g = golden("ellipsoid_sphere_gravity")
+    coords = tuple(np.ascontiguousarray(c) for c in g["coordinates"])
+    mass = 4.0 / 3.0 * np.pi * float(g["radius"]) ** 3 * float(g["density"])
+    centre = tuple(np.array([c]) for c in g["centre"])
+    for k, field in enumerate(("g_e", "g_n", "g_z")):
+        got = hb.point_gravity(coords, centre, np.array([mass]), field)
+        assert max_rel(got, g["g_sphere"][k]) < 1e-12, field

@@ -306,3 +306,18 @@ def test_dipole_against_the_references_ellipsoid_code():
         for k, field in enumerate(("b_e", "b_n", "b_u")):
             one = O.dipole_magnetic(coords, centre, tuple(np.array([m]) for m in moment), field)
             assert max_rel(np.asarray(one) * ratio, g[key][k]) < 1e-13
+
+
+def test_point_accelerations_against_the_references_ellipsoid_code():
+    """signs (g_z downward) and mGal scaling of point_gravity's accelerations against the
+    reference's own ellipsoid_gravity (numpy + scipy, independent of the point kernels) for a
+    homogeneous sphere, which is exactly a point mass outside
+    (tests/golden/ellipsoid_sphere_gravity.npz, oracle/make_golden_ellipsoid.py). G itself is the
+    constant both sides take from choclo and is not pinned by this."""
+    g = golden("ellipsoid_sphere_gravity")
+    coords = tuple(np.ascontiguousarray(c) for c in g["coordinates"])
+    mass = 4.0 / 3.0 * np.pi * float(g["radius"]) ** 3 * float(g["density"])
+    centre = tuple(np.array([c]) for c in g["centre"])
+    for k, field in enumerate(("g_e", "g_n", "g_z")):
+        got = O.point_gravity(coords, centre, np.array([mass]), field)
+        assert max_rel(got, g["g_sphere"][k]) < 1e-14, field
