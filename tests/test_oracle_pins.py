@@ -321,3 +321,22 @@ def test_point_accelerations_against_the_references_ellipsoid_code():
     for k, field in enumerate(("g_e", "g_n", "g_z")):
         got = O.point_gravity(coords, centre, np.array([mass]), field)
         assert max_rel(got, g["g_sphere"][k]) < 1e-14, field
+
+
+def test_prism_potential_scale_against_the_references_tesseroid_code():
+    """scale, sign and units of the prism POTENTIAL (no reference test holds an absolute value of
+    it) against the reference's own tesseroid forward model (real numba code, no choclo) for a
+    0.001 x 0.001 degree x 100 m tesseroid at the equator = a 111 x 111 x 100 m prism up to the
+    curvature (1e-5) and the 0.1 % design accuracy of the tesseroid quadrature; g_z beside it
+    (tests/golden/small_tesseroid.npz, oracle/make_golden_small_tesseroid.py)"""
+    g = golden("small_tesseroid")
+    R = float(g["mean_radius"])
+    lon, lat, rad = np.radians(g["longitude"]), np.radians(g["latitude"]), g["radius"]
+    # local Cartesian frame at (0, 0, R): easting, northing, upward
+    coords = (rad * np.cos(lat) * np.sin(lon), rad * np.sin(lat), rad * np.cos(lat) * np.cos(lon) - R)
+    w, e, s, n, bottom, top = g["tesseroid"][0]
+    prism = np.array([[R * np.radians(w), R * np.radians(e), R * np.radians(s), R * np.radians(n),
+                       bottom - R, top - R]])
+    for field, bar in (("potential", 1e-3), ("g_z", 2e-3)):
+        got = O.prism_gravity(coords, prism, g["density"], field)
+        npt.assert_allclose(got, g[field], rtol=bar)
