@@ -450,8 +450,7 @@ HB_HD int tess_root_fast(const TessObs& o, const double* rec, double& acc, unsig
             for (int i = 0; i < 2; i++) {
                 const double cospsi = fma(b, coslambda[i], a);
                 const double d2 = fma(rr, 1 - cospsi, dr2);
-                if (d2 == 0.0) flags |= FLAG_ZERO_DIV;  // observer on a quadrature node
-                const double inv = fast_rsqrt(d2);
+                const double inv = fast_rsqrt(d2);  // d2 == 0: not finite, looked at below
                 if (FIELD == F_POT) {
                     result = fma(mass, inv, result);
                 } else {
@@ -462,6 +461,22 @@ HB_HD int tess_root_fast(const TessObs& o, const double* rec, double& acc, unsig
         }
     }
     acc += result;
+    if (!(fabs(result) <= 1.7976931348623157e308)) {
+        // Not finite. An observer ON a quadrature node (numba raises ZeroDivisionError on
+        // 1 / distance) makes it so; NaN input does too: tell them apart here, off the hot path
+        // (eight compares + selects per pair otherwise).
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+#pragma unroll
+            for (int k = 0; k < 2; k++)
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    const double radius_p = rec[23 + k];
+                    const double dr = o.rad - radius_p;
+                    const double cospsi = fma(rec[19 + j] * o.cphi, coslambda[i], rec[21 + j] * o.sphi);
+                    if (fma(two_r * radius_p, 1 - cospsi, dr * dr) == 0.0) flags |= FLAG_ZERO_DIV;
+                }
+    }
     return 1;
 }
 
