@@ -398,8 +398,24 @@ __global__ void __launch_bounds__(kBlock) point_kernel_cart(const PointArgs a)
             const double2 en = tile[2 * s], uw = tile[2 * s + 1];
 #pragma unroll
             for (int o = 0; o < kPointObs; o++) {
-                const double k = point_kernel<FIELD>(E[o] - en.x, N[o] - en.y, U[o] - uw.x, flags);
+                const double k = point_kernel<FIELD, false>(E[o] - en.x, N[o] - en.y, U[o] - uw.x, flags);
                 acc[o] = fma(uw.y, k, acc[o]);
+            }
+        }
+    }
+    // A zero distance (the reference's jitted loop raises ZeroDivisionError) makes 1 / distance,
+    // and with it the observer's sum, non-finite for good; so does NaN input. Only such a sum is
+    // looked into, off the hot path (two integer instructions per pair otherwise).
+    bool suspect = false;
+#pragma unroll
+    for (int o = 0; o < kPointObs; o++) suspect |= !(fabs(acc[o]) <= 1.7976931348623157e308);
+    if (suspect) {
+        for (int64_t j = begin; j < end; j++) {
+            const double2 en = src[2 * j], uw = src[2 * j + 1];
+#pragma unroll
+            for (int o = 0; o < kPointObs; o++) {
+                const double de = E[o] - en.x, dn = N[o] - en.y, du = U[o] - uw.x;
+                if (is_pos_zero(point_d2(de, dn, du))) flags |= FLAG_ZERO_DIV;
             }
         }
     }

@@ -399,11 +399,15 @@ HB_HD double point_rsqrt(double d2);  // defined in hb200_xmath.cuh (MUFU.RSQ64H
 
 // choclo.point kernels (K5) without the G*mass factor; d = observer - source.
 // returns kernel value(s); zero distance reported through flags.
-template <int FIELD>
+HB_HD double point_d2(double de, double dn, double du) { return de * de + dn * dn + du * du; }
+
+// CHECK = false: the caller looks for zero distances itself (point_kernel_cart does so only when a
+// sum came out non-finite: 1 / 0 poisons it).
+template <int FIELD, bool CHECK = true>
 HB_HD double point_kernel(double de, double dn, double du, unsigned& flags)
 {
-    const double d2 = de * de + dn * dn + du * du;
-    if (is_pos_zero(d2)) flags |= FLAG_ZERO_DIV;
+    const double d2 = point_d2(de, dn, du);
+    if (CHECK && is_pos_zero(d2)) flags |= FLAG_ZERO_DIV;
     const double inv = point_rsqrt(d2);
     if (FIELD == F_POT) return inv;
     const double inv3 = inv * inv * inv;
