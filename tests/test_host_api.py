@@ -215,3 +215,21 @@ def test_cartesian_locality_order():
     jump = np.abs(np.diff(e[perm])) + np.abs(np.diff(n[perm]))
     assert np.nanmedian(jump) < 0.02 * 1.2e5
     assert order_of(e[perm], n[perm], 10**6) is None
+
+
+def test_bench_records_are_consistent():
+    """bench.py: both arms print the same `config` object, and the committed ncu table
+    (profiles/executed_per_pair.json) belongs to the kernel sources in the tree — otherwise the
+    bench line would say "stale" instead of a roofline fraction"""
+    import argparse
+
+    import bench
+
+    wl = dict(desc="w", coords=(np.zeros(4),), n_src=7, n_eval=6)
+    args = argparse.Namespace(shard="observers", scaling="strong")
+    assert bench.config_for(wl, "layer_gz", args, 2) == bench.config_for(wl, "layer_gz", args, 2)
+    assert "gather to rank 0" in bench.config_for(wl, "layer_gz", args, 8)["sharding"]
+    for workload in ("layer_gz", "c1_gz", "tensor", "mag_b", "eqs", "tess_gz"):
+        entry, why = bench.executed_for(workload)
+        assert entry is not None, (workload, why)
+        assert entry["fp64"] > 0 and entry["other"] > 0
