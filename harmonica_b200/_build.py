@@ -13,6 +13,7 @@ HEADERS = [
     os.path.join(_HERE, "csrc", "hb200_tables.h"),
     os.path.join(_HERE, "csrc", "hb200_kernels.cuh"),
     os.path.join(_HERE, "csrc", "hb200_tess.cuh"),
+    os.path.join(_HERE, "csrc", "hb200_tess_leaves.cuh"),
     os.path.join(_HERE, "csrc", "hb200_trig.cuh"),
     os.path.join(_HERE, "csrc", "hb200_fit_kernels.cuh"),
     os.path.join(_HERE, "csrc", "hb200_fit_host.cuh"),

@@ -39,6 +39,8 @@ _u32 = ctypes.c_uint32
 _int = ctypes.c_int
 _vp = ctypes.c_void_p
 _sz = ctypes.c_size_t
+# hb200_density_fn: void (*)(const double* radius, double* density_out, int64_t n, void* user)
+DENSITY_FN = ctypes.CFUNCTYPE(None, _dp, _dp, _i64, _vp)
 
 # every symbol include/harmonica_b200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
@@ -86,6 +88,8 @@ SIGNATURES = {
         _int, [_dp, _dp, _dp, _i64, _dp, _dp, _i64, _int, _int, _int, _dp, _u32p]),
     "hb200_tesseroid_gravity_variable_density": (
         _int, [_dp, _dp, _dp, _i64, _dp, _dp, _dp, _i64, _int, _int, _dp, _u32p]),
+    "hb200_tesseroid_gravity_density_function": (
+        _int, [_dp, _dp, _dp, _i64, _dp, _dp, _dp, _i64, _int, _vp, _vp, _dp, _u32p]),
     "hb200_tesseroid_inside_scan": (_int, [_dp, _dp, _dp, _i64, _dp, _i64, _u32p]),
     "hb200_tesseroid_ws_bytes": (_sz, [_i64, _i64]),
     "hb200_tesseroid_gravity_dev": (

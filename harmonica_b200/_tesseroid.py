@@ -18,7 +18,7 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from ._tesseroid_density import density_at_radial_nodes, density_based_discretization
+from ._tesseroid_density import _evaluate, density_at_radial_nodes, density_based_discretization
 from ._utils import broadcast_coordinates, observer_chunks, progress
 
 _FIELDS = {"potential": 0, "g_z": 3}
@@ -213,12 +213,6 @@ def tesseroid_gravity(
     """
     if field not in _FIELDS:
         raise ValueError(f"Gravitational field {field} not recognized")
-    if callable(density) and radial_adaptive_discretization:
-        raise NotImplementedError(
-            "harmonica_b200.tesseroid_gravity evaluates a density function on the host, at the "
-            "radial quadrature nodes of every tesseroid; with radial_adaptive_discretization=True "
-            "the leaves have their own radial nodes, which only the CUDA kernel knows"
-        )
     shape, coords = broadcast_coordinates(coordinates)
     tesseroids = np.atleast_2d(np.asarray(tesseroids, dtype=np.float64))
     if not disable_checks:
@@ -228,6 +222,7 @@ def tesseroid_gravity(
         # tesseroid_gravity.py:182-183: radial pieces in which the density is close to linear,
         # then density(radius_p) at the two radial quadrature nodes of every piece
         tesseroids = density_based_discretization(tesseroids, density)
+        density_function = density
         density, density_upper = density_at_radial_nodes(tesseroids, density)
     else:
         density = np.atleast_1d(density).ravel()
@@ -238,6 +233,7 @@ def tesseroid_gravity(
             )
         tesseroids, density = _discard_null_tesseroids(tesseroids, density)
         density_upper = None
+        density_function = None
     tesseroids, density = _lib.f64(tesseroids), _lib.f64(density)
     lib = _lib.ensure_init()
     order = None
@@ -250,6 +246,15 @@ def tesseroid_gravity(
         density_upper = _lib.f64(density_upper)
     # tesseroid_gravity.py:191-207: the reference's bar advances per computation point from inside
     # the jitted loop; here the call is split in ~20 chunks of computation points
+    if density_upper is not None and radial_adaptive_discretization:
+        # a density function with the 3-D discretisation: the leaves have their own radial nodes,
+        # which the library reports back (in batches) for the function to be evaluated at
+        with progress(coords[0].size, progressbar) as proxy:
+            all_flags = _density_function_call(lib, coords, tesseroids, density, density_upper,
+                                               density_function, _FIELDS[field], out)
+            if proxy is not None:
+                proxy.update(coords[0].size)
+        return _finish(out, all_flags, order, dtype, shape)
     with progress(coords[0].size, progressbar) as proxy:
         for lo, hi in observer_chunks(coords[0].size, proxy):
             whole = lo == 0 and hi == coords[0].size
@@ -276,6 +281,38 @@ def tesseroid_gravity(
             all_flags |= flags.value
             if proxy is not None:
                 proxy.update(hi - lo)
+    return _finish(out, all_flags, order, dtype, shape)
+
+
+def _density_function_call(lib, coords, tesseroids, density_lower, density_upper, density_function,
+                           field_id, out):
+    """hb200_tesseroid_gravity_density_function with ``density_function`` behind a ctypes callback
+    (vectorised when the function accepts arrays); an exception inside it is re-raised here."""
+    errors = []
+
+    @_lib.DENSITY_FN
+    def callback(radius_p, density_p, n, _user):
+        values = np.ctypeslib.as_array(density_p, shape=(n,))
+        try:
+            values[:] = _evaluate(density_function, np.ctypeslib.as_array(radius_p, shape=(n,)).copy())
+        except BaseException as error:  # noqa: BLE001 - must not propagate through the C frames
+            errors.append(error)
+            values[:] = np.nan
+
+    flags = ctypes.c_uint32(0)
+    rc = lib.hb200_tesseroid_gravity_density_function(
+        _lib.ptr(coords[0]), _lib.ptr(coords[1]), _lib.ptr(coords[2]), coords[0].size,
+        _lib.ptr(tesseroids), _lib.ptr(density_lower), _lib.ptr(density_upper), tesseroids.shape[0],
+        field_id, ctypes.cast(callback, ctypes.c_void_p), None, _lib.ptr(out), ctypes.byref(flags),
+    )  # fmt: skip
+    if errors:
+        raise errors[0]
+    _lib.check(rc)
+    return flags.value
+
+
+def _finish(out, all_flags, order, dtype, shape):
+    """the reference's exceptions, the caller's order, dtype and shape"""
     flags = ctypes.c_uint32(all_flags)
     # the reference raises from inside the jitted loop: numba's float division raises on a zero
     # divisor (a computation point on a corner that 3-D discretisation splits without end, or

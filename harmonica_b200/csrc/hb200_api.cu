@@ -7,6 +7,7 @@
 // hb200_kernels.cuh, download. Device entry points (*_dev) launch the same
 // kernels on caller-owned device buffers, asynchronously on the caller's stream.
 #include <cuda_runtime.h>
+#include <cstdlib>
 
 #include <algorithm>
 #include <atomic>
@@ -21,6 +22,7 @@
 #include "../../include/harmonica_b200.h"
 #include "hb200_kernels.cuh"
 #include "hb200_tess.cuh"
+#include "hb200_tess_leaves.cuh"
 
 using namespace hb;
 
@@ -1312,6 +1314,134 @@ int hb200_tesseroid_gravity_variable_density(const double* longitude, const doub
 {
     return tesseroid_gravity_host(longitude, latitude, radius, n_obs, tesseroids, density_lower,
                                   density_upper, n_tesseroids, field, 0, shard_mode, out, flags);
+}
+
+// density function + radial discretisation: root pass, leaf collection, callback, leaf quadrature
+// (hb200_tess_leaves.cuh), in batches of computation points; device 0 of the selection
+int hb200_tesseroid_gravity_density_function(const double* longitude, const double* latitude,
+                                             const double* radius, int64_t n_obs,
+                                             const double* tesseroids, const double* density_lower,
+                                             const double* density_upper, int64_t n_tess, int field,
+                                             hb200_density_fn density, void* user, double* out,
+                                             uint32_t* flags)
+{
+    if (field != F_POT && field != F_U) return fail(HB200_EINVAL, "tesseroids: potential or g_z only");
+    if (!density) return fail(HB200_EINVAL, "density function must not be NULL");
+    std::lock_guard<std::mutex> lock(g_mu);
+    int rc = lazy_init();
+    if (rc) return rc;
+    if (flags) *flags = 0;
+    if (n_obs <= 0) return HB200_OK;
+    if (n_tess <= 0) {
+        std::fill(out, out + n_obs, 0.0);
+        return HB200_OK;
+    }
+    Dev& dev = g_devs[0];
+    CU(cudaSetDevice(dev.id));
+    cudaStream_t st = dev.st;
+    int64_t chunk_len = 0;
+    const int chunks = tess_two_kernel_chunks(n_tess, &chunk_len);
+    if (chunk_len > 65535) return fail(HB200_EINVAL, "too many tesseroids for the density-function path");
+    int64_t batch = std::min<int64_t>(n_obs, 8192);
+    int cap = (int)std::min<int64_t>(1 << 24, std::max<int64_t>(1 << 16, batch * 4096));
+    if (const char* env = std::getenv("HB200_LEAF_CAP"))  // tests: provoke the smaller-batch retry
+        cap = std::max(64, std::atoi(env));
+    const size_t need = 4 * align_up(n_obs * 8) + align_up((size_t)n_tess * 6 * 8) + 2 * align_up(n_tess * 8)
+                      + align_up((size_t)n_tess * kTessRec * 8) + align_up((size_t)(chunks + 1) * batch * 8)
+                      + align_up((size_t)chunks * kTessListCap * batch * sizeof(unsigned short))
+                      + align_up((size_t)2 * chunks * batch * sizeof(int))
+                      + align_up((size_t)cap * sizeof(int)) + align_up((size_t)6 * cap * 8)
+                      + 2 * align_up((size_t)2 * cap * 8) + align_up(4 * sizeof(int));
+    rc = dev.ensure(need + 4096);
+    if (rc) return rc;
+    double* d_lon = dev.take<double>(n_obs);
+    double* d_lat = dev.take<double>(n_obs);
+    double* d_rad = dev.take<double>(n_obs);
+    double* d_out = dev.take<double>(n_obs);
+    double* d_tess = dev.take<double>((size_t)n_tess * 6);
+    double* d_rho0 = dev.take<double>(n_tess);
+    double* d_rho1 = dev.take<double>(n_tess);
+    double* packed = dev.take<double>((size_t)n_tess * kTessRec);
+    double* parts = dev.take<double>((size_t)(chunks + 1) * batch);
+    unsigned short* list = dev.take<unsigned short>((size_t)chunks * kTessListCap * batch);
+    int* count = dev.take<int>((size_t)2 * chunks * batch);
+    LeafBuf L;
+    L.obs = dev.take<int>(cap);
+    L.bounds = dev.take<double>((size_t)6 * cap);
+    L.radii = dev.take<double>((size_t)2 * cap);
+    double* d_rho = dev.take<double>((size_t)2 * cap);
+    L.count = dev.take<int>(4);
+    L.cap = cap;
+    CU(cudaMemcpyAsync(d_lon, longitude, n_obs * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_lat, latitude, n_obs * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_rad, radius, n_obs * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_tess, tesseroids, (size_t)n_tess * 6 * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_rho0, density_lower, n_tess * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_rho1, density_upper, n_tess * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(dev.d_flags, 0, sizeof(unsigned), st));
+    const double ratio = field == F_POT ? 1.0 : 2.5;  // tesseroid_gravity.py:33
+    pack_tesseroid_fast_records_kernel<<<(unsigned)((n_tess + 127) / 128), 128, 0, st>>>(
+        d_tess, d_rho0, d_rho1, n_tess, ratio, 1, packed);
+    CU(cudaGetLastError());
+    g_launches += 1;
+    // tesseroid_gravity.py:222-225: g_z is the downward component in mGal
+    Scales sc;
+    sc.s[0] = field == F_U ? -1e5 : 1.0;
+    std::vector<double> h_radii, h_rho;
+    for (int64_t o0 = 0; o0 < n_obs;) {
+        const int64_t nb = std::min(batch, n_obs - o0);
+        TessArgs a;
+        a.lon = d_lon + o0; a.lat = d_lat + o0; a.rad = d_rad + o0; a.n_obs = nb;
+        a.packed = packed; a.n_src = n_tess; a.chunk_len = chunk_len;
+        a.out = parts; a.scale = sc.s[0]; a.ratio = ratio; a.radial = 1; a.flags = dev.d_flags;
+        dim3 grid_r((unsigned)((nb + kTessRootBlock - 1) / kTessRootBlock), (unsigned)chunks);
+        dim3 grid_w((unsigned)((nb + kTessBlock - 1) / kTessBlock), (unsigned)chunks);
+        CU(cudaMemsetAsync(L.count, 0, 4 * sizeof(int), st));
+        if (field == F_POT) tesseroid_root_kernel<F_POT, 4><<<grid_r, kTessRootBlock, 0, st>>>(a, list, count);
+        else tesseroid_root_kernel<F_U, 4><<<grid_r, kTessRootBlock, 0, st>>>(a, list, count);
+        tesseroid_collect_kernel<OwnTrig><<<grid_w, kTessBlock, 0, st>>>(a, list, count, L);
+        CU(cudaGetLastError());
+        g_launches += 2;
+        int n_leaves = 0;
+        CU(cudaMemcpyAsync(&n_leaves, L.count, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (n_leaves > cap) {  // more leaves than the buffer holds: fewer computation points per batch
+            if (nb <= 1) return fail(HB200_ENOMEM, "one computation point has more than %d leaves", cap);
+            batch = std::max<int64_t>(1, nb / 2);
+            continue;
+        }
+        double* leaf_sum = parts + (size_t)chunks * nb;
+        CU(cudaMemsetAsync(leaf_sum, 0, nb * 8, st));
+        if (n_leaves > 0) {
+            h_radii.resize((size_t)2 * n_leaves);
+            h_rho.resize((size_t)2 * n_leaves);
+            for (int k = 0; k < 2; k++)
+                CU(cudaMemcpyAsync(h_radii.data() + (size_t)k * n_leaves, L.radii + (size_t)k * cap,
+                                   (size_t)n_leaves * 8, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            density(h_radii.data(), h_rho.data(), (int64_t)2 * n_leaves, user);
+            for (int k = 0; k < 2; k++)
+                CU(cudaMemcpyAsync(d_rho + (size_t)k * cap, h_rho.data() + (size_t)k * n_leaves,
+                                   (size_t)n_leaves * 8, cudaMemcpyHostToDevice, st));
+            const unsigned blocks = (unsigned)((n_leaves + 127) / 128);
+            if (field == F_POT) tesseroid_leaf_kernel<F_POT, OwnTrig><<<blocks, 128, 0, st>>>(a, L, n_leaves, d_rho, leaf_sum);
+            else tesseroid_leaf_kernel<F_U, OwnTrig><<<blocks, 128, 0, st>>>(a, L, n_leaves, d_rho, leaf_sum);
+            CU(cudaGetLastError());
+            g_launches += 1;
+        }
+        reduce_partials_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(parts, chunks + 1, 1, nb, sc,
+                                                                             d_out + o0);
+        CU(cudaGetLastError());
+        g_launches += 1;
+        CU(cudaStreamSynchronize(st));  // h_rho is reused by the next batch
+        o0 += nb;
+    }
+    CU(cudaMemcpyAsync(out, d_out, n_obs * 8, cudaMemcpyDeviceToHost, st));
+    unsigned f = 0;
+    CU(cudaMemcpyAsync(&f, dev.d_flags, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (flags) *flags = f;
+    return HB200_OK;
 }
 
 int hb200_tesseroid_inside_scan(const double* longitude, const double* latitude,

@@ -218,6 +218,24 @@ int hb200_tesseroid_gravity_variable_density(const double* longitude, const doub
                                              int field, int shard_mode, double* out,
                                              uint32_t* flags);
 
+/* replaces jit_tesseroid_gravity_variable_density, _forward/tesseroid_gravity.py:342-445, with the
+ * 3-D (radial) adaptive discretisation: the leaves then have their own radial bounds, and the
+ * density function is wanted at the two radial quadrature nodes of EVERY leaf
+ * (_tesseroid_variable_density.py:55-58). The library walks the pairs, hands the radii of all
+ * leaves of a batch of computation points to `density` (a host function: density_out[i] =
+ * density(radius[i]), i < n; called a few times per batch from the calling thread) and integrates
+ * the leaves with the values it gets back. density_lower / density_upper are the values at the
+ * two radial nodes of every (radially pre-split) tesseroid, used for the pairs whose root does
+ * not split. Runs on the first selected device. The leaves of a computation point are added with
+ * float64 atomics (last-bit differences from run to run). */
+typedef void (*hb200_density_fn)(const double* radius, double* density_out, int64_t n, void* user);
+int hb200_tesseroid_gravity_density_function(const double* longitude, const double* latitude,
+                                             const double* radius, int64_t n_obs,
+                                             const double* tesseroids, const double* density_lower,
+                                             const double* density_upper, int64_t n_tesseroids,
+                                             int field, hb200_density_fn density, void* user,
+                                             double* out, uint32_t* flags);
+
 /* replaces _check_points_outside_tesseroids, _forward/_tesseroid_utils.py:431-454, as one
  * pass: *flags gets HB200_FLAG_TESS_INSIDE if any computation point lies strictly inside any
  * tesseroid (the host then lists the pairs for the reference's error message). */

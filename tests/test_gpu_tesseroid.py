@@ -216,8 +216,38 @@ def test_density_function_rules(hb):
     for field in ("potential", "g_z"):
         npt.assert_allclose(hb.tesseroid_gravity(grid, tesseroid, lambda radius: 2900.0, field),
                             hb.tesseroid_gravity(grid, tesseroid, 2900.0, field))  # fmt: skip
-    with pytest.raises(NotImplementedError, match="radial_adaptive_discretization"):
-        hb.tesseroid_gravity(grid, tesseroid, lambda radius: 2900.0, "g_z", radial_adaptive_discretization=True)
+    above = (lon, lat, np.full_like(lon, top + 2e3))
+    for field in ("potential", "g_z"):  # ... with the 3-D discretisation too (leaf radii through the callback)
+        npt.assert_allclose(
+            hb.tesseroid_gravity(above, tesseroid, lambda radius: 2900.0, field, radial_adaptive_discretization=True),
+            hb.tesseroid_gravity(above, tesseroid, 2900.0, field, radial_adaptive_discretization=True), rtol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["linear", "exponential"])
+def test_density_function_with_the_radial_discretisation(hb, name, monkeypatch):
+    """tesseroid_gravity.py:342-445 with radial_adaptive_discretization=True: the density function
+    is wanted at the radial nodes of every LEAF. Golden values from the unmodified reference
+    (oracle/make_golden_tesseroid_density_3d.py); also with a leaf buffer so small that the
+    library has to retry with fewer computation points per batch, and a failing function."""
+    g = golden("tesseroid_density_3d")
+    density = vd_density_functions()[name]
+    coords, tesseroids = tuple(g["coords"]), g["tesseroids"]
+    for field in ("potential", "g_z"):
+        want = g[f"{name}_{field}"]
+        got = hb.tesseroid_gravity(coords, tesseroids, density, field, radial_adaptive_discretization=True)
+        bar = max(TOL, 4 * reference_conditioning(coords, tesseroids, np.full(len(tesseroids), 2900.0), field, True))
+        assert bar <= 2e-8
+        assert max_rel(got, want) <= bar, field
+    monkeypatch.setenv("HB200_LEAF_CAP", "2000")
+    got = hb.tesseroid_gravity(coords, tesseroids, density, "g_z", radial_adaptive_discretization=True)
+    assert max_rel(got, g[f"{name}_g_z"]) <= 2e-8
+    monkeypatch.delenv("HB200_LEAF_CAP")
+
+    def broken(radius):
+        raise RuntimeError("density function failed")
+
+    with pytest.raises(RuntimeError, match="density function failed"):
+        hb.tesseroid_gravity(coords, tesseroids, broken, "g_z", radial_adaptive_discretization=True)
 
 
 @pytest.mark.parametrize("variant", [9, 6, 3])

@@ -344,9 +344,6 @@ def test_argument_errors_need_no_device():
 
     with pytest.raises(ValueError, match="Gravitational field this-field-does-not-exist not recognized"):
         hb.tesseroid_gravity([0, 0, 0], [-10, 10, -10, 10, 100, 200], 1000, "this-field-does-not-exist")
-    with pytest.raises(NotImplementedError, match="radial_adaptive_discretization"):
-        hb.tesseroid_gravity([0, 0, 300], [-10, 10, -10, 10, 100, 200], lambda r: 1000.0, "g_z",
-                             radial_adaptive_discretization=True)  # fmt: skip
     with pytest.raises(ValueError, match="The bottom radius boundary can't be greater than the top one"):
         hb.tesseroid_gravity([0.0, 0.0, 10.0], [0.0, 10.0, 0.0, 10.0, 20.0, 10.0], 100.0, "potential")
 
@@ -502,6 +499,33 @@ class _StandInLibrary:
             density_upper=self._array(rho1, n_tess))  # fmt: skip
         result[:] = got * (-1e5 if field == 3 else 1.0)
         flags._obj.value = flag_bits
+        return 0
+
+    def hb200_tesseroid_gravity_density_function(self, lon, lat, rad, n, tess, rho0, rho1, n_tess, field,
+                                                 callback, user, out, flags):
+        """answered by the oracle, with the density read through the wrapper's C callback (so the
+        marshalling of the callback is what this exercises)"""
+        from harmonica_b200 import _lib
+
+        function = ctypes.cast(callback, _lib.DENSITY_FN)
+        dp = ctypes.POINTER(ctypes.c_double)
+
+        def density(radius):
+            radii = np.atleast_1d(np.asarray(radius, dtype=np.float64)).copy()
+            values = np.empty_like(radii)
+            function(radii.ctypes.data_as(dp), values.ctypes.data_as(dp), radii.size, None)
+            return values if np.ndim(radius) else float(values[0])
+
+        tesseroids = self._array(tess, n_tess * 6).reshape(n_tess, 6)
+        bottom, top = tesseroids[:, 4], tesseroids[:, 5]
+        node = 0.5773502691896257
+        for sign, given in ((-1, self._array(rho0, n_tess)), (1, self._array(rho1, n_tess))):
+            assert np.array_equal(density(0.5 * (top - bottom) * sign * node + 0.5 * (top + bottom)), given)
+        result = np.ctypeslib.as_array(out, shape=(n,))
+        result[:] = O.tesseroid_gravity_variable_density(
+            (self._array(lon, n), self._array(lat, n), self._array(rad, n)), tesseroids, density,
+            {0: "potential", 3: "g_z"}[field], radial_adaptive_discretization=True)
+        flags._obj.value = 0
         return 0
 
     def hb200_tesseroid_inside_scan(self, lon, lat, rad, n, tess, n_tess, flags):
@@ -715,8 +739,23 @@ def test_variable_density_wrapper_with_a_stand_in_library(monkeypatch):
     for field in ("potential", "g_z"):
         npt.assert_allclose(hb.tesseroid_gravity(grid, tesseroid, lambda radius: 2900.0, field),
                             hb.tesseroid_gravity(grid, tesseroid, 2900.0, field))  # fmt: skip
-    with pytest.raises(NotImplementedError, match="radial_adaptive_discretization"):
-        hb.tesseroid_gravity(grid, tesseroid, lambda radius: 2900.0, "g_z", radial_adaptive_discretization=True)
+    # ... and with the 3-D discretisation, where the library asks for the density of every leaf
+    # through a callback (tesseroid_gravity.py:342-445)
+    above = (lon, lat, np.full_like(lon, top + 5e3))
+    for field in ("potential", "g_z"):
+        npt.assert_allclose(
+            hb.tesseroid_gravity(above, tesseroid, lambda radius: 2900.0, field, radial_adaptive_discretization=True),
+            hb.tesseroid_gravity(above, tesseroid, 2900.0, field, radial_adaptive_discretization=True), rtol=1e-12)
+    g = golden("tesseroid_density_3d")
+    got = hb.tesseroid_gravity(tuple(g["coords"]), g["tesseroids"], vd_density_functions()["linear"], "g_z",
+                               radial_adaptive_discretization=True)
+    npt.assert_allclose(got, g["linear_g_z"], rtol=1e-12)
+
+    def broken(radius):
+        raise RuntimeError("density function failed")
+
+    with pytest.raises(RuntimeError, match="density function failed"):
+        hb.tesseroid_gravity(above, tesseroid, broken, "g_z", radial_adaptive_discretization=True)
 
 
 # ------------------------------------------------------------------ own trig in the walks (variant 3)
@@ -774,3 +813,16 @@ def test_own_trig_walks_match_the_oracle(field, radial):
         want = np.asarray(want).ravel()
         bar = max(1e-9, 4 * reference_conditioning(coords, tesseroids, density, field, radial, trials=2))
         assert np.max(np.abs(got - want)) <= bar * np.max(np.abs(want))
+
+
+@pytest.mark.parametrize("name", ["linear", "exponential"])
+def test_variable_density_3d_oracle_is_bit_identical_to_the_reference(name):
+    """density function + radial_adaptive_discretization=True (tesseroid_gravity.py:342-445):
+    the oracle against the unmodified reference (tests/golden/tesseroid_density_3d.npz,
+    oracle/make_golden_tesseroid_density_3d.py)"""
+    g = golden("tesseroid_density_3d")
+    density = vd_density_functions()[name]
+    for field in ("potential", "g_z"):
+        got = O.tesseroid_gravity_variable_density(tuple(g["coords"]), g["tesseroids"], density, field,
+                                                   radial_adaptive_discretization=True)
+        assert np.array_equal(got, g[f"{name}_{field}"]), field
