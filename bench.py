@@ -594,17 +594,20 @@ def run_b200(args):
     also = []
     if world == 1 and not args.no_also and args.workload == "layer_gz" and not args.n_obs:
         for name in ("tensor", "mag_b", "eqs"):
-            w2 = make_workload(name)
-            st2 = Stepper(w2, 0, 1, "strong", "observers")
-            m2 = measure(st2, 3, 3, 0, 1, local, False, e2e_steps=2)
-            roof2 = roofline_for(name, m2["value"], fp64_peak, main["clocks"], True)
-            also.append({"name": name, "workload": w2["desc"], "value": m2["value"], "unit": "pair/s",
-                         "steps": 3, "warmup": 3, "ms_per_step": m2["ms_per_step"],
-                         "e2e": m2["e2e_value"], "gpu_launches": m2["gpu_launches"],
-                         "roofline_frac": roof2.get("frac"),
-                         "fp64_instr_per_pair": (roof2.get("executed") or {}).get("fp64_instr_per_pair"),
-                         "algorithmic_speedup_over_peak": roof2["algorithmic"]["speedup_over_peak"]})
-            del st2, w2
+            try:  # a side line must never cost the main one
+                w2 = make_workload(name)
+                st2 = Stepper(w2, 0, 1, "strong", "observers")
+                m2 = measure(st2, 3, 3, 0, 1, local, False, e2e_steps=2)
+                roof2 = roofline_for(name, m2["value"], fp64_peak, main["clocks"], True)
+                also.append({"name": name, "workload": w2["desc"], "value": m2["value"], "unit": "pair/s",
+                             "steps": 3, "warmup": 3, "ms_per_step": m2["ms_per_step"],
+                             "e2e": m2["e2e_value"], "gpu_launches": m2["gpu_launches"],
+                             "roofline_frac": roof2.get("frac"),
+                             "fp64_instr_per_pair": (roof2.get("executed") or {}).get("fp64_instr_per_pair"),
+                             "algorithmic_speedup_over_peak": roof2["algorithmic"]["speedup_over_peak"]})
+                del st2, w2
+            except Exception as error:  # noqa: BLE001
+                also.append({"name": name, "error": f"{type(error).__name__}: {error}"})
             torch.cuda.empty_cache()
 
     north_star = None
@@ -643,8 +646,12 @@ def run_b200(args):
     if rank == 0 and world == 1 and not args.no_cpu:
         nthreads = host_cores()
         for kind in cpu_kinds(wl):
-            n_sample = size_cpu_sample(wl, args.cpu_seconds, nthreads, kind)
-            rate, dt = cpu_rate(wl, n_sample, nthreads, kind)
+            try:
+                n_sample = size_cpu_sample(wl, args.cpu_seconds, nthreads, kind)
+                rate, dt = cpu_rate(wl, n_sample, nthreads, kind)
+            except Exception as error:  # noqa: BLE001 - e.g. no Numba cache directory: the C port follows
+                print(f"cpu_baseline[{kind}] failed: {type(error).__name__}: {error}", file=sys.stderr)
+                continue
             entry = {"value": rate, "unit": "pair/s", "cores": nthreads, "kind": kind,
                      "sample": f"first {n_sample} of {wl['coords'][0].size} observers x all "
                                f"{wl['n_src']} sources ({dt:.1f} s); {CPU_DESCRIPTION[kind]}"}
