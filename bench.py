@@ -348,8 +348,18 @@ def run_reference(args):
     wl = make_workload(args.workload, args.n_obs, args.n_src)
     nthreads = host_cores()
     kinds = cpu_kinds(wl)
-    kind = kinds[0]
-    n_sample = size_cpu_sample(wl, args.cpu_seconds, nthreads, kind)
+    n_sample = None
+    while kinds:  # Numba first; if it cannot run here (no compiler cache directory, ...) the C port
+        kind = kinds[0]
+        try:
+            n_sample = size_cpu_sample(wl, args.cpu_seconds, nthreads, kind)
+            break
+        except Exception as error:  # noqa: BLE001
+            print(f"reference arm: {kind} failed: {type(error).__name__}: {error}", file=sys.stderr)
+            kinds = kinds[1:]
+    if n_sample is None:
+        print(json.dumps({"impl": "reference", "unavailable": "no CPU implementation could run"}), flush=True)
+        return
     for _ in range(args.warmup):
         cpu_rate(wl, n_sample, nthreads, kind)
     t_total = 0.0
